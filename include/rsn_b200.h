@@ -1,0 +1,82 @@
+/* rsn_b200 -- C-ABI of the B200-native (sm_100a) per-ray rendering hot path of
+ * 236088/reflect-sampling-nerf.
+ *
+ * The reference is pure Python on un-vendored nerfstudio and has NO native interface of its own
+ * (SURVEY.md 2.3); each entry point below names the reference call site(s) whose eager-PyTorch work it
+ * replaces (paths relative to /root/reference/reflect_sampling_nerf/).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference adds.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer to caller-owned memory (torch-allocated in the shipped host
+ *     code); the library never allocates, frees or synchronises; work is enqueued on `stream`;
+ *   - shapes are int64_t, tensors are dense row-major unless a stride argument says otherwise;
+ *   - return value: 0 = ok, < 0 = bad argument, > 0 = cudaError_t; rsn_last_error() returns the
+ *     thread-local message of the last failing call;
+ *   - all entry points are re-entrant and CUDA-graph capturable; built with -arch=sm_100a only.
+ */
+#ifndef RSN_B200_H
+#define RSN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* rsn_stream_t; /* == cudaStream_t */
+
+/* ---- housekeeping ------------------------------------------------------------------------------ */
+int rsn_version(void);               /* 100 = 0.1.0 */
+const char* rsn_last_error(void);
+int rsn_device_ok(void);             /* 0 iff the current device is sm_100 */
+
+/* ---- K1: spaced ray sampling ---------------------------------------------------------------------
+ * Replaces UniformSampler / ReciprocalSampler.generate_ray_samples:
+ *   reflect_sampling_nerf_model.py:109,111,148,292 ; reflect_sampling_nerf_components.py:14-36.
+ * lin_bins [S+1] = torch.linspace(0,1,S+1); t_rand [N, t_rand_cols] stratification noise or NULL (eval);
+ * spacing_kind 0 = uniform, 1 = reciprocal (tan = 0.25).  Writes spacing and Euclidean bins [N,S+1].
+ * Bit-exact with the oracle. */
+int rsn_sample_spaced(const float* nears, const float* fars, const float* lin_bins, const float* t_rand,
+                      int64_t t_rand_cols, int spacing_kind, float* spacing_bins, float* euclid_bins,
+                      int64_t n_rays, int64_t n_samples, rsn_stream_t stream);
+
+/* ---- K2: PDF (importance) resampling -------------------------------------------------------------
+ * Replaces PDFSampler(include_original=False).generate_ray_samples:
+ *   reflect_sampling_nerf_model.py:110,112,182,317.
+ * weights [N,S] (row stride given), spacing_bins_in [N,S+1], u_base [S'+1] (eval: already centred),
+ * rand [N,S'+1] or NULL.  Writes new spacing / Euclidean bins [N,S'+1] and, if inds_out != NULL, the
+ * searchsorted(side="right") indices (int64) for the bit-exact index test. */
+int rsn_pdf_resample(const float* weights, int64_t weights_row_stride, const float* spacing_bins_in,
+                     const float* nears, const float* fars, const float* u_base, const float* rand,
+                     int spacing_kind, float histogram_padding, float* spacing_bins_out,
+                     float* euclid_bins_out, int64_t* inds_out, int64_t n_rays, int64_t n_in_samples,
+                     int64_t n_out_samples, rsn_stream_t stream);
+
+/* ---- K8: alpha compositing ------------------------------------------------------------------------
+ * Replaces RaySamples.get_weights + Accumulation / RGB / Depth(median) / Normals / Semantic renderers:
+ *   reflect_sampling_nerf_model.py:154-156,176,188-190,210,215-226,296,311,322,337,341.
+ * sigma [N,S]; starts/ends point at element [0] of the per-ray start / end arrays with a common row
+ * stride (pass bins and bins+1 with stride S+1 to composite straight from a bins array);
+ * feat [N,S,C] per-sample channels, C in {0,1,3,4,8,16}.  Outputs: weights [N,S], accumulation [N],
+ * depth_median [N], feat_out [N,C] = sum_s w*feat (background blending is the caller's per-ray op). */
+int rsn_composite_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
+                      const float* feat, int64_t n_channels, float* weights, float* accumulation,
+                      float* depth_median, float* feat_out, int64_t n_rays, int64_t n_samples,
+                      rsn_stream_t stream);
+/* Backward of the above w.r.t. sigma and feat.  grad_weights [N,S], grad_accumulation [N],
+ * grad_feat_out [N,C] may each be NULL (= zero).  grad_feat may be NULL (not needed). */
+int rsn_composite_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
+                      const float* feat, int64_t n_channels, const float* grad_weights,
+                      const float* grad_accumulation, const float* grad_feat_out, float* grad_sigma,
+                      float* grad_feat, int64_t n_rays, int64_t n_samples, rsn_stream_t stream);
+
+/* ---- tcgen05 building-block probes (unit tests of csrc/umma.cuh) ---------------------------------- */
+int rsn_probe_umma_kmajor(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks,
+                          int64_t n_split, float* out, rsn_stream_t stream);
+int rsn_probe_umma_mnmajor(const void* u_blocks, const void* v_blocks, int64_t m_blocks, int64_t n_blocks,
+                           float* out, rsn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSN_B200_H */

@@ -1,0 +1,278 @@
+// K8: per-ray alpha compositing, forward and backward -- SURVEY.md §2.4, §8 rows a13/a14.
+//
+// Replaces (arithmetic restated in oracle/upstream.py):
+//   RaySamples.get_weights           reflect_sampling_nerf_model.py:154,188,296,322
+//   Accumulation/RGB/Depth(median)/Normals/Semantic renderers
+//                                    reflect_sampling_nerf_model.py:155-156,176,189-190,210,215-226,311,337,341
+//
+// One warp per ray.  Lane l owns K consecutive samples [l*K, l*K+K) of a 32*K-sample round, so its
+// loads are contiguous (float4 when the row allows it) and the transmittance scan is a K-step local
+// prefix plus ONE 5-step warp scan of lane totals per round.  The running optical depth and the
+// running weight sum (for the median) are carried in fp64: the reference's CPU cumsum accumulates in
+// double, and exp(-tau) amplifies an fp32 scan error beyond the 1e-5 relative weight tolerance.
+//
+// HBM-bound.  Algorithmic bytes, forward: sigma 4 + start 4 + end 4 + C*4 feature in, weight 4 out per
+// sample (28 B for C = 3) + (C + 2)*4 B out per ray.  Backward: those inputs again + 4 (dL/dw) in,
+// 4 (dL/dsigma) + C*4 (dL/dfeat) out per sample.
+#include "rsn_common.cuh"
+#include <algorithm>
+
+namespace {
+
+template <int K>
+struct Round {
+  float dd[K], w[K];
+};
+
+// Shared forward math for one 32*K-sample round.  Returns weights in w[], updates carries.
+template <int K>
+__device__ __forceinline__ void weights_round(const float* __restrict__ sigma, const float* __restrict__ starts,
+                                              const float* __restrict__ ends, int base, int S, int lane,
+                                              double& tau_carry, float (&dd)[K], float (&w)[K],
+                                              float (&t_next)[K]) {
+  const int s0 = base + lane * K;
+  double local = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int s = s0 + k;
+    float v = 0.f;
+    if (s < S) v = (__ldg(ends + s) - __ldg(starts + s)) * __ldg(sigma + s);
+    dd[k] = v;
+    local += (double)v;
+  }
+  const double incl = warp_incl_scan(local, lane);
+  double tau = tau_carry + (incl - local);  // optical depth in front of this lane's first sample
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float T = expf(-(float)tau);
+    const float alpha = 1.f - expf(-dd[k]);
+    w[k] = (s0 + k < S) ? nan_to_num(alpha * T) : 0.f;
+    tau += (double)dd[k];
+    t_next[k] = expf(-(float)tau);  // transmittance behind sample k (= d w_k / d dd_k)
+  }
+  tau_carry += __shfl_sync(RSN_FULL, incl, 31);
+}
+
+template <int K, int C>
+__global__ void __launch_bounds__(256) composite_fwd_kernel(
+    const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
+    int64_t bin_stride, const float* __restrict__ feat, float* __restrict__ weights, float* __restrict__ acc_out,
+    float* __restrict__ depth_out, float* __restrict__ feat_out, int64_t n_rays, int S) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rays; r += nwarps) {
+    const float* sg = sigma + r * S;
+    const float* st = starts + r * bin_stride;
+    const float* en = ends + r * bin_stride;
+    double tau_carry = 0.0, cw_carry = 0.0;
+    float fsum[C > 0 ? C : 1];
+#pragma unroll
+    for (int c = 0; c < (C > 0 ? C : 1); ++c) fsum[c] = 0.f;
+    float acc = 0.f;
+    int median = S;  // searchsorted(cumsum(w), 0.5, side="left")
+    for (int base = 0; base < S; base += 32 * K) {
+      float dd[K], w[K], tn[K];
+      weights_round<K>(sg, st, en, base, S, lane, tau_carry, dd, w, tn);
+      const int s0 = base + lane * K;
+      double local = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (s0 + k < S) {
+          weights[r * S + s0 + k] = w[k];
+          acc += w[k];
+          if (C > 0) {
+            const float* f = feat + ((int64_t)r * S + s0 + k) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) fsum[c] += w[k] * __ldg(f + c);
+          }
+        }
+        local += (double)w[k];
+      }
+      // median: first sample whose inclusive cumulative weight reaches 0.5
+      const double incl = warp_incl_scan(local, lane);
+      double cw = cw_carry + (incl - local);
+      int mine = S;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        cw += (double)w[k];
+        if (mine == S && s0 + k < S && (float)cw >= 0.5f) mine = s0 + k;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(RSN_FULL, mine, o));
+      median = min(median, mine);
+      cw_carry += __shfl_sync(RSN_FULL, incl, 31);
+    }
+    acc = warp_sum(acc);
+#pragma unroll
+    for (int c = 0; c < (C > 0 ? C : 1); ++c) fsum[c] = warp_sum(fsum[c]);
+    if (lane == 0) {
+      acc_out[r] = acc;
+      const int mi = min(median, S - 1);
+      depth_out[r] = (__ldg(st + mi) + __ldg(en + mi)) / 2.f;
+      if (C > 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) feat_out[r * C + c] = fsum[c];
+      }
+    }
+  }
+}
+
+// Backward.  gw_s = dL/dw_s (explicit) + dL/dacc + sum_c dL/dfeat_out_c * feat_{s,c}
+//            dL/d(dd_j) = gw_j * T_{j+1} - sum_{s>j} gw_s * w_s ;  dL/dsigma_j = dL/d(dd_j) * delta_j
+// The suffix sum is total - inclusive prefix, so a first pass accumulates total = sum_s gw_s w_s.
+template <int K, int C>
+__global__ void __launch_bounds__(256) composite_bwd_kernel(
+    const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
+    int64_t bin_stride, const float* __restrict__ feat, const float* __restrict__ g_weights,
+    const float* __restrict__ g_acc, const float* __restrict__ g_feat_out, float* __restrict__ g_sigma,
+    float* __restrict__ g_feat, int64_t n_rays, int S) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rays; r += nwarps) {
+    const float* sg = sigma + r * S;
+    const float* st = starts + r * bin_stride;
+    const float* en = ends + r * bin_stride;
+    const float ga = g_acc ? __ldg(g_acc + r) : 0.f;
+    float go[C > 0 ? C : 1];
+#pragma unroll
+    for (int c = 0; c < (C > 0 ? C : 1); ++c) go[c] = (C > 0 && g_feat_out) ? __ldg(g_feat_out + r * C + c) : 0.f;
+
+    // pass 1: total = sum_s gw_s * w_s
+    double tau_carry = 0.0;
+    double total = 0.0;
+    for (int base = 0; base < S; base += 32 * K) {
+      float dd[K], w[K], tn[K];
+      weights_round<K>(sg, st, en, base, S, lane, tau_carry, dd, w, tn);
+      const int s0 = base + lane * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (s0 + k < S) {
+          float gw = ga + (g_weights ? __ldg(g_weights + r * S + s0 + k) : 0.f);
+          if (C > 0) {
+            const float* f = feat + ((int64_t)r * S + s0 + k) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) gw += go[c] * __ldg(f + c);
+          }
+          total += (double)(gw * w[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(RSN_FULL, total, o);
+
+    // pass 2: gradients
+    tau_carry = 0.0;
+    double pre_carry = 0.0;
+    for (int base = 0; base < S; base += 32 * K) {
+      float dd[K], w[K], tn[K], gw[K];
+      weights_round<K>(sg, st, en, base, S, lane, tau_carry, dd, w, tn);
+      const int s0 = base + lane * K;
+      double local = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        gw[k] = 0.f;
+        if (s0 + k < S) {
+          float g = ga + (g_weights ? __ldg(g_weights + r * S + s0 + k) : 0.f);
+          if (C > 0) {
+            const float* f = feat + ((int64_t)r * S + s0 + k) * C;
+            float* gf = g_feat ? g_feat + ((int64_t)r * S + s0 + k) * C : nullptr;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              g += go[c] * __ldg(f + c);
+              if (gf) gf[c] = go[c] * w[k];
+            }
+          }
+          gw[k] = g;
+        }
+        local += (double)(gw[k] * w[k]);
+      }
+      const double incl = warp_incl_scan(local, lane);
+      double pre = pre_carry + (incl - local);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        pre += (double)(gw[k] * w[k]);  // inclusive prefix through sample k
+        if (s0 + k < S) {
+          const float delta = __ldg(en + s0 + k) - __ldg(st + s0 + k);
+          const float gdd = gw[k] * tn[k] - (float)(total - pre);
+          g_sigma[r * S + s0 + k] = gdd * delta;
+        }
+      }
+      pre_carry += __shfl_sync(RSN_FULL, incl, 31);
+    }
+  }
+}
+
+template <int C>
+int launch_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_stride, const float* feat,
+               float* weights, float* acc, float* depth, float* feat_out, int64_t n_rays, int S,
+               cudaStream_t stream) {
+  const int threads = 256;
+  int64_t want = (n_rays * 32 + threads - 1) / threads;
+  int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
+#define RSN_FWD(K)                                                                                        \
+  composite_fwd_kernel<K, C><<<blocks, threads, 0, stream>>>(sigma, starts, ends, bin_stride, feat, weights, \
+                                                             acc, depth, feat_out, n_rays, S)
+  if (S <= 32) RSN_FWD(1);
+  else if (S <= 64) RSN_FWD(2);
+  else RSN_FWD(4);
+#undef RSN_FWD
+  RSN_LAUNCH_CHECK("composite_fwd_kernel");
+  return 0;
+}
+
+template <int C>
+int launch_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_stride, const float* feat,
+               const float* g_weights, const float* g_acc, const float* g_feat_out, float* g_sigma, float* g_feat,
+               int64_t n_rays, int S, cudaStream_t stream) {
+  const int threads = 256;
+  int64_t want = (n_rays * 32 + threads - 1) / threads;
+  int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
+#define RSN_BWD(K)                                                                                          \
+  composite_bwd_kernel<K, C><<<blocks, threads, 0, stream>>>(sigma, starts, ends, bin_stride, feat, g_weights, \
+                                                             g_acc, g_feat_out, g_sigma, g_feat, n_rays, S)
+  if (S <= 32) RSN_BWD(1);
+  else if (S <= 64) RSN_BWD(2);
+  else RSN_BWD(4);
+#undef RSN_BWD
+  RSN_LAUNCH_CHECK("composite_bwd_kernel");
+  return 0;
+}
+
+}  // namespace
+
+#define RSN_DISPATCH_C(FN, ...)                \
+  switch (n_channels) {                        \
+    case 0: return FN<0>(__VA_ARGS__);         \
+    case 1: return FN<1>(__VA_ARGS__);         \
+    case 3: return FN<3>(__VA_ARGS__);         \
+    case 4: return FN<4>(__VA_ARGS__);         \
+    case 8: return FN<8>(__VA_ARGS__);         \
+    case 16: return FN<16>(__VA_ARGS__);       \
+    default: return rsn_fail(-1, "rsn_composite: n_channels must be one of 0,1,3,4,8,16 (got %d)", (int)n_channels); \
+  }
+
+extern "C" int rsn_composite_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
+                                 const float* feat, int64_t n_channels, float* weights, float* accumulation,
+                                 float* depth_median, float* feat_out, int64_t n_rays, int64_t n_samples,
+                                 cudaStream_t stream) {
+  RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_composite_fwd: bad shape");
+  if (n_rays == 0) return 0;
+  RSN_ARG(sigma && starts && ends && weights && accumulation && depth_median, "rsn_composite_fwd: null pointer");
+  RSN_ARG(n_channels == 0 || (feat && feat_out), "rsn_composite_fwd: feat/feat_out required when n_channels > 0");
+  RSN_DISPATCH_C(launch_fwd, sigma, starts, ends, bin_row_stride, feat, weights, accumulation, depth_median,
+                 feat_out, n_rays, (int)n_samples, stream);
+}
+
+extern "C" int rsn_composite_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
+                                 const float* feat, int64_t n_channels, const float* grad_weights,
+                                 const float* grad_accumulation, const float* grad_feat_out, float* grad_sigma,
+                                 float* grad_feat, int64_t n_rays, int64_t n_samples, cudaStream_t stream) {
+  RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_composite_bwd: bad shape");
+  if (n_rays == 0) return 0;
+  RSN_ARG(sigma && starts && ends && grad_sigma, "rsn_composite_bwd: null pointer");
+  RSN_ARG(n_channels == 0 || feat, "rsn_composite_bwd: feat required when n_channels > 0");
+  RSN_DISPATCH_C(launch_bwd, sigma, starts, ends, bin_row_stride, feat, grad_weights, grad_accumulation,
+                 grad_feat_out, grad_sigma, grad_feat, n_rays, (int)n_samples, stream);
+}

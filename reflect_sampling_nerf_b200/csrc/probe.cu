@@ -1,0 +1,163 @@
+// Unit probes for the tcgen05 building blocks in umma.cuh.  They are exported through the C-ABI and
+// exercised by tests/test_umma_probe.py so that a descriptor / swizzle / TMEM-mapping mistake shows up in
+// a 128-row single-tile GEMM rather than inside the fused field kernels.
+//
+//   rsn_probe_umma_kmajor : D[128,N]  = X[128,K] * W[N,K]^T     (forward / dgrad operand form)
+//   rsn_probe_umma_mnmajor: D[M,N]    = U[128,M]^T * V[128,N]   (wgrad operand form; K = 128 points)
+// Operands arrive as pre-swizzled block images (umma::block_off) exactly as the field kernels stage them.
+#include "rsn_common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+__global__ void __launch_bounds__(160, 1) probe_kmajor_kernel(const uint8_t* __restrict__ x_blocks,
+                                                              const uint8_t* __restrict__ w_blocks, int N, int KB,
+                                                              int n_split, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* sx = smem;
+  uint8_t* sw = smem + (size_t)KB * 16384;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_block_bytes = (uint32_t)N * 128u;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(&bar_load, 1);
+      mbar_init(&bar_mma, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == 4 && lane == 0) {
+    mbar_expect_tx(&bar_load, (uint32_t)KB * (16384u + w_block_bytes));
+    for (int kb = 0; kb < KB; ++kb) {
+      bulk_g2s(sx + (size_t)kb * 16384, x_blocks + (size_t)kb * 16384, 16384, &bar_load);
+      bulk_g2s(sw + (size_t)kb * w_block_bytes, w_blocks + (size_t)kb * w_block_bytes, w_block_bytes, &bar_load);
+    }
+    mbar_wait(&bar_load, 0);
+    tc_fence_after();
+    const int n_inst = N / n_split;
+    const uint32_t idesc = instr_desc_bf16(128, n_inst, 0, 0);
+    for (int h = 0; h < n_split; ++h) {
+      for (int kb = 0; kb < KB; ++kb) {
+        for (int k = 0; k < 4; ++k) {
+          uint64_t da = smem_desc_sw128(smem_u32(sx + (size_t)kb * 16384) + k * 32, 16, 1024);
+          uint64_t db = smem_desc_sw128(smem_u32(sw + (size_t)kb * w_block_bytes) + h * n_inst * 128 + k * 32, 16, 1024);
+          mma_bf16_ss(tmem + h * n_inst, da, db, idesc, (kb | k) != 0);
+        }
+      }
+    }
+    mma_commit(&bar_mma);
+  }
+  if (warp < 4) {
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) out[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+__global__ void __launch_bounds__(160, 1) probe_mnmajor_kernel(const uint8_t* __restrict__ u_blocks,
+                                                               const uint8_t* __restrict__ v_blocks, int MB, int NB,
+                                                               float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* su = smem;
+  uint8_t* sv = smem + (size_t)MB * 16384;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = MB * 64, N = NB * 64;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(&bar_load, 1);
+      mbar_init(&bar_mma, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == 4 && lane == 0) {
+    mbar_expect_tx(&bar_load, (uint32_t)(MB + NB) * 16384u);
+    for (int b = 0; b < MB; ++b) bulk_g2s(su + (size_t)b * 16384, u_blocks + (size_t)b * 16384, 16384, &bar_load);
+    for (int b = 0; b < NB; ++b) bulk_g2s(sv + (size_t)b * 16384, v_blocks + (size_t)b * 16384, 16384, &bar_load);
+    mbar_wait(&bar_load, 0);
+    tc_fence_after();
+    const uint32_t idesc = instr_desc_bf16(M, N, 1, 1);
+    for (int k = 0; k < 8; ++k) {  // 16 points (= 2 swizzle atoms of 8 rows) per instruction
+      uint64_t da = smem_desc_sw128(smem_u32(su) + k * 2048, 16384, 1024);
+      uint64_t db = smem_desc_sw128(smem_u32(sv) + k * 2048, 16384, 1024);
+      mma_bf16_ss(tmem, da, db, idesc, k != 0);
+    }
+    mma_commit(&bar_mma);
+  }
+  if (warp < 4) {
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+extern "C" int rsn_probe_umma_kmajor(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks,
+                                     int64_t n_split, float* out, cudaStream_t stream) {
+  RSN_ARG(n_out >= 16 && n_out <= 256 && n_out % 16 == 0, "rsn_probe_umma_kmajor: n_out in [16,256], multiple of 16");
+  RSN_ARG(k_blocks >= 1 && k_blocks <= 4, "rsn_probe_umma_kmajor: k_blocks in [1,4]");
+  RSN_ARG(n_split == 1 || (n_split == 2 && n_out % 32 == 0), "rsn_probe_umma_kmajor: n_split 1 or 2");
+  size_t smem = (size_t)k_blocks * (16384 + n_out * 128) + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_kmajor_kernel<<<1, 160, smem, stream>>>((const uint8_t*)x_blocks, (const uint8_t*)w_blocks, (int)n_out,
+                                                (int)k_blocks, (int)n_split, out);
+  RSN_LAUNCH_CHECK("probe_kmajor_kernel");
+  return 0;
+}
+
+extern "C" int rsn_probe_umma_mnmajor(const void* u_blocks, const void* v_blocks, int64_t m_blocks, int64_t n_blocks,
+                                      float* out, cudaStream_t stream) {
+  RSN_ARG(m_blocks == 2, "rsn_probe_umma_mnmajor: m_blocks must be 2 (M = 128)");
+  RSN_ARG(n_blocks >= 1 && n_blocks <= 4, "rsn_probe_umma_mnmajor: n_blocks in [1,4]");
+  size_t smem = (size_t)(m_blocks + n_blocks) * 16384 + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_mnmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_mnmajor_kernel<<<1, 160, smem, stream>>>((const uint8_t*)u_blocks, (const uint8_t*)v_blocks, (int)m_blocks,
+                                                 (int)n_blocks, out);
+  RSN_LAUNCH_CHECK("probe_mnmajor_kernel");
+  return 0;
+}

@@ -1,0 +1,165 @@
+// K1 (spaced sampling) and K2 (PDF resampling) -- SURVEY.md §2.4, §8 rows a2-a4.
+//
+// Replaces (reference call sites; arithmetic restated in oracle/upstream.py):
+//   UniformSampler / ReciprocalSampler  reflect_sampling_nerf_model.py:109,111,148,292
+//                                        reflect_sampling_nerf_components.py:14-36
+//   PDFSampler(include_original=False)   reflect_sampling_nerf_model.py:110,112,182,317
+//
+// These kernels are "bit-exact" targets: every fp32 operation is issued with an explicit
+// round-to-nearest intrinsic so nvcc cannot contract a*b+c into an FMA, and the operation order is
+// the oracle's.  The per-ray sum and the CDF cumsum accumulate in fp64 and round once per output
+// (oracle/upstream.py, SUM_MODE == "fp64"; torch's CPU cumsum already behaves that way).
+#include "rsn_common.cuh"
+#include <algorithm>
+
+namespace {
+
+__device__ __forceinline__ float spacing_fn(float x, int kind) {
+  // kind 1: x / (1/tan + x), tan = 0.25 -> 1/tan = 4.0 exactly
+  return kind == 0 ? x : __fdiv_rn(x, __fadd_rn(4.0f, x));
+}
+__device__ __forceinline__ float spacing_inv(float x, int kind) {
+  // kind 1: x / tan / (1 - x)
+  return kind == 0 ? x : __fdiv_rn(__fdiv_rn(x, 0.25f), __fsub_rn(1.0f, x));
+}
+__device__ __forceinline__ float to_euclid(float b, float s_near, float s_far, int kind) {
+  // x * s_far + (1 - x) * s_near, each op rounded separately
+  float v = __fadd_rn(__fmul_rn(b, s_far), __fmul_rn(__fsub_rn(1.0f, b), s_near));
+  return spacing_inv(v, kind);
+}
+
+// One thread per bin.  HBM-bound: 8 B written per bin (+4 B read when jitter is injected).
+__global__ void __launch_bounds__(256) sample_spaced_kernel(
+    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ lin,
+    const float* __restrict__ t_rand, int64_t t_rand_cols, int kind, float* __restrict__ spacing,
+    float* __restrict__ euclid, int64_t n_rays, int n_bins) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = n_rays * n_bins;
+  for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / n_bins;
+    int i = (int)(idx - r * n_bins);
+    float b = __ldg(lin + i);
+    if (t_rand != nullptr) {
+      float t = __ldg(t_rand + r * t_rand_cols + (t_rand_cols == 1 ? 0 : i));
+      float lower = i == 0 ? b : __fdiv_rn(__fadd_rn(b, __ldg(lin + i - 1)), 2.0f);
+      float upper = i == n_bins - 1 ? b : __fdiv_rn(__fadd_rn(__ldg(lin + i + 1), b), 2.0f);
+      b = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t));
+    }
+    float s_near = spacing_fn(__ldg(nears + r), kind);
+    float s_far = spacing_fn(__ldg(fars + r), kind);
+    spacing[idx] = b;
+    euclid[idx] = to_euclid(b, s_near, s_far, kind);
+  }
+}
+
+// One warp per ray.  smem: cdf[S+1] and the existing spacing bins[S+1] per warp.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) pdf_resample_kernel(
+    const float* __restrict__ weights, int64_t w_stride, const float* __restrict__ bins_in,
+    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ u_base,
+    const float* __restrict__ rand, int kind, float hist_pad, float* __restrict__ spacing_out,
+    float* __restrict__ euclid_out, int64_t* __restrict__ inds_out, int64_t n_rays, int S, int nb) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* cdf = smem + (size_t)warp * 2 * (S + 1);
+  float* ebins = cdf + (S + 1);
+  const int chunk = (S + 31) / 32;  // consecutive samples per lane
+
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < n_rays; r += (int64_t)gridDim.x * WARPS) {
+    const float* w = weights + r * w_stride;
+    const int lo = lane * chunk, hi = min(S, lo + chunk);
+    // weights + histogram_padding, row sum in fp64
+    double part = 0.0;
+    for (int i = lo; i < hi; ++i) part += (double)__fadd_rn(__ldg(w + i), hist_pad);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(RSN_FULL, part, o);
+    float wsum = (float)part;
+    float padding = fmaxf(__fsub_rn(1e-5f, wsum), 0.0f);  // relu(eps - sum)
+    float pad_each = __fdiv_rn(padding, (float)S);
+    wsum = __fadd_rn(wsum, padding);
+    // pdf and its inclusive cumsum (fp64 accumulate, rounded per element), clamped at 1
+    double run = 0.0;
+    for (int i = lo; i < hi; ++i) {
+      float wi = __fadd_rn(__fadd_rn(__ldg(w + i), hist_pad), pad_each);
+      run += (double)__fdiv_rn(wi, wsum);
+    }
+    double incl = warp_incl_scan(run, lane);
+    double acc = incl - run;  // exclusive offset of this lane's chunk
+    for (int i = lo; i < hi; ++i) {
+      float wi = __fadd_rn(__fadd_rn(__ldg(w + i), hist_pad), pad_each);
+      acc += (double)__fdiv_rn(wi, wsum);
+      cdf[i + 1] = fminf(1.0f, (float)acc);
+    }
+    if (lane == 0) cdf[0] = 0.0f;
+    for (int i = lane; i <= S; i += 32) ebins[i] = __ldg(bins_in + r * (S + 1) + i);
+    __syncwarp();
+
+    const float s_near = spacing_fn(__ldg(nears + r), kind);
+    const float s_far = spacing_fn(__ldg(fars + r), kind);
+    for (int j = lane; j < nb; j += 32) {
+      float u = __ldg(u_base + j);
+      if (rand != nullptr) u = __fadd_rn(u, __fdiv_rn(__ldg(rand + r * nb + j), (float)nb));
+      // searchsorted(cdf, u, side="right"): number of entries <= u
+      int a = 0, b = S + 1;
+      while (a < b) {
+        int m = (a + b) >> 1;
+        if (cdf[m] <= u) a = m + 1; else b = m;
+      }
+      const int below = min(max(a - 1, 0), S), above = min(max(a, 0), S);
+      const float c0 = cdf[below], c1 = cdf[above], b0 = ebins[below], b1 = ebins[above];
+      float t = nan_to_num(__fdiv_rn(__fsub_rn(u, c0), __fsub_rn(c1, c0)));
+      t = fminf(fmaxf(t, 0.0f), 1.0f);
+      const float nbv = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+      spacing_out[r * nb + j] = nbv;
+      euclid_out[r * nb + j] = to_euclid(nbv, s_near, s_far, kind);
+      if (inds_out != nullptr) inds_out[r * nb + j] = a;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+extern "C" int rsn_sample_spaced(const float* nears, const float* fars, const float* lin_bins,
+                                 const float* t_rand, int64_t t_rand_cols, int spacing_kind,
+                                 float* spacing_bins, float* euclid_bins, int64_t n_rays,
+                                 int64_t n_samples, cudaStream_t stream) {
+  RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_sample_spaced: bad shape (%lld rays, %lld samples)",
+          (long long)n_rays, (long long)n_samples);
+  RSN_ARG(spacing_kind == 0 || spacing_kind == 1, "rsn_sample_spaced: spacing_kind must be 0 (uniform) or 1 (reciprocal)");
+  RSN_ARG(t_rand == nullptr || t_rand_cols == 1 || t_rand_cols == n_samples + 1,
+          "rsn_sample_spaced: t_rand must have 1 or n_samples+1 columns");
+  if (n_rays == 0) return 0;
+  RSN_ARG(nears && fars && lin_bins && spacing_bins && euclid_bins, "rsn_sample_spaced: null pointer");
+  const int n_bins = (int)n_samples + 1;
+  int64_t total = n_rays * n_bins;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)rsn_num_sms() * 8);
+  sample_spaced_kernel<<<blocks, 256, 0, stream>>>(nears, fars, lin_bins, t_rand, t_rand_cols, spacing_kind,
+                                                    spacing_bins, euclid_bins, n_rays, n_bins);
+  RSN_LAUNCH_CHECK("sample_spaced_kernel");
+  return 0;
+}
+
+extern "C" int rsn_pdf_resample(const float* weights, int64_t weights_row_stride, const float* spacing_bins_in,
+                                const float* nears, const float* fars, const float* u_base, const float* rand,
+                                int spacing_kind, float histogram_padding, float* spacing_bins_out,
+                                float* euclid_bins_out, int64_t* inds_out, int64_t n_rays, int64_t n_in_samples,
+                                int64_t n_out_samples, cudaStream_t stream) {
+  RSN_ARG(n_rays >= 0 && n_in_samples >= 1 && n_out_samples >= 1, "rsn_pdf_resample: bad shape");
+  RSN_ARG(n_in_samples <= 4096, "rsn_pdf_resample: at most 4096 input samples per ray (got %lld)", (long long)n_in_samples);
+  RSN_ARG(spacing_kind == 0 || spacing_kind == 1, "rsn_pdf_resample: spacing_kind must be 0 or 1");
+  if (n_rays == 0) return 0;
+  RSN_ARG(weights && spacing_bins_in && nears && fars && u_base && spacing_bins_out && euclid_bins_out,
+          "rsn_pdf_resample: null pointer");
+  constexpr int WARPS = 4;
+  const int S = (int)n_in_samples, nb = (int)n_out_samples + 1;
+  size_t smem = (size_t)WARPS * 2 * (S + 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    RSN_CUDA(cudaFuncSetAttribute(pdf_resample_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks = (int)std::min<int64_t>((n_rays + WARPS - 1) / WARPS, (int64_t)rsn_num_sms() * 16);
+  pdf_resample_kernel<WARPS><<<blocks, WARPS * 32, smem, stream>>>(
+      weights, weights_row_stride, spacing_bins_in, nears, fars, u_base, rand, spacing_kind, histogram_padding,
+      spacing_bins_out, euclid_bins_out, inds_out, n_rays, S, nb);
+  RSN_LAUNCH_CHECK("pdf_resample_kernel");
+  return 0;
+}

@@ -1,0 +1,135 @@
+"""Python-side operators over the C-ABI (one function / autograd.Function per kernel stage).
+
+Tensors stay torch-owned; these wrappers only check shapes, allocate outputs and pass raw device
+pointers + the current CUDA stream to `librsn_b200.so`.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+UNIFORM, RECIPROCAL = 0, 1
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+@functools.lru_cache(maxsize=32)
+def _linspace_bins(n_samples: int, device: torch.device) -> Tensor:
+    # table taken from torch itself so it is bit-identical to SpacedSampler's
+    return torch.linspace(0.0, 1.0, n_samples + 1).to(device)
+
+
+@functools.lru_cache(maxsize=32)
+def _pdf_u_base(n_out: int, train: bool, device: torch.device) -> Tensor:
+    nb = n_out + 1
+    u = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb)
+    if not train:
+        u = u + 1.0 / (2 * nb)
+    return u.to(device)
+
+
+# ----------------------------------------------------------------------------------------- K1
+def sample_spaced(nears: Tensor, fars: Tensor, n_samples: int, kind: int,
+                  t_rand: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """-> (spacing bins [N,S+1], euclidean bins [N,S+1]).  t_rand: [N,S+1] or [N,1] in [0,1), None = eval."""
+    nears, fars, t_rand = _f32c(nears.reshape(-1)), _f32c(fars.reshape(-1)), _f32c(t_rand)
+    n = nears.shape[0]
+    dev = nears.device
+    spacing = torch.empty(n, n_samples + 1, device=dev, dtype=torch.float32)
+    euclid = torch.empty_like(spacing)
+    cols = 0 if t_rand is None else t_rand.shape[-1]
+    if t_rand is not None and t_rand.shape[0] != n:
+        raise ValueError(f"t_rand has {t_rand.shape[0]} rows for {n} rays")
+    _lib.call("rsn_sample_spaced", _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(_linspace_bins(n_samples, dev)),
+              _lib.ptr(t_rand), cols, kind, _lib.ptr(spacing), _lib.ptr(euclid), n, n_samples, _lib.stream())
+    return spacing, euclid
+
+
+# ----------------------------------------------------------------------------------------- K2
+def pdf_resample(weights: Tensor, spacing_bins: Tensor, nears: Tensor, fars: Tensor, n_out: int, kind: int,
+                 rand: Optional[Tensor] = None, train: Optional[bool] = None, histogram_padding: float = 0.01,
+                 return_inds: bool = False):
+    """weights [N,S] (or [N,S,1]); spacing_bins [N,S+1] -> (spacing [N,n_out+1], euclid [N,n_out+1][, inds])."""
+    if weights.dim() == 3:
+        weights = weights[..., 0]
+    weights, spacing_bins = _f32c(weights.detach()), _f32c(spacing_bins)
+    nears, fars, rand = _f32c(nears.reshape(-1)), _f32c(fars.reshape(-1)), _f32c(rand)
+    n, s = weights.shape
+    if spacing_bins.shape != (n, s + 1):
+        raise ValueError(f"spacing_bins must be [{n},{s + 1}], got {tuple(spacing_bins.shape)}")
+    if train is None:
+        train = rand is not None
+    if train and rand is None:
+        rand = torch.rand(n, n_out + 1, device=weights.device)
+    if rand is not None and rand.shape != (n, n_out + 1):
+        raise ValueError(f"rand must be [{n},{n_out + 1}], got {tuple(rand.shape)}")
+    dev = weights.device
+    out_s = torch.empty(n, n_out + 1, device=dev, dtype=torch.float32)
+    out_e = torch.empty_like(out_s)
+    inds = torch.empty(n, n_out + 1, device=dev, dtype=torch.int64) if return_inds else None
+    _lib.call("rsn_pdf_resample", _lib.ptr(weights), weights.stride(0), _lib.ptr(spacing_bins), _lib.ptr(nears),
+              _lib.ptr(fars), _lib.ptr(_pdf_u_base(n_out, bool(train), dev)), _lib.ptr(rand), kind,
+              float(histogram_padding), _lib.ptr(out_s), _lib.ptr(out_e), _lib.ptr(inds), n, s, n_out,
+              _lib.stream())
+    return (out_s, out_e, inds) if return_inds else (out_s, out_e)
+
+
+# ----------------------------------------------------------------------------------------- K8
+_COMPOSITE_CHANNELS = (0, 1, 3, 4, 8, 16)
+
+
+class _Composite(torch.autograd.Function):
+    """sigma [N,S], bins [N,S+1] (euclidean, no grad), feat [N,S,C] or None
+    -> weights [N,S], accumulation [N], median depth [N] (no grad), feat_out [N,C]."""
+
+    @staticmethod
+    def forward(ctx, sigma: Tensor, bins: Tensor, feat: Optional[Tensor]):
+        sigma, bins, feat = _f32c(sigma), _f32c(bins), _f32c(feat)
+        n, s = sigma.shape
+        c = 0 if feat is None else feat.shape[-1]
+        if c not in _COMPOSITE_CHANNELS:
+            raise ValueError(f"composite: channel count {c} not in {_COMPOSITE_CHANNELS}")
+        if bins.shape != (n, s + 1):
+            raise ValueError(f"composite: bins must be [{n},{s + 1}], got {tuple(bins.shape)}")
+        dev = sigma.device
+        weights = torch.empty(n, s, device=dev, dtype=torch.float32)
+        acc = torch.empty(n, device=dev, dtype=torch.float32)
+        depth = torch.empty(n, device=dev, dtype=torch.float32)
+        feat_out = torch.empty(n, c, device=dev, dtype=torch.float32)
+        _lib.call("rsn_composite_fwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1,
+                  _lib.ptr(feat), c, _lib.ptr(weights), _lib.ptr(acc), _lib.ptr(depth),
+                  _lib.ptr(feat_out) if c else None, n, s, _lib.stream())
+        ctx.save_for_backward(sigma, bins, feat if feat is not None else sigma.new_empty(0))
+        ctx.c = c
+        ctx.mark_non_differentiable(depth)
+        return weights, acc, depth, feat_out
+
+    @staticmethod
+    def backward(ctx, g_w, g_acc, _g_depth, g_feat_out):
+        sigma, bins, feat = ctx.saved_tensors
+        c = ctx.c
+        n, s = sigma.shape
+        need_feat = c > 0 and ctx.needs_input_grad[2]
+        g_sigma = torch.empty_like(sigma)
+        g_feat = torch.empty_like(feat) if need_feat else None
+        g_w, g_acc, g_feat_out = _f32c(g_w), _f32c(g_acc), _f32c(g_feat_out) if c else None
+        _lib.call("rsn_composite_bwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1,
+                  _lib.ptr(feat) if c else None, c, _lib.ptr(g_w), _lib.ptr(g_acc), _lib.ptr(g_feat_out),
+                  _lib.ptr(g_sigma), _lib.ptr(g_feat), n, s, _lib.stream())
+        return g_sigma, None, g_feat
+
+
+def composite(sigma: Tensor, bins: Tensor, feat: Optional[Tensor] = None):
+    """Alpha compositing of one ray batch (K8).  Returns (weights, accumulation, median_depth, feat_out)."""
+    return _Composite.apply(sigma, bins, feat)

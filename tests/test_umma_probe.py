@@ -1,0 +1,36 @@
+"""tcgen05 building blocks (csrc/umma.cuh) through single-tile GEMM probes vs torch matmul on the same
+bf16 operands.  Validates: 128B-swizzle block images, K-major and MN-major smem descriptors, the
+instruction descriptor, TMEM lane/column mapping, bulk-copy staging, N-split at a TMEM column offset."""
+import pytest
+import torch
+
+from reflect_sampling_nerf_b200 import _lib
+from reflect_sampling_nerf_b200.blocks import pack_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,KB,split", [(256, 4, 1), (256, 4, 2), (128, 2, 1), (16, 4, 1), (256, 1, 1), (64, 3, 2)])
+def test_kmajor_tile_gemm(N, KB, split):
+    g = torch.Generator().manual_seed(N + KB)
+    x = torch.randn(128, KB * 64, generator=g).bfloat16()
+    w = torch.randn(N, KB * 64, generator=g).bfloat16()
+    xb, wb = pack_blocks(x).cuda(), pack_blocks(w).cuda()
+    out = torch.full((128, N), float("nan"), device="cuda")
+    _lib.call("rsn_probe_umma_kmajor", xb.data_ptr(), wb.data_ptr(), N, KB, split, out.data_ptr(), _lib.stream())
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().T
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("NB", [1, 2, 4])
+def test_mnmajor_tile_gemm(NB):
+    g = torch.Generator().manual_seed(NB)
+    u = torch.randn(128, 128, generator=g).bfloat16()       # [points, M]
+    v = torch.randn(128, NB * 64, generator=g).bfloat16()   # [points, N]
+    ub, vb = pack_blocks(u).cuda(), pack_blocks(v).cuda()
+    out = torch.full((128, NB * 64), float("nan"), device="cuda")
+    _lib.call("rsn_probe_umma_mnmajor", ub.data_ptr(), vb.data_ptr(), 2, NB, out.data_ptr(), _lib.stream())
+    torch.cuda.synchronize()
+    ref = u.float().T @ v.float()
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-2)
