@@ -8,6 +8,10 @@ from reflect_sampling_nerf_b200 import ops
 
 pytestmark = pytest.mark.gpu
 RTOL_W = 1e-5          # north_star: compositing weights within 1e-5 relative in fp32
+# alpha = 1 - exp(-sigma*delta) cancels: one ulp of exp (libm-dependent, CUDA expf vs SLEEF) is 6e-8
+# ABSOLUTE on alpha, i.e. > 1e-5 relative once alpha < 6e-3.  The reference's own fp32 result carries
+# that noise, so the relative bound is paired with an absolute floor of 2 ulp(1.0).
+ATOL_W = 1.2e-7
 
 
 def _inputs(n, S, C, seed, dense=False):
@@ -35,7 +39,7 @@ def test_composite_forward(S, C):
     sigma, bins, feat = _inputs(301, S, C, seed=S + C)
     w_ref, acc_ref, depth_ref, fo_ref = _oracle(sigma, bins, feat)
     w, acc, depth, fo = ops.composite(sigma.cuda(), bins.cuda(), None if feat is None else feat.cuda())
-    torch.testing.assert_close(w.cpu(), w_ref, rtol=RTOL_W, atol=1e-9)
+    torch.testing.assert_close(w.cpu(), w_ref, rtol=RTOL_W, atol=ATOL_W)
     torch.testing.assert_close(acc.cpu(), acc_ref, rtol=1e-5, atol=1e-6)
     if C:
         torch.testing.assert_close(fo.cpu(), fo_ref, rtol=1e-5, atol=1e-6)
