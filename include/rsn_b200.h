@@ -70,6 +70,27 @@ int rsn_composite_bwd(const float* sigma, const float* starts, const float* ends
                       const float* grad_accumulation, const float* grad_feat_out, float* grad_sigma,
                       float* grad_feat, int64_t n_rays, int64_t n_samples, rsn_stream_t stream);
 
+/* ---- K3+K4+K5+K7: fused field forward --------------------------------------------------------------
+ * Replaces, for one pass over the samples of a ray batch (mode 0), field.get_blob -> contract ->
+ * get_density -> get_pred_normals / get_roughness / get_diff / get_tint -> IntegratedSHEncoding -> get_mid:
+ *   reflect_sampling_nerf_field.py:90-186,203-207 ; reflect_sampling_nerf_components.py:52-140 ;
+ *   call sites reflect_sampling_nerf_model.py:151-175,185-209,293-310,319-336
+ * and, in mode 1, field.get_inf_color (reflect_sampling_nerf_field.py:190-201; model.py:290) with
+ * dirs = w_r [N,3], area = sqradius [N], n_samples = 1 (origins/bins ignored).
+ * wblob: bf16 weight blob of rsn_field_blob_bytes() bytes and bias: fp32 [rsn_field_bias_count()], both
+ * produced by rsn_pack_field (or reflect_sampling_nerf_b200/packing.py).  origins/dirs [N,3], area [N]
+ * (pixel_area), bins [N,S+1] Euclidean bin edges.  Outputs: sigma [N*S] (softplus density) and
+ * feat [N*S,16]: 0-2 rgb = diff + tint*mid (mode 1: mid) | 3-5 diff | 6-8 tint | 9-11 pred_normal |
+ * 12 sigmoid(roughness) | 13 n.d | 14 raw density | 15 softplus(roughness).
+ * bf16 tensor-core MLP (tcgen05), fp32 encodings/heads. */
+int rsn_field_forward(const void* wblob, const float* bias, int mode, const float* origins, const float* dirs,
+                      const float* area, const float* bins, int64_t n_rays, int64_t n_samples, float* sigma,
+                      float* feat, rsn_stream_t stream);
+int64_t rsn_field_blob_bytes(void);
+int64_t rsn_field_bias_count(void);
+/* The 16 IPE frequencies 2**linspace(0,16,16) the kernels use (HOST pointer; for the table test). */
+int rsn_ipe_freqs(float* host_out16);
+
 /* ---- tcgen05 building-block probes (unit tests of csrc/umma.cuh) ---------------------------------- */
 int rsn_probe_umma_kmajor(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks,
                           int64_t n_split, float* out, rsn_stream_t stream);

@@ -21,6 +21,10 @@ _SIGNATURES = {
     "rsn_pdf_resample": ([P, I64, P, P, P, P, P, I32, F32, P, P, P, I64, I64, I64, P], c_int),
     "rsn_composite_fwd": ([P, P, P, I64, P, I64, P, P, P, P, I64, I64, P], c_int),
     "rsn_composite_bwd": ([P, P, P, I64, P, I64, P, P, P, P, P, I64, I64, P], c_int),
+    "rsn_field_forward": ([P, P, I32, P, P, P, P, I64, I64, P, P, P], c_int),
+    "rsn_field_blob_bytes": ([], c_int64),
+    "rsn_field_bias_count": ([], c_int64),
+    "rsn_ipe_freqs": ([P], c_int),
     "rsn_probe_umma_kmajor": ([P, P, I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_mnmajor": ([P, P, I64, I64, P, P], c_int),
 }

@@ -1,0 +1,693 @@
+// K3+K4+K5+K7 fused: frustum -> Gaussian -> contraction -> integrated positional encoding -> 8x256 base
+// MLP -> heads -> integrated directional encoding -> bottleneck / mid MLP -> rgb, for 128-point tiles.
+// SURVEY.md §2.4 (K3,K4,K5,K7), §8 rows a5-a9, a11, a12, a15, a17.
+//
+// Replaces (paths relative to /root/reference/reflect_sampling_nerf/):
+//   field.get_blob / contract / get_density          reflect_sampling_nerf_field.py:90-137
+//   get_pred_normals / get_roughness / get_diff / get_tint / get_mid / get_reflection (n.d)
+//                                                     reflect_sampling_nerf_field.py:139-207
+//   get_inf_color (mode 1)                            reflect_sampling_nerf_field.py:190-201
+//   IntegratedSHEncoding                              reflect_sampling_nerf_components.py:52-140
+//   call sites                                        reflect_sampling_nerf_model.py:151-175,185-209,290,293-310,319-336
+//
+// One persistent CTA per SM, 10 warps, one 128-point tile in flight per CTA:
+//   warp 0      weight producer: streams the pre-packed bf16 weight blob (L2 resident, 1.27 MB) through a
+//               3 x 32 KB shared-memory ring with cp.async.bulk (TMA engine) + mbarrier complete_tx
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M128, N<=256, K16, bf16 -> fp32 in TMEM)
+//   warps 2-5   epilogue: tcgen05.ld the accumulator row of "their" point, bias + ReLU, bf16, write the
+//               next layer's A operand IN PLACE into the swizzled activation blocks; heads, IDE, outputs
+//   warps 6-9   prologue for the NEXT tile: frustum gaussian, contraction, IPE -> bf16 A operand
+// The two 256-column TMEM accumulator buffers alternate by layer, and every layer's epilogue publishes
+// its output per 64-column group (mbarrier act_ready[g]) so that the next layer's K-block g is issued as
+// soon as that group is written: MMA of layer l+1 overlaps the epilogue of layer l.
+//
+// Roofline: bf16 tensor.  Algorithmic FLOPs per point: 1,230,592 (primary),
+// 1,229,056 (reflected), 1,225,472 (infinity colour).  HBM: 24 B/ray + 8 B/sample in, 68 B/point out.
+#include "rsn_common.cuh"
+#include "umma.cuh"
+#include "field_layout.cuh"
+
+namespace {
+
+using namespace umma;
+using namespace rsnf;
+
+constexpr int NUM_STAGES = 3;
+constexpr int SMEM_ACT = 0;                                    // 4 blocks
+constexpr int SMEM_ENC = 4 * BLOCK_BYTES;                      // 2 buffers x 2 blocks
+constexpr int SMEM_W = SMEM_ENC + 4 * BLOCK_BYTES;             // ring
+constexpr int SMEM_TOTAL = SMEM_W + NUM_STAGES * W_STAGE_BYTES;  // 229,376
+constexpr int NUM_THREADS = 320;
+
+// 2 ** torch.linspace(0, 16, 16) in fp32, bit for bit (NeRFEncoding, reflect_sampling_nerf_model.py:98-100)
+__constant__ float c_freq[16] = {
+    0x1.0000000000000p+0f,  0x1.0c1b780000000p+1f,  0x1.18c9880000000p+2f,  0x1.26111c0000000p+3f,
+    0x1.33f9760000000p+4f,  0x1.428a320000000p+5f,  0x1.51cb4e0000000p+6f,  0x1.61c5140000000p+7f,
+    0x1.7280340000000p+8f,  0x1.8405f60000000p+9f,  0x1.965fde0000000p+10f, 0x1.a998080000000p+11f,
+    0x1.bdb8d20000000p+12f, 0x1.d2cd4c0000000p+13f, 0x1.e8e1020000000p+14f, 0x1.0000000000000p+16f};
+const float h_freq[16] = {
+    0x1.0000000000000p+0f,  0x1.0c1b780000000p+1f,  0x1.18c9880000000p+2f,  0x1.26111c0000000p+3f,
+    0x1.33f9760000000p+4f,  0x1.428a320000000p+5f,  0x1.51cb4e0000000p+6f,  0x1.61c5140000000p+7f,
+    0x1.7280340000000p+8f,  0x1.8405f60000000p+9f,  0x1.965fde0000000p+10f, 0x1.a998080000000p+11f,
+    0x1.bdb8d20000000p+12f, 0x1.d2cd4c0000000p+13f, 0x1.e8e1020000000p+14f, 0x1.0000000000000p+16f};
+
+struct FwdParams {
+  const uint8_t* wblob;     // forward weight blob (FWD_BLOB_BYTES)
+  const float* bias;        // [N_BIAS]
+  int mode;                 // 0 = frustum samples of a ray batch, 1 = infinity colour (one point per ray)
+  const float* origins;     // [N,3]   (mode 0)
+  const float* dirs;        // [N,3]
+  const float* area;        // [N] pixel_area (mode 0) | sqradius (mode 1)
+  const float* bins;        // [N,S+1] euclidean bins (mode 0)
+  int n_samples;            // S (mode 1: 1)
+  int n_points;             // P = N*S
+  int n_tiles;
+  float* sigma;             // [P]
+  float* feat;              // [P][16]
+};
+
+struct Barriers {
+  uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
+  uint64_t enc_full[2], enc_empty[2];
+  uint64_t act_ready[4];
+  uint64_t ide_ready;
+  uint64_t acc_full[2];
+  uint32_t tmem_slot;
+};
+
+// ---------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// sin of an fp32 argument of any magnitude the encoding produces (|s| <= 2pi * 2 * 65536): two-term
+// Cody-Waite reduction by 2pi (exact products through fma), then the SFU on [-pi, pi].  Absolute error
+// < 1e-6, far below the bf16 resolution of the feature it feeds.
+__device__ __forceinline__ float sin_reduced(float s) {
+  const float k = rintf(s * 0.15915494309189535f);
+  float r = fmaf(-k, 0x1.921fb60000000p+2f, s);
+  r = fmaf(-k, -0x1.777a5cp-23f, r);
+  return __sinf(r);
+}
+
+// 8 encoded columns -> one 16-byte chunk of the row
+__device__ __forceinline__ void store_chunk(uint32_t row_saddr, int row, int chunk, const float (&f)[8]) {
+  sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------------------------------------- prologue
+// Contracted Gaussian of one frustum sample: field.get_blob (field.py:90-96) followed by
+// field.contract (field.py:98-119).  Only diag(J cov J) is consumed downstream (NeRFEncoding reads
+// torch.diagonal(covs) only).  The mean follows the reference's fp32 operation order without fma
+// contraction because it feeds sin(2 pi x f) at f up to 65536.
+__device__ __forceinline__ void frustum_gaussian_contracted(const float o[3], const float d[3], float t0, float t1,
+                                                            float pixel_area, float (&xm)[3], float (&dg)[3]) {
+  const float radius = __fdiv_rn(__fsqrt_rn(pixel_area), 1.7724538509055159f);
+  const float mu = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+  const float hw = __fmul_rn(__fsub_rn(t1, t0), 0.5f);
+  const float hw2 = __fmul_rn(hw, hw), mu2 = __fmul_rn(mu, mu);
+  const float den = __fadd_rn(__fmul_rn(3.0f, mu2), hw2);
+  const float tmean = __fadd_rn(mu, __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, mu), hw2), den));
+  float m[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) m[a] = __fadd_rn(o[a], __fmul_rn(d[a], tmean));
+  const float hw4 = hw2 * hw2;
+  const float dir_var = hw2 / 3.0f - 0.26666668f * ((hw4 * (12.0f * mu2 - hw2)) / (den * den));
+  const float rad_var = (radius * radius) * (mu2 * 0.25f + 0.41666666f * hw2 - 0.26666668f * hw4 / den);
+  // cov = dir_var d d^T + rad_var (I - d (d / max(|d|^2, 1e-10))^T)      (symmetric; 6 entries)
+  const float dd = fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-10f);
+  const float dn[3] = {d[0] / dd, d[1] / dd, d[2] / dd};
+  float cov[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      cov[i][j] = dir_var * (d[i] * d[j]) + rad_var * ((i == j ? 1.0f : 0.0f) - d[i] * dn[j]);
+  // contraction
+  const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(m[0], m[0]), __fmul_rn(m[1], m[1])), __fmul_rn(m[2], m[2]));
+  const float n1 = __fsqrt_rn(n2);
+  if (n1 > 1.0f) {
+    const float sc = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, n1), 1.0f), n2);
+    // J = ((2 n1 - 2)(I - m m^T / n2) + I) / n2   (symmetric)
+    const float a2 = 2.0f * n1 - 2.0f;
+    float J[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float e = (i == j) ? 1.0f : 0.0f;
+        J[i][j] = (a2 * (e - m[i] * m[j] / n2) + e) / n2;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      // (J cov J)_ii = sum_k (sum_j J_ij cov_jk) J_ki
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) t += J[i][j] * cov[j][k];
+        acc += t * J[k][i];
+      }
+      dg[i] = fmaxf(acc, 0.f);
+      xm[i] = __fmul_rn(sc, m[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      dg[i] = fmaxf(cov[i][i], 0.f);
+      xm[i] = m[i];
+    }
+  }
+}
+
+// IPE of (xm, diag dg) -> bf16 row of the enc operand (columns 0..111; 99..111 zero).
+// NeRFEncoding.forward with covs: s = fl(fl(2pi x) f), v = fl(diag fl(f f)),
+// enc = exp(-v/2) sin(s | s + pi/2), raw xyz appended last.
+__device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const float (&xm)[3], const float (&dg)[3]) {
+  const uint32_t row0 = enc_saddr + (uint32_t)row * 128u;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float sx = __fmul_rn(6.2831854820251465f, xm[a]);
+      const float va = dg[a];
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        float f8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float f = c_freq[kk * 8 + i];
+          float s = __fmul_rn(sx, f);
+          if (half) s = __fadd_rn(s, 1.5707963705062866f);
+          const float e = 0.5f * (va * (f * f));
+          f8[i] = (e < 24.f) ? __expf(-e) * sin_reduced(s) : 0.f;
+        }
+        const int j = half * 6 + a * 2 + kk;  // 16-byte chunk index along the 112 columns
+        store_chunk(row0 + (uint32_t)(j >> 3) * BLOCK_BYTES, row, j & 7, f8);
+      }
+    }
+  }
+  const float f12[8] = {xm[0], xm[1], xm[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float f13[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  store_chunk(row0 + BLOCK_BYTES, row, 12 & 7, f12);
+  store_chunk(row0 + BLOCK_BYTES, row, 13 & 7, f13);
+}
+
+// ---------------------------------------------------------------------------------------------- IDE
+// IntegratedSHEncoding.pytorch_fwd (components.py:52-140): 34 hand-expanded polynomials for l = 1,2,4,8 with
+// the reference's constants (entries 17/18/32 keep 5.8314...), each band attenuated by
+// exp(-rho l(l+1)/2) = exp(-rho {1,3,10,36}).
+__device__ __forceinline__ void ide_features(const float d[3], float rho, float (&t)[48]) {
+  const float x = d[0], y = d[1], z = d[2];
+  const float x2 = x * x, y2 = y * y, z2 = z * z;
+  const float xy = x * y, xz = x * z, yz = y * z;
+  const float dxy = x2 - y2;
+  const float a = 3.f * x2 - y2, b = x2 - 3.f * y2;
+  const float z4 = z2 * z2, x4 = x2 * x2, y4 = y2 * y2;
+  const float p = y4 - 10.f * x2 * y2 + 5.f * x4;
+  const float q = x4 - 10.f * x2 * y2 + 5.f * y4;
+  const float r = (x2 - 5.f * y2) * 7.f * x4 + (21.f * x2 - y2) * y4;
+  const float s = (x2 - 21.f * y2) * x4 + (5.f * x2 - y2) * 7.f * y4;
+  const float e1 = __expf(-rho), e2 = __expf(-3.f * rho), e4 = __expf(-10.f * rho), e8 = __expf(-36.f * rho);
+  const float c1 = 0.48860251190291992f;
+  t[0] = e1 * c1 * y;
+  t[1] = e1 * c1 * z;
+  t[2] = e1 * c1 * x;
+  t[3] = e2 * 1.09254843059207907f * xy;
+  t[4] = e2 * 1.09254843059207907f * yz;
+  t[5] = e2 * 0.31539156525252001f * (3.f * z2 - 1.f);
+  t[6] = e2 * 1.09254843059207907f * xz;
+  t[7] = e2 * 0.54627421529603953f * dxy;
+  t[8] = e4 * 2.50334294179670453f * xy * dxy;
+  t[9] = e4 * 1.77013076977993053f * yz * a;
+  t[10] = e4 * 0.94617469575756001f * xy * (7.f * z2 - 1.f);
+  t[11] = e4 * 0.66904654355728916f * yz * (7.f * z2 - 3.f);
+  t[12] = e4 * 0.1057855469152043038f * (35.f * z4 - 30.f * z2 + 3.f);
+  t[13] = e4 * 0.66904654355728916f * xz * (7.f * z2 - 3.f);
+  t[14] = e4 * 0.473087347878780009f * dxy * (7.f * z2 - 1.f);
+  t[15] = e4 * 1.77013076977993053f * xz * b;
+  t[16] = e4 * 0.62583573544917613f * (x2 * b - y2 * a);
+  t[17] = e8 * 5.83141328139863895f * xy * (x2 * x4 - 7.f * x4 * y2 + 7.f * x2 * y4 - y2 * y4);
+  t[18] = e8 * 5.83141328139863895f * yz * r;
+  t[19] = e8 * 1.06466553211908514f * xy * (15.f * z2 - 1.f) * (3.f * x4 - 10.f * x2 * y2 + 3.f * y4);
+  t[20] = e8 * 3.44991062209810801f * yz * (5.f * z2 - 1.f) * p;
+  t[21] = e8 * 1.91366609903732278f * xy * (65.f * z4 - 26.f * z2 + 1.f) * dxy;
+  t[22] = e8 * 1.23526615529554407f * yz * (39.f * z4 - 26.f * z2 + 3.f) * a;
+  t[23] = e8 * 0.91230451686981894f * xy * (143.f * z4 * z2 - 143.f * z4 + 33.f * z2 - 1.f);
+  t[24] = e8 * 0.1090412458987799555f * yz * (715.f * z4 * z2 - 1001.f * z4 + 385.f * z2 - 35.f);
+  t[25] = e8 * 0.0090867704915649962938f * (6435.f * z4 * z4 - 12012.f * z4 * z2 + 6930.f * z4 - 1260.f * z2 + 35.f);
+  t[26] = e8 * 0.1090412458987799555f * xz * (715.f * z4 * z2 - 1001.f * z4 + 385.f * z2 - 35.f);
+  t[27] = e8 * 0.456152258434909470f * (143.f * z4 * z2 - 143.f * z4 + 33.f * z2 - 1.f) * dxy;
+  t[28] = e8 * 1.23526615529554407f * xz * (39.f * z4 - 26.f * z2 + 3.f) * b;
+  t[29] = e8 * 0.478416524759330697f * (65.f * z4 - 26.f * z2 + 1.f) * (x2 * b - y2 * a);
+  t[30] = e8 * 3.44991062209810801f * xz * (5.f * z2 - 1.f) * q;
+  t[31] = e8 * 0.53233276605954257f * (15.f * z2 - 1.f) * (x2 * q - y2 * p);
+  t[32] = e8 * 5.83141328139863895f * xz * s;
+  t[33] = e8 * 0.72892666017482986f * (x2 * s - y2 * r);
+#pragma unroll
+  for (int i = 34; i < 48; ++i) t[i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------- epilogue
+// 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> activation block `blk`.
+template <bool RELU>
+__device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, const float* __restrict__ bias,
+                                               uint32_t blk_saddr, int row) {
+  uint32_t v[2][32];
+  tmem_ld32(tmem_row_col, v[0]);
+  tmem_ld32(tmem_row_col + 32, v[1]);
+  float4 b[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
+  tmem_ld_wait();
+  const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // 8 columns per 16-byte chunk
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 bb = b[h * 8 + c * 2 + q];
+        const float x0 = __uint_as_float(v[h][c * 8 + q * 4 + 0]) + bb.x;
+        const float x1 = __uint_as_float(v[h][c * 8 + q * 4 + 1]) + bb.y;
+        const float x2 = __uint_as_float(v[h][c * 8 + q * 4 + 2]) + bb.z;
+        const float x3 = __uint_as_float(v[h][c * 8 + q * 4 + 3]) + bb.w;
+        pk[q * 2 + 0] = RELU ? pack_relu_bf16x2(x0, x1) : pack_bf16x2(x0, x1);
+        pk[q * 2 + 1] = RELU ? pack_relu_bf16x2(x2, x3) : pack_bf16x2(x2, x3);
+      }
+      const int chunk = h * 4 + c;
+      sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ Barriers bars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_act = smem_u32(smem + SMEM_ACT);
+  const uint32_t s_enc = smem_u32(smem + SMEM_ENC);
+  const uint32_t s_w = smem_u32(smem + SMEM_W);
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < NUM_STAGES; ++i) {
+        mbar_init(&bars.w_full[i], 1);
+        mbar_init(&bars.w_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars.enc_full[i], TILE);
+        mbar_init(&bars.enc_empty[i], 1);
+        mbar_init(&bars.acc_full[i], 1);
+      }
+      for (int i = 0; i < 4; ++i) mbar_init(&bars.act_ready[i], TILE);
+      mbar_init(&bars.ide_ready, TILE);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars.tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_slot;
+  const int n_my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    // ===================================================================== weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_my_tiles; ++it) {
+        uint32_t off = 0;
+        for (int c = 0; c < N_FWD_CHUNKS; ++c) {
+          const uint32_t bytes = fwd_chunk_bytes(c);
+          mbar_wait(&bars.w_empty[stage], phase ^ 1);
+          mbar_expect_tx(&bars.w_full[stage], bytes);
+          bulk_g2s(smem + SMEM_W + stage * W_STAGE_BYTES, p.wblob + off, bytes, &bars.w_full[stage]);
+          off += bytes;
+          if (++stage == NUM_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t wphase = 0;
+      uint32_t ar_phase = 0;  // bit g: parity of the next completion of act_ready[g]
+      int buf = 0;
+      constexpr uint32_t ID256 = instr_desc_bf16(128, 256, 0, 0);
+      constexpr uint32_t ID128 = instr_desc_bf16(128, 128, 0, 0);
+      constexpr uint32_t ID16 = instr_desc_bf16(128, 16, 0, 0);
+      auto ring_wait = [&]() -> uint32_t {
+        mbar_wait(&bars.w_full[stage], wphase);
+        tc_fence_after();
+        return s_w + (uint32_t)stage * W_STAGE_BYTES;
+      };
+      auto ring_release = [&]() {
+        mma_commit(&bars.w_empty[stage]);
+        if (++stage == NUM_STAGES) {
+          stage = 0;
+          wphase ^= 1;
+        }
+      };
+      auto wait_act = [&](int g) {
+        mbar_wait(&bars.act_ready[g], (ar_phase >> g) & 1u);
+        ar_phase ^= (1u << g);
+        tc_fence_after();
+      };
+      auto issue_kb = [&](uint32_t a_addr, uint32_t b_addr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool& acc) {
+        for (int k = 0; k < ksteps; ++k) {
+          mma_bf16_ss(tmem_d, smem_desc_sw128(a_addr + k * 32, 16, 1024), smem_desc_sw128(b_addr + k * 32, 16, 1024),
+                      idesc, acc ? 1u : 0u);
+          acc = true;
+        }
+      };
+      for (int it = 0; it < n_my_tiles; ++it) {
+        const int eb = it & 1;
+        const uint32_t enc_a = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
+        bool acc;
+        // ---- base layers 0..7
+        for (int l = 0; l < 8; ++l) {
+          const uint32_t tm = tmem + (uint32_t)buf * 256;
+          acc = false;
+          if (l == 0) {
+            mbar_wait(&bars.enc_full[eb], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+          }
+          if (l == 0 || l == 4) {
+            uint32_t w = ring_wait();
+            issue_kb(enc_a, w, 4, ID256, tm, acc);
+            ring_release();
+            w = ring_wait();
+            issue_kb(enc_a + BLOCK_BYTES, w, ENC_KSTEPS_B1, ID256, tm, acc);
+            ring_release();
+          }
+          if (l > 0) {
+            for (int g = 0; g < 4; ++g) {
+              wait_act(g);
+              const uint32_t w = ring_wait();
+              issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tm, acc);
+              ring_release();
+            }
+          }
+          mma_commit(&bars.acc_full[buf]);
+          buf ^= 1;
+        }
+        // ---- layer 8: bottleneck (N=256) + heads (N=16, other buffer, columns 240..255)
+        {
+          const uint32_t tm = tmem + (uint32_t)buf * 256;
+          acc = false;
+          for (int g = 0; g < 4; ++g) {
+            wait_act(g);
+            const uint32_t w = ring_wait();
+            issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tm, acc);
+            ring_release();
+          }
+          const uint32_t w = ring_wait();
+          bool acc_h = false;
+          for (int kb = 0; kb < 4; ++kb)
+            issue_kb(s_act + kb * BLOCK_BYTES, w + kb * (N_HEAD * 128), 4, ID16,
+                     tmem + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, acc_h);
+          ring_release();
+          mma_commit(&bars.acc_full[buf]);
+          buf ^= 1;
+        }
+        // ---- layer 9: mid MLP, A = [bottleneck 256 | IDE 48], N = 128
+        {
+          const uint32_t tm = tmem + (uint32_t)buf * 256;
+          acc = false;
+          for (int c = 0; c < 2; ++c) {
+            wait_act(2 * c);
+            wait_act(2 * c + 1);
+            const uint32_t w = ring_wait();
+            issue_kb(s_act + (2 * c) * BLOCK_BYTES, w, 4, ID128, tm, acc);
+            issue_kb(s_act + (2 * c + 1) * BLOCK_BYTES, w + 128 * 128, 4, ID128, tm, acc);
+            ring_release();
+          }
+          mbar_wait(&bars.ide_ready, (uint32_t)it & 1u);
+          tc_fence_after();
+          const uint32_t w = ring_wait();
+          issue_kb(enc_a, w, IDE_KSTEPS, ID128, tm, acc);
+          ring_release();
+          mma_commit(&bars.acc_full[buf]);
+          mma_commit(&bars.enc_empty[eb]);
+          buf ^= 1;
+        }
+        // ---- layer 10: rgb head, A = mid hidden 128, N = 16
+        {
+          const uint32_t tm = tmem + (uint32_t)buf * 256;
+          acc = false;
+          wait_act(0);
+          wait_act(1);
+          const uint32_t w = ring_wait();
+          issue_kb(s_act, w, 4, ID16, tm, acc);
+          issue_kb(s_act + BLOCK_BYTES, w + N_HEAD * 128, 4, ID16, tm, acc);
+          ring_release();
+          mma_commit(&bars.acc_full[buf]);
+          buf ^= 1;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================================================================== epilogue warps (thread = point row)
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t af_phase = 0;
+    int buf = 0;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int eb = it & 1;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int pt = tile * TILE + row;
+      const bool valid = pt < p.n_points;
+      auto wait_acc = [&]() {
+        mbar_wait(&bars.acc_full[buf], (af_phase >> buf) & 1u);
+        af_phase ^= (1u << buf);
+        tc_fence_after();
+      };
+      auto publish = [&](uint64_t* bar) {
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar);
+      };
+      for (int l = 0; l < 8; ++l) {
+        wait_acc();
+        for (int g = 0; g < 4; ++g) {
+          epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_BASE + l * 256 + g * 64,
+                               s_act + g * BLOCK_BYTES, row);
+          publish(&bars.act_ready[g]);
+        }
+        buf ^= 1;
+      }
+      // ---- layer 8: bottleneck -> activation blocks (no activation), then heads + IDE
+      float diff[3], tint[3];
+      {
+        wait_acc();
+        for (int g = 0; g < 4; ++g) {
+          epilogue_group<false>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_BOTT + g * 64,
+                                s_act + g * BLOCK_BYTES, row);
+          publish(&bars.act_ready[g]);
+        }
+        uint32_t hv[16];
+        tmem_ld16(tlane + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, hv);
+        float hb[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + BIAS_HEAD) + i);
+          hb[i * 4 + 0] = t4.x, hb[i * 4 + 1] = t4.y, hb[i * 4 + 2] = t4.z, hb[i * 4 + 3] = t4.w;
+        }
+        tmem_ld_wait();
+        float h[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) h[i] = __uint_as_float(hv[i]) + hb[i];
+        // view direction of this point's ray
+        float d[3] = {0.f, 0.f, 1.f};
+        if (valid) {
+          const int ray = pt / p.n_samples;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) d[a] = __ldg(p.dirs + (size_t)ray * 3 + a);
+        }
+        const float raw_sigma = h[0];
+        const float sigma = softplusf(raw_sigma + 0.5f);  // density_bias = 0.5 (field.py:46,136)
+        // pred normals = normalize(-normalize(Linear(emb)))  (field.py:139-144)
+        float n[3] = {h[1], h[2], h[3]};
+        float nn = fmaxf(sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), 1e-12f);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) n[a] = -(n[a] / nn);
+        nn = fmaxf(sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), 1e-12f);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) n[a] = n[a] / nn;
+        const float ndd = d[0] * n[0] + d[1] * n[1] + d[2] * n[2];  // field.py:204
+        const float rough_sp = softplusf(h[4]);                     // model.py:173 (Softplus -> IDE)
+        const float rough_sg = sigmoid_acc(h[4]);                   // model.py:225 (Sigmoid -> rendered)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          diff[a] = sigmoid_acc(h[5 + a]);
+          tint[a] = sigmoid_acc(h[8 + a]);
+        }
+        // IDE of the VIEW direction (App. B Q1) -> first 48 columns of this tile's enc block 0
+        float t[48];
+        if (p.mode == 0) {
+          ide_features(d, rough_sp, t);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 48; ++i) t[i] = 0.f;  // get_inf_color feeds a zero IDE (field.py:199)
+        }
+        const uint32_t ide_row = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const float f8[8] = {t[c * 8 + 0], t[c * 8 + 1], t[c * 8 + 2], t[c * 8 + 3],
+                               t[c * 8 + 4], t[c * 8 + 5], t[c * 8 + 6], t[c * 8 + 7]};
+          store_chunk(ide_row, row, c, f8);
+        }
+        publish(&bars.ide_ready);
+        if (valid) {
+          p.sigma[pt] = sigma;
+          float4* fo = reinterpret_cast<float4*>(p.feat + (size_t)pt * N_FEAT);
+          fo[1] = make_float4(diff[1], diff[2], tint[0], tint[1]);           // cols 4..7
+          fo[2] = make_float4(tint[2], n[0], n[1], n[2]);                    // cols 8..11
+          fo[3] = make_float4(rough_sg, ndd, raw_sigma, rough_sp);           // cols 12..15
+        }
+        buf ^= 1;
+      }
+      // ---- layer 9: mid hidden (ReLU) -> activation blocks 0,1
+      {
+        wait_acc();
+        for (int g = 0; g < 2; ++g) {
+          epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_MID + g * 64,
+                               s_act + g * BLOCK_BYTES, row);
+          publish(&bars.act_ready[g]);
+        }
+        buf ^= 1;
+      }
+      // ---- layer 10: rgb
+      {
+        wait_acc();
+        uint32_t rv[16];
+        tmem_ld16(tlane + (uint32_t)buf * 256, rv);
+        const float4 rb = __ldg(reinterpret_cast<const float4*>(p.bias + BIAS_RGB));
+        tmem_ld_wait();
+        tc_fence_before();
+        const float mid[3] = {sigmoid_acc(__uint_as_float(rv[0]) + rb.x), sigmoid_acc(__uint_as_float(rv[1]) + rb.y),
+                              sigmoid_acc(__uint_as_float(rv[2]) + rb.z)};
+        if (valid) {
+          float rgb[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) rgb[a] = (p.mode == 0) ? diff[a] + tint[a] * mid[a] : mid[a];
+          float4* fo = reinterpret_cast<float4*>(p.feat + (size_t)pt * N_FEAT);
+          fo[0] = make_float4(rgb[0], rgb[1], rgb[2], diff[0]);  // cols 0..3
+        }
+        buf ^= 1;
+      }
+    }
+  } else {
+    // ===================================================================== prologue warps (next tile's IPE)
+    const int row = (warp - 6) * 32 + lane;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int eb = it & 1;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int pt = tile * TILE + row;
+      float xm[3] = {0.f, 0.f, 0.f}, dg[3] = {0.f, 0.f, 0.f};
+      if (pt < p.n_points) {
+        if (p.mode == 0) {
+          const int ray = pt / p.n_samples;
+          const int s = pt - ray * p.n_samples;
+          float o[3], d[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            o[a] = __ldg(p.origins + (size_t)ray * 3 + a);
+            d[a] = __ldg(p.dirs + (size_t)ray * 3 + a);
+          }
+          const float* b = p.bins + (size_t)ray * (p.n_samples + 1) + s;
+          frustum_gaussian_contracted(o, d, __ldg(b), __ldg(b + 1), __ldg(p.area + ray), xm, dg);
+        } else {
+          // get_inf_color (field.py:190-201): mean = 2 w, cov = 0.6 sqradius (I - w w^T), NOT contracted
+          const float sq = __fmul_rn(0.6f, __ldg(p.area + pt));
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const float w = __ldg(p.dirs + (size_t)pt * 3 + a);
+            xm[a] = __fmul_rn(2.0f, w);
+            dg[a] = __fmul_rn(sq, __fsub_rn(1.0f, __fmul_rn(w, w)));
+          }
+        }
+      }
+      mbar_wait(&bars.enc_empty[eb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      encode_row(s_enc + (uint32_t)eb * 2 * BLOCK_BYTES, row, xm, dg);
+      fence_proxy_async();
+      mbar_arrive(&bars.enc_full[eb]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+extern "C" int rsn_ipe_freqs(float* host_out16) {
+  RSN_ARG(host_out16 != nullptr, "rsn_ipe_freqs: null pointer");
+  for (int i = 0; i < 16; ++i) host_out16[i] = h_freq[i];
+  return 0;
+}
+
+extern "C" int64_t rsn_field_blob_bytes(void) { return (int64_t)FWD_BLOB_BYTES; }
+extern "C" int64_t rsn_field_bias_count(void) { return (int64_t)N_BIAS; }
+
+extern "C" int rsn_field_forward(const void* wblob, const float* bias, int mode, const float* origins,
+                                 const float* dirs, const float* area, const float* bins, int64_t n_rays,
+                                 int64_t n_samples, float* sigma, float* feat, cudaStream_t stream) {
+  RSN_ARG(mode == 0 || mode == 1, "rsn_field_forward: mode must be 0 (samples) or 1 (infinity colour)");
+  RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_field_forward: bad shape");
+  RSN_ARG(mode == 0 || n_samples == 1, "rsn_field_forward: mode 1 takes one point per ray");
+  if (n_rays == 0) return 0;
+  RSN_ARG(n_rays * n_samples < (int64_t)2147483647 - TILE, "rsn_field_forward: more than 2^31 points in one call");
+  RSN_ARG(wblob && bias && dirs && area && sigma && feat, "rsn_field_forward: null pointer");
+  RSN_ARG(mode == 1 || (origins && bins), "rsn_field_forward: origins/bins required in mode 0");
+  RSN_ARG(((uintptr_t)wblob & 15) == 0 && ((uintptr_t)bias & 15) == 0 && ((uintptr_t)feat & 15) == 0,
+          "rsn_field_forward: wblob/bias/feat must be 16-byte aligned");
+  FwdParams p;
+  p.wblob = (const uint8_t*)wblob;
+  p.bias = bias;
+  p.mode = mode;
+  p.origins = origins;
+  p.dirs = dirs;
+  p.area = area;
+  p.bins = bins;
+  p.n_samples = (int)n_samples;
+  p.n_points = (int)(n_rays * n_samples);
+  p.n_tiles = (p.n_points + TILE - 1) / TILE;
+  p.sigma = sigma;
+  p.feat = feat;
+  const size_t smem = SMEM_TOTAL + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.n_tiles, rsn_num_sms());
+  field_fwd_kernel<<<grid, NUM_THREADS, smem, stream>>>(p);
+  RSN_LAUNCH_CHECK("field_fwd_kernel");
+  return 0;
+}

@@ -1,0 +1,52 @@
+// Layout constants shared by the fused field kernels (forward, dgrad chain, wgrad) and by the host-side
+// packer (reflect_sampling_nerf_b200/packing.py mirrors these numbers; tests/test_packing.py checks them).
+//
+// The field is reflect_sampling_nerf_field.py:54-86:
+//   mlp_base   8 x 256, input = 99-dim IPE, skip-concat [enc, h] at layer 4, ReLU after every layer
+//   heads      density 1 | pred-normals 3 | roughness 1 | diff 3 | tint 3   (one N=16 GEMM, 11 used)
+//   bottleneck 256 -> 256 (no activation)
+//   mlp_mid    [IDE 34, bottleneck 256] -> 128, ReLU
+//   mid rgb    128 -> 3, sigmoid
+//
+// GEMM "layers" of one 128-point tile, in issue order (li = 0..10):
+//   0..7 base layers | 8 bottleneck (+ the heads GEMM riding on the same A operand) | 9 mid | 10 rgb
+//
+// Operands are "block images" (umma.cuh: block_off): [rows][64] bf16, 128-byte swizzled.
+// Activations: rows = the 128 points of the tile.  Weights: rows = output features, one image per
+// 64-wide K block, concatenated in the order the MMA issuer consumes them ("chunks").
+#pragma once
+#include <stdint.h>
+
+namespace rsnf {
+
+constexpr int TILE = 128;            // points per tile (= UMMA M)
+constexpr int BLOCK_BYTES = 16384;   // one [128][64] bf16 activation block
+constexpr int ENC_DIM = 99;          // IPE output (48 sin + 48 cos-like + xyz)
+constexpr int ENC_KSTEPS_B1 = 3;     // second enc block: columns 64..111 (99 real + zero pad) = 3 K-steps
+constexpr int IDE_DIM = 34;
+constexpr int IDE_KSTEPS = 3;        // 34 -> 48 columns
+constexpr int N_HEAD = 16;           // density, normals(3), roughness, diff(3), tint(3), 5 x pad
+constexpr int HEAD_TMEM_COL = 240;   // heads accumulate in the OTHER accumulator buffer, columns 240..255
+
+// ---- forward weight blob: chunk sizes in consumption order -----------------------------------------
+constexpr int W_STAGE_BYTES = 32768;
+constexpr int N_FWD_CHUNKS = 41;
+constexpr uint32_t FWD_BLOB_BYTES = 36u * 32768u + 8192u + 32768u + 32768u + 16384u + 4096u;  // 1,273,856
+__host__ __device__ constexpr uint32_t fwd_chunk_bytes(int c) {
+  return c < 36 ? 32768u : c == 36 ? 8192u : c < 39 ? 32768u : c == 39 ? 16384u : 4096u;
+}
+
+// ---- bias vector (fp32) -----------------------------------------------------------------------------
+constexpr int BIAS_BASE = 0;          // 8 x 256
+constexpr int BIAS_BOTT = 2048;       // 256
+constexpr int BIAS_HEAD = 2304;       // 16
+constexpr int BIAS_MID = 2320;        // 128
+constexpr int BIAS_RGB = 2448;        // 16
+constexpr int N_BIAS = 2464;
+
+// ---- per-point feature row written by the forward kernel ([P][16] fp32) ------------------------------
+// 0-2 rgb = diff + tint*mid | 3-5 diff | 6-8 tint | 9-11 pred_normal | 12 sigmoid(rough) | 13 n.d
+// 14 raw density (before softplus, without the 0.5 bias) | 15 softplus(rough)
+constexpr int N_FEAT = 16;
+
+}  // namespace rsnf

@@ -133,3 +133,37 @@ class _Composite(torch.autograd.Function):
 def composite(sigma: Tensor, bins: Tensor, feat: Optional[Tensor] = None):
     """Alpha compositing of one ray batch (K8).  Returns (weights, accumulation, median_depth, feat_out)."""
     return _Composite.apply(sigma, bins, feat)
+
+
+# ----------------------------------------------------------------------------------------- K3+K4+K5+K7
+MODE_SAMPLES, MODE_INF_COLOR = 0, 1
+N_FEAT = 16
+(F_RGB, F_DIFF, F_TINT, F_NORMAL, F_ROUGH_SIGMOID, F_NDOTD, F_RAW_DENSITY, F_ROUGH_SOFTPLUS) = (
+    slice(0, 3), slice(3, 6), slice(6, 9), slice(9, 12), 12, 13, 14, 15)
+
+
+def field_forward(wblob: Tensor, bias: Tensor, origins: Tensor, dirs: Tensor, pixel_area: Tensor,
+                  bins: Tensor) -> Tuple[Tensor, Tensor]:
+    """Fused field evaluation of every frustum sample of a ray batch (inference form, no autograd).
+    origins/dirs [N,3], pixel_area [N] or [N,1], bins [N,S+1] euclidean -> sigma [N,S], feat [N,S,16]."""
+    origins, dirs, bins = _f32c(origins), _f32c(dirs), _f32c(bins)
+    area = _f32c(pixel_area.reshape(-1))
+    n, s = bins.shape[0], bins.shape[1] - 1
+    if origins.shape != (n, 3) or dirs.shape != (n, 3) or area.shape[0] != n:
+        raise ValueError("field_forward: origins/dirs must be [N,3] and pixel_area [N] for bins [N,S+1]")
+    sigma = torch.empty(n, s, device=bins.device, dtype=torch.float32)
+    feat = torch.empty(n, s, N_FEAT, device=bins.device, dtype=torch.float32)
+    _lib.call("rsn_field_forward", _lib.ptr(wblob), _lib.ptr(bias), MODE_SAMPLES, _lib.ptr(origins), _lib.ptr(dirs),
+              _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), _lib.stream())
+    return sigma, feat
+
+
+def field_inf_color(wblob: Tensor, bias: Tensor, dirs: Tensor, sqradius: Tensor) -> Tensor:
+    """field.get_inf_color (field.py:190-201): dirs [M,3], sqradius [M] or [M,1] -> rgb [M,3]."""
+    dirs, sq = _f32c(dirs), _f32c(sqradius.reshape(-1))
+    m = dirs.shape[0]
+    sigma = torch.empty(m, device=dirs.device, dtype=torch.float32)
+    feat = torch.empty(m, N_FEAT, device=dirs.device, dtype=torch.float32)
+    _lib.call("rsn_field_forward", _lib.ptr(wblob), _lib.ptr(bias), MODE_INF_COLOR, None, _lib.ptr(dirs),
+              _lib.ptr(sq), None, m, 1, _lib.ptr(sigma), _lib.ptr(feat), _lib.stream())
+    return feat[:, :3]

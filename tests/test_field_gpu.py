@@ -1,0 +1,98 @@
+"""Fused field forward (K3+K4+K5+K7, tcgen05) vs the oracle field on the same rays, bins and random-init
+weights.  Two references: (i) the fp32 oracle -- tolerance of the bf16 MLP (north_star: rendered RGB within
+1e-2); (ii) the same oracle with every GEMM operand rounded to bf16 exactly where the kernel rounds --
+tight tolerance, catches layout / schedule / swizzle mistakes that a loose bound would hide."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import refpath as R
+from reflect_sampling_nerf_b200 import ops, packing
+from helpers import synthetic_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.bfloat16().float()
+
+
+def bf16_field(field, mean, cov, dirs, zero_ide=False):
+    """Oracle field with GEMM operands rounded to bf16 (fp32 accumulate), as the kernel computes."""
+    sd = {k: v.detach() for k, v in field.state_dict().items()}
+    lin = lambda x, w, b: _bf(x) @ _bf(sd[w]).T + sd[b]  # noqa: E731
+    enc = R.ipe(mean, cov)
+    h = enc
+    for l in range(8):
+        if l == 4:
+            h = torch.cat([enc, h], -1)
+        h = F.relu(lin(h, f"mlp_base.layers.{l}.weight", f"mlp_base.layers.{l}.bias"))
+    head = lambda n: lin(h, f"field_output_{n}.net.weight", f"field_output_{n}.net.bias")  # noqa: E731
+    raw = head("density")
+    out = {"raw": raw, "density": F.softplus(raw + 0.5)}
+    out["pred_normals"] = F.normalize(-F.normalize(head("normals"), dim=-1), dim=-1)
+    rr = head("roughness")
+    out["rs"], out["rp"] = torch.sigmoid(rr), F.softplus(rr)
+    out["diff"], out["tint"] = torch.sigmoid(head("diff")), torch.sigmoid(head("tint"))
+    bott = head("bottleneck")
+    ide = torch.zeros(*h.shape[:-1], 34) if zero_ide else R.ide(dirs, out["rp"])
+    mid_h = F.relu(lin(torch.cat([ide, bott], -1), "mlp_mid.layers.0.weight", "mlp_mid.layers.0.bias"))
+    out["mid"] = torch.sigmoid(lin(mid_h, "field_output_mid.net.weight", "field_output_mid.net.bias"))
+    out["rgb"] = out["diff"] + out["tint"] * out["mid"]
+    return out
+
+
+def _setup(n, s, seed, kind="uniform", area=3.2e-6):
+    torch.manual_seed(seed)
+    field = R.OracleField().eval()
+    o, d, pa, _ = synthetic_rays(n, seed, pixel_area=area)
+    g = torch.Generator().manual_seed(seed + 1)
+    if kind == "uniform":
+        nears, fars = torch.full((n, 1), 2.0), torch.full((n, 1), 6.0)
+    else:
+        nears, fars = torch.zeros(n, 1), torch.full((n, 1), 256.0)
+    _, bins = R.spaced_bins(nears, fars, s, kind, torch.rand(n, s + 1, generator=g))
+    return field, o, d, pa, bins
+
+
+@pytest.mark.parametrize("n,s,kind,area", [(8, 64, "uniform", 3.2e-6), (37, 24, "uniform", 8.1e-7),
+                                          (300, 128, "uniform", 3.2e-6), (64, 64, "reciprocal", 0.05),
+                                          (3, 5, "uniform", 3.2e-6)])
+def test_field_forward_matches_oracle(n, s, kind, area):
+    field, o, d, pa, bins = _setup(n, s, 11 + n, kind, area)
+    wblob, bias = packing.pack_field(field.state_dict())
+    sigma, feat = ops.field_forward(wblob.cuda(), bias.cuda(), o.cuda(), d.cuda(), pa.cuda(), bins.cuda())
+    torch.cuda.synchronize()
+    sigma, feat = sigma.cpu(), feat.cpu()
+    ex = lambda x: x[:, None, :].expand(n, s, x.shape[-1])  # noqa: E731
+    with torch.no_grad():
+        mean, cov = R.frustum_gaussian(ex(o), ex(d), bins[:, :-1, None], bins[:, 1:, None], ex(pa))
+        mean, cov = R.contract(mean, cov)
+        ref = field.point_heads(mean, cov, ex(d), primary=True)
+        emu = bf16_field(field, mean, cov, ex(d))
+    # (ii) bf16-emulated reference: tight
+    torch.testing.assert_close(feat[..., ops.F_RAW_DENSITY], emu["raw"][..., 0], rtol=2e-2, atol=4e-3)
+    torch.testing.assert_close(feat[..., ops.F_RGB], emu["rgb"], rtol=0, atol=4e-3)
+    torch.testing.assert_close(feat[..., ops.F_DIFF], emu["diff"], rtol=0, atol=3e-3)
+    torch.testing.assert_close(feat[..., ops.F_TINT], emu["tint"], rtol=0, atol=3e-3)
+    torch.testing.assert_close(feat[..., ops.F_ROUGH_SIGMOID], emu["rs"][..., 0], rtol=0, atol=3e-3)
+    # (i) fp32 oracle: the north_star tolerance for the bf16 MLP
+    torch.testing.assert_close(feat[..., ops.F_RGB], ref["rgb"], rtol=0, atol=1e-2)
+    torch.testing.assert_close(sigma, ref["density"][..., 0], rtol=3e-2, atol=1e-2)
+    torch.testing.assert_close(feat[..., ops.F_ROUGH_SOFTPLUS], ref["roughness_softplus"][..., 0], rtol=0, atol=1e-2)
+    cosang = (feat[..., ops.F_NORMAL] * ref["pred_normals"]).sum(-1)
+    assert cosang.min() > 0.995
+    torch.testing.assert_close(feat[..., ops.F_NDOTD], ref["n_dot_d"][..., 0], rtol=0, atol=3e-2)
+
+
+def test_inf_color_matches_oracle():
+    torch.manual_seed(5)
+    field = R.OracleField().eval()
+    m = 200
+    w = F.normalize(torch.randn(m, 3), dim=-1)
+    sq = torch.rand(m, 1) * 0.3 + 1e-3
+    wblob, bias = packing.pack_field(field.state_dict())
+    rgb = ops.field_inf_color(wblob.cuda(), bias.cuda(), w.cuda(), sq.cuda()).cpu()
+    with torch.no_grad():
+        ref = field.inf_color(w, sq)
+    torch.testing.assert_close(rgb, ref, rtol=0, atol=1e-2)
