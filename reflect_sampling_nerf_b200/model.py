@@ -1,0 +1,264 @@
+"""Drop-in model: the per-ray rendering hot path of ReflectSamplingNeRFModel.get_outputs / get_loss_dict
+(reflect_sampling_nerf_model.py:142-430) on the sm_100a kernels.
+
+Same config fields (model.py:46-75), module attribute names (model.py:97-127), output keys / shapes / detach
+status (model.py:233-258,341) and loss keys (model.py:415-428) as the reference.  What differs is only how
+the work is dispatched: each pass over the samples is sampler kernel -> fused field kernel -> compositing
+kernel (3 launches instead of ~3,000 eager ops), the reference's debug prints / quantiles /
+.item() host syncs (App. B Q12) are gone, and the broken eval-image method (Q13) is not reproduced.
+
+When nerfstudio is importable the classes derive from its Model / ModelConfig so `ns-train
+reflect-sampling-nerf` instantiates them through the usual `_target` mechanism; otherwise they fall back to
+plain nn.Module / dataclass bases with the same constructor contract.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Type
+
+import torch
+from torch import Tensor, nn
+from torch.nn import Parameter
+
+from . import ops
+from .field import ReflectSamplingNeRFNerfField
+from .rays import RayBundle
+
+try:  # pragma: no cover - nerfstudio is not installed in the build image
+    from nerfstudio.models.base_model import Model as _BaseModel, ModelConfig as _BaseConfig  # type: ignore
+    HAVE_NERFSTUDIO = True
+except Exception:  # noqa: BLE001
+    HAVE_NERFSTUDIO = False
+
+    @dataclass
+    class _BaseConfig:  # the ModelConfig fields the reference relies on
+        _target: Type = field(default_factory=lambda: ReflectSamplingNeRFModel)
+        enable_collider: bool = True
+        collider_params: Optional[Dict[str, float]] = field(
+            default_factory=lambda: {"near_plane": 2.0, "far_plane": 6.0})
+        eval_num_rays_per_chunk: int = 4096
+
+        def setup(self, **kwargs) -> Any:
+            return self._target(self, **kwargs)
+
+    class _BaseModel(nn.Module):
+        def __init__(self, config, scene_box=None, num_train_data: int = 0, **kwargs) -> None:
+            super().__init__()
+            self.config = config
+            self.scene_box = scene_box
+            self.num_train_data = num_train_data
+            self.kwargs = kwargs
+            self.collider = None
+            self.populate_modules()
+            self.device_indicator_param = nn.Parameter(torch.empty(0))
+
+        @property
+        def device(self):
+            return self.device_indicator_param.device
+
+        def populate_modules(self):
+            pass
+
+        def forward(self, ray_bundle):
+            if self.collider is not None:
+                ray_bundle = self.collider(ray_bundle)
+            return self.get_outputs(ray_bundle)
+
+
+LOSS_COEFFICIENTS = {  # model.py:56-69
+    "loss_low_coarse": 1e-1, "loss_low_fine": 1e-1, "loss_mid_coarse": 1.0, "loss_mid_fine": 1.0,
+    "loss_reflect_low_coarse": 1e-1, "loss_reflect_low_fine": 1e-1,
+    "loss_reflect_mid_coarse": 1.0, "loss_reflect_mid_fine": 1.0,
+    "predicted_normal_loss_coarse": 3e-5, "predicted_normal_loss_fine": 3e-4,
+    "orientation_loss_coarse": 1e-2, "orientation_loss_fine": 1e-1,
+}
+
+
+@dataclass
+class ReflectSamplingNeRFModelConfig(_BaseConfig):
+    """model.py:38-75."""
+    num_coarse_samples: int = 128
+    num_importance_samples: int = 128
+    num_reflect_coarse_samples: int = 64
+    num_reflect_importance_samples: int = 64
+    loss_coefficients: Dict[str, float] = field(default_factory=lambda: dict(LOSS_COEFFICIENTS))
+    enable_temporal_distortion: bool = False          # never read by the reference either
+    temporal_distortion_params: Dict[str, Any] = field(default_factory=lambda: {"kind": "dnerf"})
+    _target: Type = field(default_factory=lambda: ReflectSamplingNeRFModel)
+
+
+class _NearFarCollider(nn.Module):
+    """nerfstudio NearFarCollider: eval resets the near plane to 0."""
+
+    def __init__(self, near_plane: float, far_plane: float) -> None:
+        super().__init__()
+        self.near_plane, self.far_plane = near_plane, far_plane
+
+    def forward(self, ray_bundle):
+        if ray_bundle.nears is not None and ray_bundle.fars is not None:
+            return ray_bundle
+        ones = torch.ones_like(ray_bundle.origins[..., 0:1])
+        ray_bundle.nears = ones * (self.near_plane if self.training else 0.0)
+        ray_bundle.fars = ones * self.far_plane
+        return ray_bundle
+
+
+class _Sampler(nn.Module):
+    """Holds the sampler hyper-parameters under the reference's attribute names (model.py:109-112); the work is
+    ops.sample_spaced / ops.pdf_resample.  `injected_rand` lets parity tests supply the stratification noise."""
+
+    def __init__(self, num_samples: int, kind: int) -> None:
+        super().__init__()
+        self.num_samples, self.kind = num_samples, kind
+        self.injected_rand: Optional[Tensor] = None
+
+    def noise(self, n: int, device) -> Optional[Tensor]:
+        if not self.training:
+            return None
+        if self.injected_rand is not None:
+            return self.injected_rand.to(device)
+        return torch.rand(n, self.num_samples + 1, device=device)
+
+
+class ReflectSamplingNeRFModel(_BaseModel):
+    """B200-native ReflectSamplingNeRF model."""
+
+    config: ReflectSamplingNeRFModelConfig
+
+    def __init__(self, config: ReflectSamplingNeRFModelConfig, **kwargs) -> None:
+        self.field = None
+        assert config.collider_params is not None, "MipNeRF model requires bounding box collider parameters."
+        super().__init__(config=config, **kwargs)
+
+    def populate_modules(self):
+        super().populate_modules()
+        if not HAVE_NERFSTUDIO and self.config.enable_collider:
+            self.collider = _NearFarCollider(self.config.collider_params["near_plane"],
+                                             self.config.collider_params["far_plane"])
+        self.field = ReflectSamplingNeRFNerfField()
+        c = self.config
+        self.sampler_uniform = _Sampler(c.num_coarse_samples, ops.UNIFORM)
+        self.sampler_pdf = _Sampler(c.num_importance_samples, ops.UNIFORM)
+        self.sampler_reciprocal = _Sampler(c.num_reflect_coarse_samples, ops.RECIPROCAL)
+        self.sampler_reflect_pdf = _Sampler(c.num_reflect_importance_samples, ops.RECIPROCAL)
+        self.far = 2 ** 8
+        self.near = 1.0 / 16
+        self.background_color = torch.tensor([1.0, 1.0, 1.0])   # colors.WHITE (model.py:117)
+        self.rgb_loss = nn.MSELoss()
+
+    def get_param_groups(self) -> Dict[str, List[Parameter]]:
+        if self.field is None:
+            raise ValueError("populate_fields() must be called before get_param_groups")
+        return {"fields": list(self.field.parameters())}
+
+    def set_jitter(self, uniform=None, pdf=None, reciprocal=None, reflect_pdf=None) -> None:
+        self.sampler_uniform.injected_rand = uniform
+        self.sampler_pdf.injected_rand = pdf
+        self.sampler_reciprocal.injected_rand = reciprocal
+        self.sampler_reflect_pdf.injected_rand = reflect_pdf
+
+    # ------------------------------------------------------------------------------------------ one pass
+    def _pass(self, origins, directions, pixel_area, euclid_bins):
+        """sampled bins -> fused field -> compositing (model.py:151-177 and its three repeats)."""
+        f = self.field.evaluate_samples(origins, directions, pixel_area, euclid_bins)
+        w, acc, depth, comp = ops.composite(f["density"], euclid_bins, f["feat"])
+        return f["feat"], w, acc[:, None], depth[:, None], comp
+
+    def get_outputs(self, ray_bundle: RayBundle) -> Dict[str, Tensor]:
+        if self.field is None:
+            raise ValueError("populate_fields() must be called before get_outputs")
+        if torch.is_grad_enabled() and self.training:
+            from .train_path import get_outputs_train   # hand-written backward kernels (autograd.Functions)
+            return get_outputs_train(self, ray_bundle)
+        return self._get_outputs_nograd(ray_bundle)
+
+    @torch.no_grad()
+    def _get_outputs_nograd(self, ray_bundle: RayBundle) -> Dict[str, Tensor]:
+        o, d = ray_bundle.origins, ray_bundle.directions
+        area, nears, fars = ray_bundle.pixel_area, ray_bundle.nears, ray_bundle.fars
+        n, dev = o.shape[0], o.device
+        clip01 = lambda x: torch.clip(x, 0.0, 1.0)  # noqa: E731
+        ev = (lambda x: x) if self.training else clip01   # RGBRenderer clamps in eval mode (App. A.6)
+
+        # A. coarse (model.py:148-177)
+        su, sp = self.sampler_uniform, self.sampler_pdf
+        sp_c, eu_c = ops.sample_spaced(nears, fars, su.num_samples, su.kind, su.noise(n, dev))
+        feat_c, w_c, acc_c, depth_c, comp_c = self._pass(o, d, area, eu_c)
+        rgb_c = clip01(ev(comp_c[:, ops.F_RGB] + (1.0 - acc_c)))
+        # B. fine (model.py:182-211)
+        sp_f, eu_f = ops.pdf_resample(w_c, sp_c, nears, fars, sp.num_samples, sp.kind, rand=sp.noise(n, dev),
+                                      train=self.training)
+        feat_f, w_f, acc_f, depth_f, comp_f = self._pass(o, d, area, eu_f)
+        rgb_f = clip01(ev(comp_f[:, ops.F_RGB] + (1.0 - acc_f)))
+        # C. per-ray quantities of the bounce (model.py:215-229)
+        diff_r = ev(comp_f[:, ops.F_DIFF] + (1.0 - acc_f))        # renderer_rgb, white background
+        tint_r = ev(comp_f[:, ops.F_TINT])                        # renderer_factor: "random" -> unblended
+        nrm = comp_f[:, ops.F_NORMAL]
+        nrm_r = nrm / (torch.linalg.norm(nrm, dim=-1, keepdim=True) + 1e-10)   # NormalsRenderer safe_normalize
+        ndd = torch.sum(nrm_r * d, dim=-1, keepdim=True)
+        rough = comp_f[:, ops.F_ROUGH_SIGMOID, None]
+        mask = torch.logical_and(acc_f > 1e-2, ndd < 0).reshape(-1)
+        white = torch.ones(n, 3, device=dev)
+        outputs = {
+            "mid_rgb_coarse": rgb_c, "mid_rgb_fine": rgb_f,
+            "mid_reflect_coarse": white * (1.0 - acc_f), "mid_reflect_fine": white * (1.0 - acc_f),
+            "accumulation_coarse": acc_c, "accumulation_fine": acc_f,
+            "depth_coarse": depth_c, "depth_fine": depth_f,
+            "weights_coarse": w_c[..., None], "weights_fine": w_f[..., None],
+            "pred_normals_coarse": feat_c[..., ops.F_NORMAL], "pred_normals_fine": feat_f[..., ops.F_NORMAL],
+            # eval: normals = predicted normals (model.py:161-162, App. B Q8); the no-grad training forward
+            # has no density gradient to offer either
+            "normals_coarse": feat_c[..., ops.F_NORMAL], "normals_fine": feat_f[..., ops.F_NORMAL],
+            "n_dot_d_coarse": feat_c[..., ops.F_NDOTD, None], "n_dot_d_fine": feat_f[..., ops.F_NDOTD, None],
+            "diff": diff_r, "tint": tint_r, "roughness": rough, "mask": mask,
+        }
+        idx = torch.nonzero(mask).reshape(-1)            # the reference's boolean indexing syncs here too
+        m = idx.numel()
+        if m == 0:                                        # App. B Q11
+            return outputs
+        # D. reflected bundle (model.py:267-290)
+        o2 = o[idx] + depth_f[idx] * d[idx]
+        w_r = torch.nn.functional.normalize(d[idx] - 2 * ndd[idx] * nrm_r[idx], dim=-1)
+        sqr = 2 * torch.abs(ndd[idx]) * rough[idx] ** 2
+        area2 = math.pi * sqr
+        nears2 = torch.zeros(m, 1, device=dev)            # zeros * near (App. B Q4)
+        fars2 = torch.full((m, 1), float(self.far), device=dev)
+        bg = self.field.get_inf_color(w_r, sqr)
+        # E. reflected coarse (model.py:292-313)
+        sr, sq = self.sampler_reciprocal, self.sampler_reflect_pdf
+        sp_rc, eu_rc = ops.sample_spaced(nears2, fars2, sr.num_samples, sr.kind, sr.noise(m, dev))
+        _, w_rc, acc_rc, _, comp_rc = self._pass(o2, w_r, area2, eu_rc)
+        refl_c = ev(comp_rc[:, ops.F_RGB] + bg * (1.0 - acc_rc))
+        outputs["mid_reflect_coarse"][idx] = clip01(diff_r[idx] + tint_r[idx] * refl_c)
+        # F. reflected fine (model.py:317-341)
+        sp_rf, eu_rf = ops.pdf_resample(w_rc, sp_rc, nears2, fars2, sq.num_samples, sq.kind,
+                                        rand=sq.noise(m, dev), train=self.training)
+        _, w_rf, acc_rf, depth_rf, comp_rf = self._pass(o2, w_r, area2, eu_rf)
+        refl_f = ev(comp_rf[:, ops.F_RGB] + bg * (1.0 - acc_rf))
+        outputs["mid_reflect_fine"][idx] = clip01(diff_r[idx] + tint_r[idx] * refl_f)
+        outputs["depth_reflect_fine"] = depth_rf
+        return outputs
+
+    # ------------------------------------------------------------------------------------------ losses
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
+        """model.py:346-430.  blend_background_for_loss_computation is the identity for the tensor (white)
+        background and an RGB ground truth; the .item() prints are dropped (Q12)."""
+        image = batch["image"].to(outputs["mid_rgb_fine"].device)[..., :3]
+        wc, wf = outputs["weights_coarse"], outputs["weights_fine"]
+        sqd = lambda a, b: torch.sum((a - b) ** 2, dim=-1, keepdim=True)   # noqa: E731
+        pos = lambda v: torch.clamp_min(v, 0.0) ** 2                       # noqa: E731
+        loss = {
+            "loss_mid_coarse": self.rgb_loss(image, outputs["mid_rgb_coarse"]),
+            "loss_mid_fine": self.rgb_loss(image, outputs["mid_rgb_fine"]),
+            "loss_reflect_mid_coarse": self.rgb_loss(image, outputs["mid_reflect_coarse"]),
+            "loss_reflect_mid_fine": self.rgb_loss(image, outputs["mid_reflect_fine"]),
+            "predicted_normal_loss_coarse": torch.sum(wc * sqd(outputs["normals_coarse"], outputs["pred_normals_coarse"])),
+            "predicted_normal_loss_fine": torch.sum(wf * sqd(outputs["normals_fine"], outputs["pred_normals_fine"])),
+            "orientation_loss_coarse": torch.sum(wc * pos(outputs["n_dot_d_coarse"])),
+            "orientation_loss_fine": torch.sum(wf * pos(outputs["n_dot_d_fine"])),
+        }
+        for k in loss:   # misc.scale_dict
+            if k in self.config.loss_coefficients:
+                loss[k] = loss[k] * self.config.loss_coefficients[k]
+        return loss
