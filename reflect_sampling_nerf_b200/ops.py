@@ -14,6 +14,10 @@ from torch import Tensor
 from . import _lib
 
 UNIFORM, RECIPROCAL = 0, 1
+# bench.py sets PROFILE to a list to collect (kernel, start event, end event, algorithmic FLOPs) per launch of
+# the dominant kernel on the launching stream; None (default) = no events recorded.
+PROFILE = None
+FLOP_PER_POINT = {0: 1230592, 1: 1225472}   # SURVEY.md §8d (forward; primary figure used for every sample pass)
 
 
 def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
@@ -153,8 +157,15 @@ def field_forward(wblob: Tensor, bias: Tensor, origins: Tensor, dirs: Tensor, pi
         raise ValueError("field_forward: origins/dirs must be [N,3] and pixel_area [N] for bins [N,S+1]")
     sigma = torch.empty(n, s, device=bins.device, dtype=torch.float32)
     feat = torch.empty(n, s, N_FEAT, device=bins.device, dtype=torch.float32)
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("rsn_field_forward", _lib.ptr(wblob), _lib.ptr(bias), MODE_SAMPLES, _lib.ptr(origins), _lib.ptr(dirs),
               _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), _lib.stream())
+    if prof is not None:
+        e1.record()
+        prof.append(("field_fwd_kernel", e0, e1, n * s * FLOP_PER_POINT[0]))
     return sigma, feat
 
 
