@@ -86,6 +86,47 @@ int rsn_composite_bwd(const float* sigma, const float* starts, const float* ends
 int rsn_field_forward(const void* wblob, const float* bias, int mode, const float* origins, const float* dirs,
                       const float* area, const float* bins, int64_t n_rays, int64_t n_samples, float* sigma,
                       float* feat, rsn_stream_t stream);
+/* Training form of rsn_field_forward: additionally writes the activation stash (rsn_field_stash_bytes(N*S)
+ * bytes: per 128-point tile 41 bf16 block images = IPE, the 8 hidden activations, bottleneck, IDE, mid hidden)
+ * that the normals / backward / wgrad kernels read, and aux [N*S,8] = mid rgb (3), raw normal head (3), 2 spare. */
+int rsn_field_forward_train(const void* wblob, const float* bias, int mode, const float* origins,
+                            const float* dirs, const float* area, const float* bins, int64_t n_rays,
+                            int64_t n_samples, float* sigma, float* feat, void* stash, float* aux,
+                            rsn_stream_t stream);
+int64_t rsn_field_stash_bytes(int64_t n_points);
+
+/* ---- K6: density-gradient normals -------------------------------------------------------------------
+ * Replaces Field.get_normals = -normalize(d raw_density / d contracted mean) (autograd.grad through the
+ * density head, the 8 base layers and the IPE with the covariance held constant):
+ *   reflect_sampling_nerf_field.py:125-127,134-135,146-147 ; reflect_sampling_nerf_model.py:159-160,194-195.
+ * wblob_t: transposed bf16 weight blob (rsn_field_blob_t_bytes()), wd_bf16: the density head row as 256 bf16,
+ * x_stash: the stash of the forward pass.  Output normals [N*S,3]. */
+int rsn_field_normals(const void* wblob_t, const void* wd_bf16, const void* x_stash, int64_t n_rays,
+                      int64_t n_samples, float* normals, rsn_stream_t stream);
+int64_t rsn_field_blob_t_bytes(void);
+
+/* ---- K5 backward, dgrad chain -----------------------------------------------------------------------
+ * Replaces the autograd backward of reflect_sampling_nerf_field.py:122-186 (mode 0) / 190-201 (mode 1) for one
+ * pass: from g_sigma [N*S] = dL/d sigma and g_feat [N*S,16] = dL/d feat (forward layout; columns 14,15 are
+ * ignored) to the pre-activation gradient of every Linear, written to dy_stash (rsn_field_dy_stash_bytes) for
+ * rsn_field_wgrad.  feat / aux are the forward outputs.  If g_area != NULL the chain continues through layer 0
+ * and the IPE damping and writes dL/d pixel_area (mode 0) or dL/d sqradius (mode 1) of every POINT [N*S]
+ * (the caller sums over the samples of a ray): the roughness -> cone width path of
+ * reflect_sampling_nerf_model.py:272,286,290. */
+int rsn_field_backward(const void* wblob_t, const void* x_stash, int mode, const float* origins, const float* dirs,
+                       const float* area, const float* bins, int64_t n_rays, int64_t n_samples,
+                       const float* g_sigma, const float* g_feat, const float* feat, const float* aux,
+                       void* dy_stash, float* g_area, rsn_stream_t stream);
+int64_t rsn_field_dy_stash_bytes(int64_t n_points);
+
+/* ---- K5 backward, wgrad -----------------------------------------------------------------------------
+ * dW = dY^T X and db = sum dY of every Linear of the field over all points of a pass, ACCUMULATED (fp32
+ * atomics) into grad_blob, whose regions rsn_field_wgrad_layout describes (HOST pointers: offsets[2j] = dW
+ * offset, offsets[2j+1] = db offset or -1, shapes[2j], shapes[2j+1] = rows, cols; returns the job count). */
+int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_t n_points, float* grad_blob,
+                    rsn_stream_t stream);
+int rsn_field_wgrad_layout(int64_t* host_offsets, int64_t* host_shapes, int64_t* total_floats);
+
 int64_t rsn_field_blob_bytes(void);
 int64_t rsn_field_bias_count(void);
 /* The 16 IPE frequencies 2**linspace(0,16,16) the kernels use (HOST pointer; for the table test). */

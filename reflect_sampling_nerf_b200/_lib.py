@@ -22,6 +22,14 @@ _SIGNATURES = {
     "rsn_composite_fwd": ([P, P, P, I64, P, I64, P, P, P, P, I64, I64, P], c_int),
     "rsn_composite_bwd": ([P, P, P, I64, P, I64, P, P, P, P, P, I64, I64, P], c_int),
     "rsn_field_forward": ([P, P, I32, P, P, P, P, I64, I64, P, P, P], c_int),
+    "rsn_field_forward_train": ([P, P, I32, P, P, P, P, I64, I64, P, P, P, P, P], c_int),
+    "rsn_field_stash_bytes": ([I64], c_int64),
+    "rsn_field_normals": ([P, P, P, I64, I64, P, P], c_int),
+    "rsn_field_blob_t_bytes": ([], c_int64),
+    "rsn_field_backward": ([P, P, I32, P, P, P, P, I64, I64, P, P, P, P, P, P, P], c_int),
+    "rsn_field_dy_stash_bytes": ([I64], c_int64),
+    "rsn_field_wgrad": ([P, P, I64, P, P], c_int),
+    "rsn_field_wgrad_layout": ([P, P, P], c_int),
     "rsn_field_blob_bytes": ([], c_int64),
     "rsn_field_bias_count": ([], c_int64),
     "rsn_ipe_freqs": ([P], c_int),

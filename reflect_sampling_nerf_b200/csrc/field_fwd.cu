@@ -26,6 +26,7 @@
 #include "rsn_common.cuh"
 #include "umma.cuh"
 #include "field_layout.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -64,6 +65,8 @@ struct FwdParams {
   int n_tiles;
   float* sigma;             // [P]
   float* feat;              // [P][16]
+  uint8_t* stash;           // training: [n_tiles][STASH_BLOCKS][16 KB] activation block images, or NULL
+  float* aux;               // training: [P][8] = mid rgb (3), raw normal head (3), 2 spare, or NULL
 };
 
 struct Barriers {
@@ -100,9 +103,14 @@ __device__ __forceinline__ float sin_reduced(float s) {
 }
 
 // 8 encoded columns -> one 16-byte chunk of the row
-__device__ __forceinline__ void store_chunk(uint32_t row_saddr, int row, int chunk, const float (&f)[8]) {
-  sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+// (and, when training, into the same position of the stashed copy of the block in global memory)
+__device__ __forceinline__ void store_chunk(uint32_t row_saddr, int row, int chunk, const float (&f)[8],
+                                            uint8_t* stash_row = nullptr) {
+  const uint32_t off = (uint32_t)((chunk ^ (row & 7)) << 4);
+  const uint4 v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+  sts128(row_saddr + off, v.x, v.y, v.z, v.w);
+  if (stash_row) *reinterpret_cast<uint4*>(stash_row + off) = v;
 }
 
 // ---------------------------------------------------------------------------------------------- prologue
@@ -174,8 +182,10 @@ __device__ __forceinline__ void frustum_gaussian_contracted(const float o[3], co
 // IPE of (xm, diag dg) -> bf16 row of the enc operand (columns 0..111; 99..111 zero).
 // NeRFEncoding.forward with covs: s = fl(fl(2pi x) f), v = fl(diag fl(f f)),
 // enc = exp(-v/2) sin(s | s + pi/2), raw xyz appended last.
-__device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const float (&xm)[3], const float (&dg)[3]) {
+__device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const float (&xm)[3], const float (&dg)[3],
+                                           uint8_t* stash_enc) {
   const uint32_t row0 = enc_saddr + (uint32_t)row * 128u;
+  uint8_t* srow = stash_enc ? stash_enc + (size_t)row * 128 : nullptr;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -194,14 +204,20 @@ __device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const fl
           f8[i] = (e < 24.f) ? __expf(-e) * sin_reduced(s) : 0.f;
         }
         const int j = half * 6 + a * 2 + kk;  // 16-byte chunk index along the 112 columns
-        store_chunk(row0 + (uint32_t)(j >> 3) * BLOCK_BYTES, row, j & 7, f8);
+        store_chunk(row0 + (uint32_t)(j >> 3) * BLOCK_BYTES, row, j & 7, f8,
+                    srow ? srow + (size_t)(j >> 3) * BLOCK_BYTES : nullptr);
       }
     }
   }
   const float f12[8] = {xm[0], xm[1], xm[2], 0.f, 0.f, 0.f, 0.f, 0.f};
   const float f13[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  store_chunk(row0 + BLOCK_BYTES, row, 12 & 7, f12);
-  store_chunk(row0 + BLOCK_BYTES, row, 13 & 7, f13);
+  uint8_t* s1 = srow ? srow + BLOCK_BYTES : nullptr;
+  store_chunk(row0 + BLOCK_BYTES, row, 12 & 7, f12, s1);
+  store_chunk(row0 + BLOCK_BYTES, row, 13 & 7, f13, s1);
+  if (s1) {  // columns 112..127 are never read by the forward MMAs but the wgrad reads whole blocks
+    store_chunk(row0 + BLOCK_BYTES, row, 14 & 7, f13, s1);
+    store_chunk(row0 + BLOCK_BYTES, row, 15 & 7, f13, s1);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- IDE
@@ -263,7 +279,7 @@ __device__ __forceinline__ void ide_features(const float d[3], float rho, float 
 // 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> activation block `blk`.
 template <bool RELU>
 __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, const float* __restrict__ bias,
-                                               uint32_t blk_saddr, int row) {
+                                               uint32_t blk_saddr, int row, uint8_t* stash_blk) {
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
@@ -288,7 +304,10 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, const floa
         pk[q * 2 + 1] = RELU ? pack_relu_bf16x2(x2, x3) : pack_bf16x2(x2, x3);
       }
       const int chunk = h * 4 + c;
-      sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      const uint32_t off = (uint32_t)((chunk ^ (row & 7)) << 4);
+      sts128(row_saddr + off, pk[0], pk[1], pk[2], pk[3]);
+      if (stash_blk)
+        *reinterpret_cast<uint4*>(stash_blk + (size_t)row * 128 + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -481,6 +500,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int pt = tile * TILE + row;
       const bool valid = pt < p.n_points;
+      uint8_t* const st = p.stash ? p.stash + (size_t)tile * STASH_BLOCKS * BLOCK_BYTES : nullptr;
+      auto sblk = [&](int b) -> uint8_t* { return st ? st + (size_t)b * BLOCK_BYTES : nullptr; };
       auto wait_acc = [&]() {
         mbar_wait(&bars.acc_full[buf], (af_phase >> buf) & 1u);
         af_phase ^= (1u << buf);
@@ -495,7 +516,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         for (int g = 0; g < 4; ++g) {
           epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_BASE + l * 256 + g * 64,
-                               s_act + g * BLOCK_BYTES, row);
+                               s_act + g * BLOCK_BYTES, row, sblk(STASH_H + 4 * l + g));
           publish(&bars.act_ready[g]);
         }
         buf ^= 1;
@@ -506,7 +527,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         for (int g = 0; g < 4; ++g) {
           epilogue_group<false>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_BOTT + g * 64,
-                                s_act + g * BLOCK_BYTES, row);
+                                s_act + g * BLOCK_BYTES, row, sblk(STASH_BOTT + g));
           publish(&bars.act_ready[g]);
         }
         uint32_t hv[16];
@@ -559,9 +580,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         for (int c = 0; c < 6; ++c) {
           const float f8[8] = {t[c * 8 + 0], t[c * 8 + 1], t[c * 8 + 2], t[c * 8 + 3],
                                t[c * 8 + 4], t[c * 8 + 5], t[c * 8 + 6], t[c * 8 + 7]};
-          store_chunk(ide_row, row, c, f8);
+          store_chunk(ide_row, row, c, f8, st ? sblk(STASH_IDE) + (size_t)row * 128 : nullptr);
+        }
+        if (st) {
+          uint8_t* ir = sblk(STASH_IDE) + (size_t)row * 128;
+          *reinterpret_cast<uint4*>(ir + ((6 ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(ir + ((7 ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
         }
         publish(&bars.ide_ready);
+        if (valid && p.aux) {
+          p.aux[(size_t)pt * 8 + 3] = h[1];
+          p.aux[(size_t)pt * 8 + 4] = h[2];
+          p.aux[(size_t)pt * 8 + 5] = h[3];
+        }
         if (valid) {
           p.sigma[pt] = sigma;
           float4* fo = reinterpret_cast<float4*>(p.feat + (size_t)pt * N_FEAT);
@@ -576,7 +607,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         for (int g = 0; g < 2; ++g) {
           epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_MID + g * 64,
-                               s_act + g * BLOCK_BYTES, row);
+                               s_act + g * BLOCK_BYTES, row, sblk(STASH_MIDH + g));
           publish(&bars.act_ready[g]);
         }
         buf ^= 1;
@@ -597,6 +628,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           for (int a = 0; a < 3; ++a) rgb[a] = (p.mode == 0) ? diff[a] + tint[a] * mid[a] : mid[a];
           float4* fo = reinterpret_cast<float4*>(p.feat + (size_t)pt * N_FEAT);
           fo[0] = make_float4(rgb[0], rgb[1], rgb[2], diff[0]);  // cols 0..3
+          if (p.aux) {
+            p.aux[(size_t)pt * 8 + 0] = mid[0];
+            p.aux[(size_t)pt * 8 + 1] = mid[1];
+            p.aux[(size_t)pt * 8 + 2] = mid[2];
+          }
         }
         buf ^= 1;
       }
@@ -633,7 +669,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         }
       }
       mbar_wait(&bars.enc_empty[eb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      encode_row(s_enc + (uint32_t)eb * 2 * BLOCK_BYTES, row, xm, dg);
+      encode_row(s_enc + (uint32_t)eb * 2 * BLOCK_BYTES, row, xm, dg,
+                 p.stash ? p.stash + ((size_t)tile * STASH_BLOCKS + STASH_ENC) * BLOCK_BYTES : nullptr);
       fence_proxy_async();
       mbar_arrive(&bars.enc_full[eb]);
     }
@@ -655,9 +692,14 @@ extern "C" int rsn_ipe_freqs(float* host_out16) {
 extern "C" int64_t rsn_field_blob_bytes(void) { return (int64_t)FWD_BLOB_BYTES; }
 extern "C" int64_t rsn_field_bias_count(void) { return (int64_t)N_BIAS; }
 
-extern "C" int rsn_field_forward(const void* wblob, const float* bias, int mode, const float* origins,
-                                 const float* dirs, const float* area, const float* bins, int64_t n_rays,
-                                 int64_t n_samples, float* sigma, float* feat, cudaStream_t stream) {
+extern "C" int64_t rsn_field_stash_bytes(int64_t n_points) {
+  return ((n_points + TILE - 1) / TILE) * (int64_t)STASH_BLOCKS * BLOCK_BYTES;
+}
+
+extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int mode, const float* origins,
+                                       const float* dirs, const float* area, const float* bins, int64_t n_rays,
+                                       int64_t n_samples, float* sigma, float* feat, void* stash, float* aux,
+                                       cudaStream_t stream) {
   RSN_ARG(mode == 0 || mode == 1, "rsn_field_forward: mode must be 0 (samples) or 1 (infinity colour)");
   RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_field_forward: bad shape");
   RSN_ARG(mode == 0 || n_samples == 1, "rsn_field_forward: mode 1 takes one point per ray");
@@ -680,6 +722,9 @@ extern "C" int rsn_field_forward(const void* wblob, const float* bias, int mode,
   p.n_tiles = (p.n_points + TILE - 1) / TILE;
   p.sigma = sigma;
   p.feat = feat;
+  p.stash = (uint8_t*)stash;
+  p.aux = aux;
+  RSN_ARG(((uintptr_t)stash & 15) == 0, "rsn_field_forward: stash must be 16-byte aligned");
   const size_t smem = SMEM_TOTAL + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -690,4 +735,11 @@ extern "C" int rsn_field_forward(const void* wblob, const float* bias, int mode,
   field_fwd_kernel<<<grid, NUM_THREADS, smem, stream>>>(p);
   RSN_LAUNCH_CHECK("field_fwd_kernel");
   return 0;
+}
+
+extern "C" int rsn_field_forward(const void* wblob, const float* bias, int mode, const float* origins,
+                                 const float* dirs, const float* area, const float* bins, int64_t n_rays,
+                                 int64_t n_samples, float* sigma, float* feat, cudaStream_t stream) {
+  return rsn_field_forward_train(wblob, bias, mode, origins, dirs, area, bins, n_rays, n_samples, sigma, feat,
+                                 nullptr, nullptr, stream);
 }

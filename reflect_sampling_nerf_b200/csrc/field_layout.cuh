@@ -36,6 +36,17 @@ __host__ __device__ constexpr uint32_t fwd_chunk_bytes(int c) {
   return c < 36 ? 32768u : c == 36 ? 8192u : c < 39 ? 32768u : c == 39 ? 16384u : 4096u;
 }
 
+// ---- transposed weight blob of the dgrad chains: B[n = input feature][k = output feature] K-block images ----
+constexpr uint32_t BT_RGB = 0;                         // [128 mid-hidden][64 (3 used)]            16 KB
+constexpr uint32_t BT_MID = 16384;                     // [256 bottleneck][128 mid-hidden]         2 x 32 KB
+constexpr uint32_t BT_BOTT = BT_MID + 2 * 32768;       // [256 emb][256 bottleneck]                4 x 32 KB
+constexpr uint32_t BT_HEADS = BT_BOTT + 4 * 32768;     // [256 emb][64 (11 used)]                  32 KB
+constexpr uint32_t BT_LBASE = BT_HEADS + 32768;        // base layers 1..7 (layer 4: hidden part)  7 x 4 x 32 KB
+__host__ __device__ constexpr uint32_t BT_L(int l) { return BT_LBASE + (uint32_t)(l - 1) * 131072u; }
+constexpr uint32_t BT_L4E = BT_LBASE + 7 * 131072;     // [128 enc (99 used)][256]                 4 x 16 KB
+constexpr uint32_t BT_L0 = BT_L4E + 65536;             // [128 enc (99 used)][256]                 4 x 16 KB
+constexpr uint32_t BWD_BLOB_BYTES = BT_L0 + 65536;     // 1,294,336
+
 // ---- bias vector (fp32) -----------------------------------------------------------------------------
 constexpr int BIAS_BASE = 0;          // 8 x 256
 constexpr int BIAS_BOTT = 2048;       // 256
@@ -43,6 +54,21 @@ constexpr int BIAS_HEAD = 2304;       // 16
 constexpr int BIAS_MID = 2320;        // 128
 constexpr int BIAS_RGB = 2448;        // 16
 constexpr int N_BIAS = 2464;
+
+// ---- training stash: per tile, STASH_BLOCKS activation block images of 16 KB (written by the forward) ----
+constexpr int STASH_ENC = 0;     // 2 blocks: IPE (columns 99..127 zero)
+constexpr int STASH_H = 2;       // + 4*l + g : post-ReLU output of base layer l, 64-column group g
+constexpr int STASH_BOTT = 34;   // 4 blocks: bottleneck (no activation)
+constexpr int STASH_IDE = 38;    // 1 block: IDE (columns 34..63 zero)
+constexpr int STASH_MIDH = 39;   // 2 blocks: mid hidden (post-ReLU)
+constexpr int STASH_BLOCKS = 41;
+
+// ---- dgrad stash: per tile, DY_BLOCKS block images of the pre-activation gradients (written by the dgrad chain)
+constexpr int DY_SEED = 0;       // 1 block: columns 0-15 d(rgb head pre-activation), 16-31 d(heads pre-activation)
+constexpr int DY_MID = 1;        // 2 blocks: d(mid hidden pre-activation), 128 columns
+constexpr int DY_BOTT = 3;       // 4 blocks: d(bottleneck)
+constexpr int DY_H = 7;          // + 4*l + g : d(pre-activation of base layer l)
+constexpr int DY_BLOCKS = 39;
 
 // ---- per-point feature row written by the forward kernel ([P][16] fp32) ------------------------------
 // 0-2 rgb = diff + tint*mid | 3-5 diff | 6-8 tint | 9-11 pred_normal | 12 sigmoid(rough) | 13 n.d

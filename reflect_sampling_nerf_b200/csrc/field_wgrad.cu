@@ -1,0 +1,275 @@
+// Weight / bias gradients of the field: dW_l = dY_l^T X_l and db_l = sum_points dY_l, accumulated over every
+// 128-point tile of a pass.  SURVEY.md §2.4 K5 (bwd, wgrad), §8 rows a8, a9, a12.
+//
+// Replaces the autograd wgrad of every nn.Linear the reference evaluates per sample:
+//   mlp_base.layers.0-7, field_output_{density,normals,roughness,diff,tint,bottleneck}, mlp_mid.layers.0,
+//   field_output_mid            reflect_sampling_nerf_field.py:54-86 (forward at field.py:132-186)
+//
+// Operands are the block images the forward (X, csrc/field_fwd.cu stash) and the dgrad chain (dY,
+// csrc/field_bwd.cu) left in HBM: [128 points][64 features] bf16, 128-byte swizzled.  Read "transposed"
+// (MN-major UMMA descriptors, features contiguous) they are directly the A = dY^T and B = X operands of
+//   D[out, in] (+)= sum over 16 points  dY[pt, out] * X[pt, in]            (tcgen05.mma, fp32 in TMEM)
+// One CTA owns one job = (layer, all <=256 output features, <=256 input features) and a contiguous range of
+// tiles (split-K over points); its accumulators stay in TMEM for the whole range and are flushed once with
+// fp32 atomics.  db comes from the same shared-memory dY slabs, summed by the otherwise idle epilogue warps.
+//
+// HBM-bound: algorithmic bytes = (m_blocks + n_blocks) * 16 KB per tile and job; 95 blocks = 1.52 MB per tile
+// over the 12 jobs (11.9 KB per point) against 2 * 618k * 128 = 158 MFLOP per tile.
+#include "rsn_common.cuh"
+#include "umma.cuh"
+#include "field_layout.cuh"
+#include <algorithm>
+
+namespace {
+
+using namespace umma;
+using namespace rsnf;
+
+constexpr int W_THREADS = 192;      // warp 0 producer, warp 1 MMA issuer, warps 2-5 db + epilogue
+constexpr int SLAB_ROWS = 32;       // points per pipeline slab (2 K-steps)
+constexpr int SLAB_BLOCK_BYTES = SLAB_ROWS * 128;
+constexpr int SLAB_BYTES = 8 * SLAB_BLOCK_BYTES;   // up to 4 dY + 4 X blocks
+constexpr int W_STAGES = 6;
+constexpr int MAX_JOBS = 16;
+
+struct WJob {
+  int a_blk, m_blocks;   // first dY block of the job inside a dY tile; 2 (M=128) or 4 (M=256)
+  int b_blk, n_blocks;   // first X block inside a stash tile; 1, 2 or 4 (N = 64, 128, 256)
+  int out_off, db_off;   // float offsets into the gradient blob: dW [64 m_blocks][64 n_blocks], db or -1
+  int cta_begin, n_ctas;
+};
+struct WParams {
+  const uint8_t* x;      // forward stash  [n_tiles][STASH_BLOCKS][16 KB]
+  const uint8_t* dy;     // dgrad stash    [n_tiles][DY_BLOCKS][16 KB]
+  int n_tiles;
+  float* grad;
+  int n_jobs;
+  WJob jobs[MAX_JOBS];
+};
+
+struct WBarriers {
+  uint64_t full[W_STAGES], empty[W_STAGES];
+  uint64_t acc_full;
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_constant__ WParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ WBarriers bars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int j = 0;
+  for (int i = 0; i < p.n_jobs; ++i)
+    if ((int)blockIdx.x >= p.jobs[i].cta_begin && (int)blockIdx.x < p.jobs[i].cta_begin + p.jobs[i].n_ctas) j = i;
+  const WJob job = p.jobs[j];
+  const int split = (int)blockIdx.x - job.cta_begin;
+  const int t0 = (int)(((int64_t)p.n_tiles * split) / job.n_ctas);
+  const int t1 = (int)(((int64_t)p.n_tiles * (split + 1)) / job.n_ctas);
+  const int mb = job.m_blocks, nb = job.n_blocks;
+  const int n_slabs = (t1 - t0) * (TILE / SLAB_ROWS);
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < W_STAGES; ++i) {
+        mbar_init(&bars.full[i], 1);
+        mbar_init(&bars.empty[i], 1 + 4);   // tcgen05.commit + one arrival per db warp
+      }
+      mbar_init(&bars.acc_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars.tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        const uint8_t* dyt = p.dy + ((size_t)t * DY_BLOCKS + job.a_blk) * BLOCK_BYTES;
+        const uint8_t* xt = p.x + ((size_t)t * STASH_BLOCKS + job.b_blk) * BLOCK_BYTES;
+        for (int s = 0; s < TILE / SLAB_ROWS; ++s) {
+          mbar_wait(&bars.empty[stage], phase ^ 1);
+          mbar_expect_tx(&bars.full[stage], (uint32_t)(mb + nb) * SLAB_BLOCK_BYTES);
+          uint8_t* dst = smem + (size_t)stage * SLAB_BYTES;
+          for (int i = 0; i < mb; ++i)
+            bulk_g2s(dst + i * SLAB_BLOCK_BYTES, dyt + (size_t)i * BLOCK_BYTES + s * SLAB_BLOCK_BYTES,
+                     SLAB_BLOCK_BYTES, &bars.full[stage]);
+          for (int i = 0; i < nb; ++i)
+            bulk_g2s(dst + (mb + i) * SLAB_BLOCK_BYTES, xt + (size_t)i * BLOCK_BYTES + s * SLAB_BLOCK_BYTES,
+                     SLAB_BLOCK_BYTES, &bars.full[stage]);
+          if (++stage == W_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_slabs > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = instr_desc_bf16(128, nb * 64, 1, 1);
+      for (int s = 0; s < n_slabs; ++s) {
+        mbar_wait(&bars.full[stage], phase);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + (size_t)stage * SLAB_BYTES);
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t db = smem_desc_sw128(base + mb * SLAB_BLOCK_BYTES + ks * 2048, SLAB_BLOCK_BYTES, 1024);
+          for (int h = 0; h < mb / 2; ++h) {
+            const uint64_t da = smem_desc_sw128(base + (2 * h) * SLAB_BLOCK_BYTES + ks * 2048, SLAB_BLOCK_BYTES, 1024);
+            mma_bf16_ss(tmem + h * 256, da, db, idesc, (s | ks) != 0);
+          }
+        }
+        mma_commit(&bars.empty[stage]);
+        if (++stage == W_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      mma_commit(&bars.acc_full);
+    }
+  } else {
+    // ---- db: column sums of the dY slabs while they sit in shared memory; then the dW flush
+    const int t = threadIdx.x - 64;          // 0..127 -> feature pair (2t, 2t+1) of the job's M features
+    const int blk = t >> 5, pr = t & 31;
+    const bool db_active = blk < mb;
+    float a0 = 0.f, a1 = 0.f;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < n_slabs; ++s) {
+      mbar_wait(&bars.full[stage], phase);
+      if (db_active) {
+        const uint8_t* src = smem + (size_t)stage * SLAB_BYTES + blk * SLAB_BLOCK_BYTES;
+#pragma unroll 8
+        for (int r = 0; r < SLAB_ROWS; ++r) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(src + r * 128 + ((((pr >> 2) ^ (r & 7)) << 4) | ((pr & 3) << 2)));
+          a0 += __uint_as_float(v << 16);
+          a1 += __uint_as_float(v & 0xffff0000u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.empty[stage]);
+      if (++stage == W_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (n_slabs > 0) {
+      if (db_active && job.db_off >= 0) {
+        atomicAdd(p.grad + job.db_off + 2 * t, a0);
+        atomicAdd(p.grad + job.db_off + 2 * t + 1, a1);
+      }
+      mbar_wait(&bars.acc_full, 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int N = nb * 64;
+      for (int h = 0; h < mb / 2; ++h) {
+        float* out = p.grad + job.out_off + (size_t)(h * 128 + row) * N;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 256 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(out + c0 + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// The 12 jobs of one pass.  Gradient blob regions (fp32): dW [64 m_blocks][64 n_blocks] row-major, then db.
+struct JobSpec {
+  int a_blk, m_blocks, b_blk, n_blocks, has_db;
+};
+const JobSpec kJobs[] = {
+    {DY_H + 0, 4, STASH_ENC, 2, 1},             //  0  layer 0            x enc
+    {DY_H + 4, 4, STASH_H + 0, 4, 1},           //  1  layer 1            x h0
+    {DY_H + 8, 4, STASH_H + 4, 4, 1},           //  2  layer 2            x h1
+    {DY_H + 12, 4, STASH_H + 8, 4, 1},          //  3  layer 3            x h2
+    {DY_H + 16, 4, STASH_ENC, 2, 0},            //  4  layer 4 (enc part) x enc
+    {DY_H + 16, 4, STASH_H + 12, 4, 1},         //  5  layer 4 (hidden)   x h3
+    {DY_H + 20, 4, STASH_H + 16, 4, 1},         //  6  layer 5            x h4
+    {DY_H + 24, 4, STASH_H + 20, 4, 1},         //  7  layer 6            x h5
+    {DY_H + 28, 4, STASH_H + 24, 4, 1},         //  8  layer 7            x h6
+    {DY_BOTT, 4, STASH_H + 28, 4, 1},           //  9  bottleneck         x h7
+    {DY_SEED, 2, STASH_H + 28, 4, 1},           // 10  heads (rows 16-31) x h7   (rows 0-15: unused product)
+    {DY_SEED, 2, STASH_MIDH, 2, 0},             // 11  rgb (rows 0-15)    x mid hidden (db from job 10's sums)
+    {DY_MID, 2, STASH_BOTT, 4, 1},              // 12  mid                x bottleneck
+    {DY_MID, 2, STASH_IDE, 1, 0},               // 13  mid (IDE part)     x IDE
+};
+constexpr int kNumJobs = sizeof(kJobs) / sizeof(kJobs[0]);
+static_assert(kNumJobs <= MAX_JOBS, "job table too small");
+
+}  // namespace
+
+extern "C" int64_t rsn_field_dy_stash_bytes(int64_t n_points) {
+  return ((n_points + TILE - 1) / TILE) * (int64_t)DY_BLOCKS * BLOCK_BYTES;
+}
+
+// Float offsets of every job's dW / db region inside the gradient blob: out[2*j] = dW offset, out[2*j+1] = db
+// offset or -1.  Returns the number of jobs; *total_floats = blob size.  HOST pointers.
+extern "C" int rsn_field_wgrad_layout(int64_t* host_offsets, int64_t* host_shapes, int64_t* total_floats) {
+  int64_t off = 0;
+  for (int j = 0; j < kNumJobs; ++j) {
+    const int m = kJobs[j].m_blocks * 64, n = kJobs[j].n_blocks * 64;
+    if (host_offsets) host_offsets[2 * j] = off;
+    if (host_shapes) host_shapes[2 * j] = m, host_shapes[2 * j + 1] = n;
+    off += (int64_t)m * n;
+    if (host_offsets) host_offsets[2 * j + 1] = kJobs[j].has_db ? off : -1;
+    if (kJobs[j].has_db) off += m;
+  }
+  if (total_floats) *total_floats = off;
+  return kNumJobs;
+}
+
+extern "C" int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_t n_points, float* grad_blob,
+                               cudaStream_t stream) {
+  RSN_ARG(n_points >= 0, "rsn_field_wgrad: bad shape");
+  if (n_points == 0) return 0;
+  RSN_ARG(x_stash && dy_stash && grad_blob, "rsn_field_wgrad: null pointer");
+  RSN_ARG(((uintptr_t)x_stash & 15) == 0 && ((uintptr_t)dy_stash & 15) == 0, "rsn_field_wgrad: stashes must be 16-byte aligned");
+  WParams p;
+  p.x = (const uint8_t*)x_stash;
+  p.dy = (const uint8_t*)dy_stash;
+  p.n_tiles = (int)((n_points + TILE - 1) / TILE);
+  p.grad = grad_blob;
+  p.n_jobs = kNumJobs;
+  // CTAs per job proportional to the job's bytes per tile (the kernel is HBM-bound), one wave of <= #SM CTAs
+  const int sms = rsn_num_sms();
+  int units = 0;
+  for (int j = 0; j < kNumJobs; ++j) units += kJobs[j].m_blocks + kJobs[j].n_blocks;
+  int64_t off = 0;
+  int cta = 0;
+  for (int j = 0; j < kNumJobs; ++j) {
+    const int u = kJobs[j].m_blocks + kJobs[j].n_blocks;
+    int n = std::max(1, (u * sms) / units);
+    n = std::min(n, p.n_tiles);
+    WJob& w = p.jobs[j];
+    w.a_blk = kJobs[j].a_blk, w.m_blocks = kJobs[j].m_blocks, w.b_blk = kJobs[j].b_blk, w.n_blocks = kJobs[j].n_blocks;
+    w.out_off = (int)off;
+    off += (int64_t)w.m_blocks * 64 * w.n_blocks * 64;
+    w.db_off = kJobs[j].has_db ? (int)off : -1;
+    if (kJobs[j].has_db) off += w.m_blocks * 64;
+    w.cta_begin = cta, w.n_ctas = n;
+    cta += n;
+  }
+  const size_t smem = (size_t)W_STAGES * SLAB_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RSN_CUDA(cudaFuncSetAttribute(field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  field_wgrad_kernel<<<cta, W_THREADS, smem, stream>>>(p);
+  RSN_LAUNCH_CHECK("field_wgrad_kernel");
+  return 0;
+}

@@ -178,3 +178,71 @@ def field_inf_color(wblob: Tensor, bias: Tensor, dirs: Tensor, sqradius: Tensor)
     _lib.call("rsn_field_forward", _lib.ptr(wblob), _lib.ptr(bias), MODE_INF_COLOR, None, _lib.ptr(dirs),
               _lib.ptr(sq), None, m, 1, _lib.ptr(sigma), _lib.ptr(feat), _lib.stream())
     return feat[:, :3]
+
+
+# ----------------------------------------------------------------------------------------- training kernels
+import ctypes as _ct  # noqa: E402
+
+
+@functools.lru_cache(maxsize=1)
+def wgrad_layout():
+    """(offsets [2*J], shapes [(rows, cols)]*J, total floats) of the rsn_field_wgrad gradient blob."""
+    offs = (_ct.c_int64 * 64)()
+    shp = (_ct.c_int64 * 64)()
+    tot = _ct.c_int64(0)
+    n = _lib.lib().rsn_field_wgrad_layout(offs, shp, _ct.byref(tot))
+    return [int(offs[i]) for i in range(2 * n)], [(int(shp[2 * j]), int(shp[2 * j + 1])) for j in range(n)], int(tot.value)
+
+
+def field_forward_train(wblob: Tensor, bias: Tensor, mode: int, origins: Optional[Tensor], dirs: Tensor,
+                        area: Tensor, bins: Optional[Tensor]):
+    """Forward pass that also leaves the activation stash + aux for the backward kernels.
+    mode 0: bins [N,S+1]; mode 1 (infinity colour): one point per ray.  -> sigma [N,S], feat [N,S,16], stash, aux"""
+    dirs, area = _f32c(dirs), _f32c(area.reshape(-1))
+    n = dirs.shape[0]
+    if mode == MODE_SAMPLES:
+        origins, bins = _f32c(origins), _f32c(bins)
+        s = bins.shape[1] - 1
+    else:
+        s = 1
+    dev = dirs.device
+    sigma = torch.empty(n, s, device=dev, dtype=torch.float32)
+    feat = torch.empty(n, s, N_FEAT, device=dev, dtype=torch.float32)
+    aux = torch.empty(n, s, 8, device=dev, dtype=torch.float32)
+    stash = torch.empty(_lib.lib().rsn_field_stash_bytes(n * s), device=dev, dtype=torch.uint8)
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.call("rsn_field_forward_train", _lib.ptr(wblob), _lib.ptr(bias), mode, _lib.ptr(origins), _lib.ptr(dirs),
+              _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), _lib.ptr(stash), _lib.ptr(aux),
+              _lib.stream())
+    if prof is not None:
+        e1.record()
+        prof.append(("field_fwd_kernel", e0, e1, n * s * FLOP_PER_POINT[mode]))
+    return sigma, feat, stash, aux
+
+
+def field_normals(wblob_t: Tensor, wd_bf16: Tensor, stash: Tensor, n: int, s: int) -> Tensor:
+    """K6: -normalize(d raw_density / d contracted mean) of every sample of the pass that produced `stash`."""
+    normals = torch.empty(n, s, 3, device=stash.device, dtype=torch.float32)
+    _lib.call("rsn_field_normals", _lib.ptr(wblob_t), _lib.ptr(wd_bf16), _lib.ptr(stash), n, s, _lib.ptr(normals),
+              _lib.stream())
+    return normals
+
+
+def field_backward(wblob_t: Tensor, stash: Tensor, mode: int, origins, dirs, area, bins, n: int, s: int,
+                   g_sigma: Optional[Tensor], g_feat: Tensor, feat: Tensor, aux: Tensor, dy_stash: Tensor,
+                   want_area: bool) -> Optional[Tensor]:
+    """K5 dgrad chain: fills dy_stash; returns dL/d pixel_area (mode 0) / dL/d sqradius (mode 1) per POINT [n,s]
+    when want_area."""
+    g_area = torch.empty(n, s, device=stash.device, dtype=torch.float32) if want_area else None
+    _lib.call("rsn_field_backward", _lib.ptr(wblob_t), _lib.ptr(stash), mode, _lib.ptr(origins), _lib.ptr(dirs),
+              _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(g_sigma), _lib.ptr(g_feat), _lib.ptr(feat), _lib.ptr(aux),
+              _lib.ptr(dy_stash), _lib.ptr(g_area), _lib.stream())
+    return g_area
+
+
+def field_wgrad(stash: Tensor, dy_stash: Tensor, n_points: int, grad_blob: Tensor) -> None:
+    """K5 wgrad: accumulates dW / db of every Linear over the pass into grad_blob (fp32, wgrad_layout())."""
+    _lib.call("rsn_field_wgrad", _lib.ptr(stash), _lib.ptr(dy_stash), n_points, _lib.ptr(grad_blob), _lib.stream())

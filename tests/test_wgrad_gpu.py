@@ -1,0 +1,44 @@
+"""K5 wgrad kernel alone: random bf16 X / dY block-image stashes vs fp32 torch matmuls of the same operands
+(exercises the MN-major operand reads, the 32-point slab pipeline, split-K atomics and the db column sums)."""
+import pytest
+import torch
+
+from reflect_sampling_nerf_b200 import _lib, ops
+from reflect_sampling_nerf_b200.blocks import pack_blocks
+
+pytestmark = pytest.mark.gpu
+STASH_BLOCKS, DY_BLOCKS = 41, 39
+# (dY first block, m_blocks, X first block, n_blocks, has_db) -- csrc/field_wgrad.cu kJobs
+JOBS = [(7, 4, 0, 2, 1), (11, 4, 2, 4, 1), (15, 4, 6, 4, 1), (19, 4, 10, 4, 1), (23, 4, 0, 2, 0), (23, 4, 14, 4, 1),
+        (27, 4, 18, 4, 1), (31, 4, 22, 4, 1), (35, 4, 26, 4, 1), (3, 4, 30, 4, 1), (0, 2, 30, 4, 1), (0, 2, 39, 2, 0),
+        (1, 2, 34, 4, 1), (1, 2, 38, 1, 0)]
+
+
+@pytest.mark.parametrize("n_tiles", [1, 3, 40])
+def test_wgrad_matches_matmul(n_tiles):
+    g = torch.Generator().manual_seed(n_tiles)
+    pts = n_tiles * 128
+    x = (torch.randn(pts, STASH_BLOCKS * 64, generator=g) * 0.5).bfloat16()
+    dy = (torch.randn(pts, DY_BLOCKS * 64, generator=g) * 0.1).bfloat16()
+    # stash layout: [tile][block][16 KB]; pack_blocks gives [K/64 blocks][rows][128] for a [rows, K] matrix
+    xs = torch.stack([pack_blocks(x[t * 128:(t + 1) * 128]) for t in range(n_tiles)]).cuda()
+    dys = torch.stack([pack_blocks(dy[t * 128:(t + 1) * 128]) for t in range(n_tiles)]).cuda()
+    offs, shapes, total = ops.wgrad_layout()
+    assert len(shapes) == len(JOBS)
+    blob = torch.zeros(total, device="cuda")
+    ops.field_wgrad(xs, dys, pts, blob)
+    torch.cuda.synchronize()
+    blob = blob.cpu()
+    xf, dyf = x.float(), dy.float()
+    for j, (a, mb, b, nb, has_db) in enumerate(JOBS):
+        m, n = shapes[j]
+        assert (m, n) == (mb * 64, nb * 64)
+        ref = dyf[:, a * 64:(a + mb) * 64].T @ xf[:, b * 64:(b + nb) * 64]
+        got = blob[offs[2 * j]: offs[2 * j] + m * n].view(m, n)
+        torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()), msg=lambda s, j=j: f"job {j}: {s}")
+        if has_db:
+            refb = dyf[:, a * 64:(a + mb) * 64].sum(0)
+            gotb = blob[offs[2 * j + 1]: offs[2 * j + 1] + m]
+            torch.testing.assert_close(gotb, refb, rtol=2e-3, atol=2e-3 * float(refb.abs().max()))
+        else:
+            assert offs[2 * j + 1] == -1
