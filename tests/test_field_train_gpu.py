@@ -1,0 +1,133 @@
+"""Training kernels of the field (forward stash, K6 normals, K5 dgrad chain + wgrad) against fp32 autograd of the
+oracle field on the same points, weights and upstream gradients.  The kernels run the GEMMs in bf16 (fp32
+accumulate), so gradients are compared by direction (cosine) and norm, parameter by parameter."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import synthetic_rays
+from oracle import refpath as R
+from reflect_sampling_nerf_b200 import _lib, ops, packing
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n, s, seed, kind, area):
+    torch.manual_seed(seed)
+    field = R.OracleField().train()
+    o, d, pa, _ = synthetic_rays(n, seed, pixel_area=area)
+    g = torch.Generator().manual_seed(seed + 1)
+    if kind == "uniform":
+        nears, fars = torch.full((n, 1), 2.0), torch.full((n, 1), 6.0)
+    else:
+        nears, fars = torch.zeros(n, 1), torch.full((n, 1), 256.0)
+        pa = torch.rand(n, 1, generator=g) * 0.02 + 1e-4        # pi * sqradius of a reflected bundle
+    _, bins = R.spaced_bins(nears, fars, s, kind, torch.rand(n, s + 1, generator=g))
+    return field, o, d, pa, bins, g
+
+
+def _cos(a, b):
+    return float(F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+
+
+def _check_param_grads(field, grads, min_cos=0.99, norm_tol=0.04, skip=("field_output_low",)):
+    for name, p in field.named_parameters():
+        if any(s in name for s in skip):
+            continue
+        ref = p.grad if p.grad is not None else torch.zeros_like(p)
+        got = grads[name].cpu()
+        assert got.shape == ref.shape, name
+        rn, gn = float(ref.norm()), float(got.norm())
+        if rn < 1e-12:
+            assert gn < 1e-6, name
+            continue
+        c = _cos(got, ref)
+        assert c > min_cos, f"{name}: cosine {c:.5f}"
+        assert abs(gn / rn - 1) < norm_tol, f"{name}: norm ratio {gn / rn:.4f}"
+
+
+def _run_mine(field, mode, o, d, pa, bins, g_sigma, g_feat, want_area):
+    sd = field.state_dict()
+    wblob, bias = packing.pack_field(sd)
+    wblob_t, wd = packing.pack_field_t(sd)
+    wblob, bias, wblob_t, wd = wblob.cuda(), bias.cuda(), wblob_t.cuda(), wd.cuda()
+    cu = lambda t: None if t is None else t.cuda()  # noqa: E731
+    sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, mode, cu(o), cu(d), cu(pa), cu(bins))
+    n, s = sigma.shape
+    dy = torch.empty(_lib.lib().rsn_field_dy_stash_bytes(n * s), dtype=torch.uint8, device="cuda")
+    g_area = ops.field_backward(wblob_t, stash, mode, cu(o), cu(d), cu(pa.reshape(-1)), cu(bins), n, s, cu(g_sigma),
+                                cu(g_feat), feat, aux, dy, want_area)
+    offs, shapes, total = ops.wgrad_layout()
+    blob = torch.zeros(total, device="cuda")
+    ops.field_wgrad(stash, dy, n * s, blob)
+    torch.cuda.synchronize()
+    return sigma, feat, stash, (wblob_t, wd), packing.unpack_grads(blob, offs, shapes), g_area
+
+
+@pytest.mark.parametrize("n,s,kind,area", [(16, 64, "uniform", 3.2e-6), (5, 24, "uniform", 8.1e-7),
+                                          (40, 128, "uniform", 3.2e-6)])
+def test_primary_pass_normals_and_gradients(n, s, kind, area):
+    field, o, d, pa, bins, g = _setup(n, s, 7 + n, kind, area)
+    ex = lambda x: x[:, None, :].expand(n, s, x.shape[-1])  # noqa: E731
+    mean, cov = R.frustum_gaussian(ex(o), ex(d), bins[:, :-1, None], bins[:, 1:, None], ex(pa))
+    mean, cov = R.contract(mean, cov)
+    ref = field.point_heads(mean.detach(), cov.detach(), ex(d), primary=True)
+    g_sigma = torch.randn(n, s, generator=g) * 0.1
+    g_feat = torch.zeros(n, s, 16)
+    g_feat[..., 0:14] = torch.randn(n, s, 14, generator=g) * 0.1
+    loss = (g_sigma * ref["density"][..., 0]).sum() + (g_feat[..., 0:3] * ref["rgb"]).sum() \
+        + (g_feat[..., 3:6] * ref["diff"]).sum() + (g_feat[..., 6:9] * ref["tint"]).sum() \
+        + (g_feat[..., 9:12] * ref["pred_normals"]).sum() + (g_feat[..., 12] * ref["roughness_sigmoid"][..., 0]).sum() \
+        + (g_feat[..., 13] * ref["n_dot_d"][..., 0]).sum()
+    loss.backward()
+    sigma, feat, stash, (wblob_t, wd), grads, _ = _run_mine(field, 0, o, d, pa, bins, g_sigma, g_feat, False)
+    torch.testing.assert_close(sigma.cpu(), ref["density"][..., 0].detach(), rtol=3e-2, atol=1e-2)
+    # K6: density-gradient normals
+    normals = ops.field_normals(wblob_t, wd, stash, n, s).cpu()
+    cosang = (normals * ref["normals"].detach()).sum(-1)
+    qs = torch.quantile(cosang.flatten(), torch.tensor([0.01, 0.05, 0.25, 0.5]))
+    print("normals cosine quantiles 1/5/25/50 %:", qs.tolist())
+    # bf16 GEMMs + bf16-stashed encodings: individual points whose gradient nearly cancels can swing, the bulk
+    # must agree tightly
+    assert float(qs[3]) > 0.999 and float(qs[1]) > 0.95 and float(cosang.mean()) > 0.98, (qs.tolist(), float(cosang.mean()))
+    torch.testing.assert_close(normals.norm(dim=-1), torch.ones(n, s), rtol=1e-4, atol=1e-4)
+    _check_param_grads(field, grads)
+
+
+def test_reflected_pass_gradients_and_pixel_area():
+    n, s = 24, 64
+    field, o, d, pa, bins, g = _setup(n, s, 31, "reciprocal", 1.0)
+    pa.requires_grad_(True)
+    ex = lambda x: x[:, None, :].expand(n, s, x.shape[-1])  # noqa: E731
+    mean, cov = R.frustum_gaussian(ex(o), ex(d), bins[:, :-1, None], bins[:, 1:, None], ex(pa))
+    mean, cov = R.contract(mean, cov)
+    ref = field.point_heads(mean, cov, ex(d), primary=False)
+    g_feat = torch.zeros(n, s, 16)
+    g_feat[..., 0:3] = torch.randn(n, s, 3, generator=g) * 0.1
+    (g_feat[..., 0:3] * ref["rgb"]).sum().backward()
+    _, _, _, _, grads, g_area = _run_mine(field, 0, o, d, pa.detach(), bins, torch.zeros(n, s), g_feat, True)
+    _check_param_grads(field, grads)
+    got = g_area.cpu().sum(-1)
+    refg = pa.grad[:, 0]
+    assert _cos(got, refg) > 0.98 and abs(float(got.norm() / refg.norm()) - 1) < 0.06, (_cos(got, refg), got[:5], refg[:5])
+
+
+def test_inf_color_gradients_and_sqradius():
+    torch.manual_seed(5)
+    field = R.OracleField().train()
+    m = 300
+    w = F.normalize(torch.randn(m, 3), dim=-1)
+    sq = (torch.rand(m, 1) * 0.02 + 1e-5).requires_grad_(True)
+    g_rgb = torch.randn(m, 3) * 0.1
+    (g_rgb * field.inf_color(w, sq)).sum().backward()
+    g_feat = torch.zeros(m, 1, 16)
+    g_feat[:, 0, 0:3] = g_rgb
+    _, _, _, _, grads, g_area = _run_mine(field, 1, None, w, sq.detach(), None, None, g_feat, True)
+    _check_param_grads(field, grads, skip=("field_output_low", "field_output_density", "field_output_normals",
+                                           "field_output_roughness", "field_output_diff", "field_output_tint"))
+    for name in ("density", "normals", "roughness", "diff", "tint"):
+        assert float(grads[f"field_output_{name}.net.weight"].abs().max()) == 0.0
+    got, refg = g_area.cpu()[:, 0], sq.grad[:, 0]
+    assert _cos(got, refg) > 0.98 and abs(float(got.norm() / refg.norm()) - 1) < 0.06, (_cos(got, refg), got[:5], refg[:5])
