@@ -108,7 +108,7 @@ int64_t rsn_field_blob_t_bytes(void);
 /* ---- K5 backward, dgrad chain -----------------------------------------------------------------------
  * Replaces the autograd backward of reflect_sampling_nerf_field.py:122-186 (mode 0) / 190-201 (mode 1) for one
  * pass: from g_sigma [N*S] = dL/d sigma and g_feat [N*S,16] = dL/d feat (forward layout; columns 14,15 are
- * ignored) to the pre-activation gradient of every Linear, written to dy_stash (rsn_field_dy_stash_bytes) for
+ * ignored; g_sigma may be NULL = zero) to the pre-activation gradient of every Linear, written to dy_stash (rsn_field_dy_stash_bytes) for
  * rsn_field_wgrad.  feat / aux are the forward outputs.  If g_area != NULL the chain continues through layer 0
  * and the IPE damping and writes dL/d pixel_area (mode 0) or dL/d sqradius (mode 1) of every POINT [N*S]
  * (the caller sums over the samples of a ray): the roughness -> cone width path of

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
               dh[8 + a] = (g_rgb[a] * mid[a] + g_tint[a]) * tint[a] * (1.f - tint[a]);
             }
             const float z = raw + 0.5f;
-            dh[0] = __ldg(p.g_sigma + pt) * (z > 20.f ? 1.f : 1.f / (1.f + __expf(-z)));   // softplus'
+            dh[0] = (p.g_sigma ? __ldg(p.g_sigma + pt) : 0.f) * (z > 20.f ? 1.f : 1.f / (1.f + __expf(-z)));   // softplus'
             // pn = normalize(-normalize(v)):  d v = -(I - pn pn^T) d pn / |v|
             const float nv = fmaxf(sqrtf(rawn[0] * rawn[0] + rawn[1] * rawn[1] + rawn[2] * rawn[2]), 1e-12f);
             const float dot = pn[0] * g_pn[0] + pn[1] * g_pn[1] + pn[2] * g_pn[2];
@@ -683,7 +683,6 @@ extern "C" int rsn_field_backward(const void* wblob_t, const void* x_stash, int 
   if (n_rays == 0) return 0;
   RSN_ARG(n_rays * n_samples < (int64_t)2147483647 - TILE, "rsn_field_backward: more than 2^31 points in one call");
   RSN_ARG(wblob_t && x_stash && dirs && g_feat && feat && aux && dy_stash, "rsn_field_backward: null pointer");
-  RSN_ARG(mode == 1 || g_sigma, "rsn_field_backward: g_sigma required in mode 0");
   RSN_ARG(!g_area || mode == 1 || (origins && bins && area), "rsn_field_backward: rays required for d pixel_area");
   RSN_ARG(((uintptr_t)wblob_t & 15) == 0 && ((uintptr_t)x_stash & 15) == 0 && ((uintptr_t)dy_stash & 15) == 0 &&
               ((uintptr_t)g_feat & 15) == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)aux & 15) == 0,

@@ -70,6 +70,13 @@ class ReflectSamplingNeRFNerfField(nn.Module):
         self.field_output_tint = _Head(w, 3)
         self._packed: Optional[Tuple[Tensor, Tensor]] = None
         self._packed_key = None
+        self._packed_t: Optional[Tuple[Tensor, Tensor]] = None
+        self._packed_t_key = None
+        # training state (see train_path.py): gradient blob of the wgrad kernel for the backward in flight,
+        # the reusable dY stash, and the data-parallel world size for the flat gradient all-reduce
+        self._grad_blob: Optional[Tensor] = None
+        self._dy_buffer: Optional[Tensor] = None
+        self.dp_world_size = 1
 
     # ------------------------------------------------------------------------------------ derived state
     def _version_key(self):
@@ -83,6 +90,15 @@ class ReflectSamplingNeRFNerfField(nn.Module):
                 self._packed = packing.pack_field(dict(self.named_parameters()))
             self._packed_key = key
         return self._packed
+
+    def packed_t(self) -> Tuple[Tensor, Tensor]:
+        """(transposed bf16 operand blob of the dgrad chains, bf16 density-head row)."""
+        key = self._version_key()
+        if self._packed_t is None or key != self._packed_t_key:
+            with torch.no_grad():
+                self._packed_t = packing.pack_field_t(dict(self.named_parameters()))
+            self._packed_t_key = key
+        return self._packed_t
 
     # ------------------------------------------------------------------------------------ evaluation
     def evaluate_samples(self, origins: Tensor, directions: Tensor, pixel_area: Tensor, bins: Tensor
