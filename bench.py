@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="render", choices=["train", "render"])
+    ap.add_argument("--workload", default="train", choices=["train", "render"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--ref-rays", type=int, default=1024, help="bounded CPU sample (rays per oracle step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

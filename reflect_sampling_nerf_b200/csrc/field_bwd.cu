@@ -100,8 +100,7 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 // 64 accumulator columns of this row -> (optional ReLU mask from the stashed activation block) -> bf16 ->
 // activation block in place, and (optional) the same chunk into the dY stash.
 template <bool MASK>
-__device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_saddr, uint32_t mask_saddr, int row,
-                                            uint8_t* stash_blk) {
+__device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_saddr, uint32_t mask_saddr, int row) {
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
@@ -123,9 +122,7 @@ __device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_
       pk.z &= relu_mask2(hm[c].z);
       pk.w &= relu_mask2(hm[c].w);
     }
-    const uint32_t off = (uint32_t)((c ^ (row & 7)) << 4);
-    sts128b(row_saddr + off, pk);
-    if (stash_blk) *reinterpret_cast<uint4*>(stash_blk + (size_t)row * 128 + off) = pk;
+    sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), pk);
   }
 }
 
@@ -446,10 +443,19 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
         af_phase ^= (1u << buf);
         tc_fence_after();
       };
-      auto publish = [&](uint64_t* bar) {
-        fence_proxy_async();
+      // publish a freshly written block (rows of this warp): optional coalesced stash store, then the barrier
+      auto publish = [&](uint64_t* bar, uint32_t blk_saddr = 0, uint8_t* stash_blk = nullptr) {
+        if (stash_blk) {
+          warp_store_rows(stash_blk, blk_saddr, q, lane);
+        } else {
+          fence_proxy_async();
+        }
         tc_fence_before();
         mbar_arrive(bar);
+      };
+      // the act slice about to be overwritten was handed to the TMA engine at most 4 bulk groups ago
+      auto guard = [&]() {
+        if (KIND == KIND_BACKWARD) warp_store_guard<3>(lane);
       };
       auto mask_wait = [&]() -> uint32_t {
         mbar_wait(&bars.m_full[mstage], mphase);
@@ -508,29 +514,28 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
         const uint4 c3 = make_uint4(pack2(dh[8], dh[9]), pack2(dh[10], 0.f), 0u, 0u);
         const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
         const uint32_t srow = s_seed + (uint32_t)row * 128u;
-        uint8_t* grow = dblk(DY_SEED) + (size_t)row * 128;
+        warp_store_guard<0>(lane);   // previous tile's seed store (and everything older) has left shared memory
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 v = (c == 0) ? c0 : (c == 2) ? c2 : (c == 3) ? c3 : zz;
-          const uint32_t off = (uint32_t)((c ^ (row & 7)) << 4);
-          if (c < 4) sts128b(srow + off, v);
-          *reinterpret_cast<uint4*>(grow + off) = v;
+          sts128b(srow + (uint32_t)((c ^ (row & 7)) << 4), v);
         }
-        publish(&bars.seed_ready);
+        publish(&bars.seed_ready, s_seed, dblk(DY_SEED));
         // ---- E0: d mid_hidden * (mid_hidden > 0) -> dY_mid (act blocks 0,1)
         wait_acc();
         for (int g = 0; g < 2; ++g) {
           const uint32_t ms = mask_wait();
-          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, ms, row, dblk(DY_MID + g));
+          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, ms, row);
           mask_release();
-          publish(&bars.act_ready[g]);
+          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, dblk(DY_MID + g));
         }
         buf ^= 1;
         // ---- E1: d bottleneck (no activation) -> dY_bott
         wait_acc();
         for (int g = 0; g < 4; ++g) {
-          dgrad_group<false>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, 0, row, dblk(DY_BOTT + g));
-          publish(&bars.act_ready[g]);
+          warp_store_guard<1>(lane);   // blocks 0/1 were handed to the TMA engine by E0, 2 groups ago
+          dgrad_group<false>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, 0, row);
+          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, dblk(DY_BOTT + g));
         }
         buf ^= 1;
       } else {
@@ -572,11 +577,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
         }
         for (int g = 0; g < 4; ++g) {
           const uint32_t ms = mask_wait();
+          guard();
           // output = dY_{l-1}: stash block DY_H + 4 (l-1) + g
-          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, ms, row,
-                            (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr);
+          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, ms, row);
           mask_release();
-          publish(&bars.act_ready[g]);
+          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES,
+                  (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr);
         }
         buf ^= 1;
       }
@@ -631,6 +637,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
       }
     }
   }
+  if (KIND == KIND_BACKWARD && lane == 0 && warp >= 2 && warp < 6) bulk_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);

@@ -103,14 +103,9 @@ __device__ __forceinline__ float sin_reduced(float s) {
 }
 
 // 8 encoded columns -> one 16-byte chunk of the row
-// (and, when training, into the same position of the stashed copy of the block in global memory)
-__device__ __forceinline__ void store_chunk(uint32_t row_saddr, int row, int chunk, const float (&f)[8],
-                                            uint8_t* stash_row = nullptr) {
-  const uint32_t off = (uint32_t)((chunk ^ (row & 7)) << 4);
-  const uint4 v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
-  sts128(row_saddr + off, v.x, v.y, v.z, v.w);
-  if (stash_row) *reinterpret_cast<uint4*>(stash_row + off) = v;
+__device__ __forceinline__ void store_chunk(uint32_t row_saddr, int row, int chunk, const float (&f)[8]) {
+  sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
 // ---------------------------------------------------------------------------------------------- prologue
@@ -183,9 +178,8 @@ __device__ __forceinline__ void frustum_gaussian_contracted(const float o[3], co
 // NeRFEncoding.forward with covs: s = fl(fl(2pi x) f), v = fl(diag fl(f f)),
 // enc = exp(-v/2) sin(s | s + pi/2), raw xyz appended last.
 __device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const float (&xm)[3], const float (&dg)[3],
-                                           uint8_t* stash_enc) {
+                                           bool zero_tail) {
   const uint32_t row0 = enc_saddr + (uint32_t)row * 128u;
-  uint8_t* srow = stash_enc ? stash_enc + (size_t)row * 128 : nullptr;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -204,19 +198,17 @@ __device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const fl
           f8[i] = (e < 24.f) ? __expf(-e) * sin_reduced(s) : 0.f;
         }
         const int j = half * 6 + a * 2 + kk;  // 16-byte chunk index along the 112 columns
-        store_chunk(row0 + (uint32_t)(j >> 3) * BLOCK_BYTES, row, j & 7, f8,
-                    srow ? srow + (size_t)(j >> 3) * BLOCK_BYTES : nullptr);
+        store_chunk(row0 + (uint32_t)(j >> 3) * BLOCK_BYTES, row, j & 7, f8);
       }
     }
   }
   const float f12[8] = {xm[0], xm[1], xm[2], 0.f, 0.f, 0.f, 0.f, 0.f};
   const float f13[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  uint8_t* s1 = srow ? srow + BLOCK_BYTES : nullptr;
-  store_chunk(row0 + BLOCK_BYTES, row, 12 & 7, f12, s1);
-  store_chunk(row0 + BLOCK_BYTES, row, 13 & 7, f13, s1);
-  if (s1) {  // columns 112..127 are never read by the forward MMAs but the wgrad reads whole blocks
-    store_chunk(row0 + BLOCK_BYTES, row, 14 & 7, f13, s1);
-    store_chunk(row0 + BLOCK_BYTES, row, 15 & 7, f13, s1);
+  store_chunk(row0 + BLOCK_BYTES, row, 12 & 7, f12);
+  store_chunk(row0 + BLOCK_BYTES, row, 13 & 7, f13);
+  if (zero_tail) {  // columns 112..127 are never read by the forward MMAs but the wgrad reads whole blocks
+    store_chunk(row0 + BLOCK_BYTES, row, 14 & 7, f13);
+    store_chunk(row0 + BLOCK_BYTES, row, 15 & 7, f13);
   }
 }
 
@@ -279,7 +271,7 @@ __device__ __forceinline__ void ide_features(const float d[3], float rho, float 
 // 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> activation block `blk`.
 template <bool RELU>
 __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, const float* __restrict__ bias,
-                                               uint32_t blk_saddr, int row, uint8_t* stash_blk) {
+                                               uint32_t blk_saddr, int row) {
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
@@ -304,10 +296,7 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, const floa
         pk[q * 2 + 1] = RELU ? pack_relu_bf16x2(x2, x3) : pack_bf16x2(x2, x3);
       }
       const int chunk = h * 4 + c;
-      const uint32_t off = (uint32_t)((chunk ^ (row & 7)) << 4);
-      sts128(row_saddr + off, pk[0], pk[1], pk[2], pk[3]);
-      if (stash_blk)
-        *reinterpret_cast<uint4*>(stash_blk + (size_t)row * 128 + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -507,17 +496,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         af_phase ^= (1u << buf);
         tc_fence_after();
       };
-      auto publish = [&](uint64_t* bar) {
-        fence_proxy_async();
+      // publish a freshly written block (rows of this warp): optional coalesced stash store, then the barrier
+      auto publish = [&](uint64_t* bar, uint32_t blk_saddr, uint8_t* stash_blk, bool drain = false) {
+        if (stash_blk) {
+          warp_store_rows(stash_blk, blk_saddr, q, lane);
+          if (drain) warp_store_guard<0>(lane);   // another warp role overwrites this block later
+        } else {
+          fence_proxy_async();
+        }
         tc_fence_before();
         mbar_arrive(bar);
+      };
+      // The slice about to be overwritten was handed to the TMA engine 4 bulk groups ago (layer l-1, same g),
+      // except in layer 0, where blocks 0/1 were last stored by the previous tile's mid layer, 2 groups ago.
+      auto guard = [&]() {
+        if (st) warp_store_guard<3>(lane);
       };
       for (int l = 0; l < 8; ++l) {
         wait_acc();
         for (int g = 0; g < 4; ++g) {
+          if (l == 0) {
+            if (st) warp_store_guard<1>(lane);
+          } else {
+            guard();
+          }
           epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_BASE + l * 256 + g * 64,
-                               s_act + g * BLOCK_BYTES, row, sblk(STASH_H + 4 * l + g));
-          publish(&bars.act_ready[g]);
+                               s_act + g * BLOCK_BYTES, row);
+          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_H + 4 * l + g));
         }
         buf ^= 1;
       }
@@ -526,9 +531,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       {
         wait_acc();
         for (int g = 0; g < 4; ++g) {
+          guard();
           epilogue_group<false>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_BOTT + g * 64,
-                                s_act + g * BLOCK_BYTES, row, sblk(STASH_BOTT + g));
-          publish(&bars.act_ready[g]);
+                                s_act + g * BLOCK_BYTES, row);
+          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_BOTT + g));
         }
         uint32_t hv[16];
         tmem_ld16(tlane + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, hv);
@@ -575,19 +581,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
 #pragma unroll
           for (int i = 0; i < 48; ++i) t[i] = 0.f;  // get_inf_color feeds a zero IDE (field.py:199)
         }
-        const uint32_t ide_row = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES + (uint32_t)row * 128u;
+        const uint32_t ide_blk = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
+        const uint32_t ide_row = ide_blk + (uint32_t)row * 128u;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           const float f8[8] = {t[c * 8 + 0], t[c * 8 + 1], t[c * 8 + 2], t[c * 8 + 3],
                                t[c * 8 + 4], t[c * 8 + 5], t[c * 8 + 6], t[c * 8 + 7]};
-          store_chunk(ide_row, row, c, f8, st ? sblk(STASH_IDE) + (size_t)row * 128 : nullptr);
+          store_chunk(ide_row, row, c, f8);
         }
-        if (st) {
-          uint8_t* ir = sblk(STASH_IDE) + (size_t)row * 128;
-          *reinterpret_cast<uint4*>(ir + ((6 ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(ir + ((7 ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+        if (st) {   // columns 48..63 are not read by the mid MMA but the wgrad reads the whole block
+          const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          store_chunk(ide_row, row, 6, z8);
+          store_chunk(ide_row, row, 7, z8);
         }
-        publish(&bars.ide_ready);
+        publish(&bars.ide_ready, ide_blk, sblk(STASH_IDE), true);
         if (valid && p.aux) {
           p.aux[(size_t)pt * 8 + 3] = h[1];
           p.aux[(size_t)pt * 8 + 4] = h[2];
@@ -606,9 +613,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       {
         wait_acc();
         for (int g = 0; g < 2; ++g) {
+          guard();
           epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_MID + g * 64,
-                               s_act + g * BLOCK_BYTES, row, sblk(STASH_MIDH + g));
-          publish(&bars.act_ready[g]);
+                               s_act + g * BLOCK_BYTES, row);
+          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_MIDH + g));
         }
         buf ^= 1;
       }
@@ -669,13 +677,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         }
       }
       mbar_wait(&bars.enc_empty[eb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      encode_row(s_enc + (uint32_t)eb * 2 * BLOCK_BYTES, row, xm, dg,
-                 p.stash ? p.stash + ((size_t)tile * STASH_BLOCKS + STASH_ENC) * BLOCK_BYTES : nullptr);
-      fence_proxy_async();
+      const uint32_t enc_blk = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
+      encode_row(enc_blk, row, xm, dg, p.stash != nullptr);
+      if (p.stash) {
+        // stash the two enc blocks (this warp's rows) and wait until the TMA engine has READ them: the epilogue
+        // warps overwrite block 0 with the IDE later in the tile
+        uint8_t* se = p.stash + ((size_t)tile * STASH_BLOCKS + STASH_ENC) * BLOCK_BYTES;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g_u32(se + (warp - 6) * 4096, enc_blk + (uint32_t)(warp - 6) * 4096u, 4096);
+          bulk_s2g_u32(se + BLOCK_BYTES + (warp - 6) * 4096, enc_blk + BLOCK_BYTES + (uint32_t)(warp - 6) * 4096u, 4096);
+          bulk_commit();
+          bulk_wait_read<0>();
+        }
+        __syncwarp();
+      } else {
+        fence_proxy_async();
+      }
       mbar_arrive(&bars.enc_full[eb]);
     }
   }
 
+  if (p.stash && lane == 0 && warp >= 2) bulk_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);

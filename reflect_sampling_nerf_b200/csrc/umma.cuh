@@ -71,6 +71,10 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
                "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void bulk_s2g_u32(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -79,6 +83,24 @@ __device__ __forceinline__ void bulk_wait_read() {
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// A warp owns rows [32q, 32q+32) of a [128][64] bf16 block image = one contiguous 4 KB slice of it.  After the
+// warp's lanes have written their rows with st.shared, lane 0 hands the slice to the TMA engine (coalesced 4 KB
+// store to the block's copy in global memory).  Before the warp overwrites the slice again it calls
+// warp_store_guard<N>() (N = bulk groups that may still be pending).
+__device__ __forceinline__ void warp_store_rows(uint8_t* gdst_block, uint32_t smem_block, int q, int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    bulk_s2g_u32(gdst_block + q * 4096, smem_block + (uint32_t)q * 4096u, 4096);
+    bulk_commit();
+  }
+}
+template <int N>
+__device__ __forceinline__ void warp_store_guard(int lane) {
+  if (lane == 0) bulk_wait_read<N>();
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ TMEM
