@@ -384,12 +384,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         ar_phase ^= (1u << g);
         tc_fence_after();
       };
+      // K-major operands: LBO unused (16), SBO = 1024; one K=16 step advances both start addresses by 32 bytes
+      constexpr uint32_t HI = desc_hi_sw128(1024);
       auto issue_kb = [&](uint32_t a_addr, uint32_t b_addr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool& acc) {
-        for (int k = 0; k < ksteps; ++k) {
-          mma_bf16_ss(tmem_d, smem_desc_sw128(a_addr + k * 32, 16, 1024), smem_desc_sw128(b_addr + k * 32, 16, 1024),
-                      idesc, acc ? 1u : 0u);
-          acc = true;
-        }
+        const uint32_t a_lo = desc_lo(a_addr, 16), b_lo = desc_lo(b_addr, 16);
+        mma_bf16_ss_lo(tmem_d, a_lo, b_lo, HI, idesc, acc ? 1u : 0u);
+        mma_bf16_ss_lo(tmem_d, a_lo + 2, b_lo + 2, HI, idesc, 1u);
+        mma_bf16_ss_lo(tmem_d, a_lo + 4, b_lo + 4, HI, idesc, 1u);
+        if (ksteps == 4) mma_bf16_ss_lo(tmem_d, a_lo + 6, b_lo + 6, HI, idesc, 1u);
+        acc = true;
       };
       for (int it = 0; it < n_my_tiles; ++it) {
         const int eb = it & 1;

@@ -19,6 +19,7 @@
 #include "umma.cuh"
 #include "field_layout.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -26,10 +27,13 @@ using namespace umma;
 using namespace rsnf;
 
 constexpr int W_THREADS = 192;      // warp 0 producer, warp 1 MMA issuer, warps 2-5 db + epilogue
-constexpr int SLAB_ROWS = 32;       // points per pipeline slab (2 K-steps)
+#ifndef RSN_WGRAD_SLAB_ROWS
+#define RSN_WGRAD_SLAB_ROWS 64
+#endif
+constexpr int SLAB_ROWS = RSN_WGRAD_SLAB_ROWS;   // points per pipeline slab (SLAB_ROWS / 16 K-steps)
 constexpr int SLAB_BLOCK_BYTES = SLAB_ROWS * 128;
 constexpr int SLAB_BYTES = 8 * SLAB_BLOCK_BYTES;   // up to 4 dY + 4 X blocks
-constexpr int W_STAGES = 6;
+constexpr int W_STAGES = 196608 / SLAB_BYTES;    // 192 KB ring
 constexpr int MAX_JOBS = 16;
 
 struct WJob {
@@ -44,6 +48,7 @@ struct WParams {
   int n_tiles;
   float* grad;
   int n_jobs;
+  int debug;   // RSN_WGRAD_DEBUG: 1 = MMA only (no loads, no db), 2 = loads only (no MMA)
   WJob jobs[MAX_JOBS];
 };
 
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
   const uint32_t tmem = bars.tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && (p.debug & 3) != 1) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t0; t < t1; ++t) {
@@ -116,14 +121,23 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
       uint32_t phase = 0;
       const uint32_t idesc = instr_desc_bf16(128, nb * 64, 1, 1);
       for (int s = 0; s < n_slabs; ++s) {
-        mbar_wait(&bars.full[stage], phase);
+        if ((p.debug & 3) != 1) mbar_wait(&bars.full[stage], phase);
         tc_fence_after();
         const uint32_t base = smem_u32(smem + (size_t)stage * SLAB_BYTES);
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t db = smem_desc_sw128(base + mb * SLAB_BLOCK_BYTES + ks * 2048, SLAB_BLOCK_BYTES, 1024);
-          for (int h = 0; h < mb / 2; ++h) {
-            const uint64_t da = smem_desc_sw128(base + (2 * h) * SLAB_BLOCK_BYTES + ks * 2048, SLAB_BLOCK_BYTES, 1024);
-            mma_bf16_ss(tmem + h * 256, da, db, idesc, (s | ks) != 0);
+        // MN-major operands: LBO = stride between the 64-feature blocks of the slab, SBO = 1024 (8 points);
+        // one K=16 step (16 points) advances the start address by 2048 bytes
+        constexpr uint32_t HI = desc_hi_sw128(1024);
+        const uint32_t a_lo = desc_lo(base, SLAB_BLOCK_BYTES), b_lo = desc_lo(base + mb * SLAB_BLOCK_BYTES, SLAB_BLOCK_BYTES);
+        if ((p.debug & 3) != 2) {
+          // all K-steps of the slab into one accumulator, then the other: interleaving the two accumulators MMA by
+          // MMA is measurably slower (2.6 vs 4.2 ms for the MMA stream alone at C2)
+#pragma unroll
+          for (int ks = 0; ks < SLAB_ROWS / 16; ++ks)
+            mma_bf16_ss_lo(tmem, a_lo + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
+          if (mb == 4) {
+#pragma unroll
+            for (int ks = 0; ks < SLAB_ROWS / 16; ++ks)
+              mma_bf16_ss_lo(tmem + 256, a_lo + (2 * SLAB_BLOCK_BYTES >> 4) + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
           }
         }
         mma_commit(&bars.empty[stage]);
@@ -135,22 +149,36 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
       mma_commit(&bars.acc_full);
     }
   } else {
-    // ---- db: column sums of the dY slabs while they sit in shared memory; then the dW flush
-    const int t = threadIdx.x - 64;          // 0..127 -> feature pair (2t, 2t+1) of the job's M features
-    const int blk = t >> 5, pr = t & 31;
+    // ---- db: column sums of the dY slabs while they sit in shared memory; then the dW flush.
+    // Thread -> one 16-byte chunk column (8 features) of one dY block, every 4th row: within a warp the 32 lanes
+    // read the 8 chunks of one row of each of the 4 blocks = conflict-free 128-bit shared loads.
+    const int t = threadIdx.x - 64;
+    const int cc = t & 31, rphase = t >> 5;
+    const int blk = cc >> 3, ch = cc & 7;
     const bool db_active = blk < mb;
-    float a0 = 0.f, a1 = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     int stage = 0;
     uint32_t phase = 0;
-    for (int s = 0; s < n_slabs; ++s) {
+    for (int s = 0; s < ((p.debug & 3) == 1 ? 0 : n_slabs); ++s) {
       mbar_wait(&bars.full[stage], phase);
-      if (db_active) {
-        const uint8_t* src = smem + (size_t)stage * SLAB_BYTES + blk * SLAB_BLOCK_BYTES;
-#pragma unroll 8
-        for (int r = 0; r < SLAB_ROWS; ++r) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(src + r * 128 + ((((pr >> 2) ^ (r & 7)) << 4) | ((pr & 3) << 2)));
-          a0 += __uint_as_float(v << 16);
-          a1 += __uint_as_float(v & 0xffff0000u);
+      if (db_active && (p.debug & 3) != 3) {
+        const uint32_t src = smem_u32(smem + (size_t)stage * SLAB_BYTES) + blk * SLAB_BLOCK_BYTES;
+        uint4 v[SLAB_ROWS / 4];
+#pragma unroll
+        for (int i = 0; i < SLAB_ROWS / 4; ++i) {
+          const int r = rphase + 4 * i;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                       : "r"(src + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4)));
+        }
+#pragma unroll
+        for (int i = 0; i < SLAB_ROWS / 4; ++i) {
+          acc[0] += __uint_as_float(v[i].x << 16), acc[1] += __uint_as_float(v[i].x & 0xffff0000u);
+          acc[2] += __uint_as_float(v[i].y << 16), acc[3] += __uint_as_float(v[i].y & 0xffff0000u);
+          acc[4] += __uint_as_float(v[i].z << 16), acc[5] += __uint_as_float(v[i].z & 0xffff0000u);
+          acc[6] += __uint_as_float(v[i].w << 16), acc[7] += __uint_as_float(v[i].w & 0xffff0000u);
         }
       }
       __syncwarp();
@@ -161,23 +189,26 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
       }
     }
     if (n_slabs > 0) {
-      if (db_active && job.db_off >= 0) {
-        atomicAdd(p.grad + job.db_off + 2 * t, a0);
-        atomicAdd(p.grad + job.db_off + 2 * t + 1, a1);
+      if (db_active && job.db_off >= 0 && (p.debug & 3) != 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(p.grad + job.db_off + blk * 64 + ch * 8 + i, acc[i]);
       }
       mbar_wait(&bars.acc_full, 0);
       tc_fence_after();
       const int q = warp & 3;
       const int row = q * 32 + lane;
       const int N = nb * 64;
-      for (int h = 0; h < mb / 2; ++h) {
+      for (int h = 0; h < ((p.debug & 4) ? 0 : mb / 2); ++h) {
         float* out = p.grad + job.out_off + (size_t)(h * 128 + row) * N;
         for (int c0 = 0; c0 < N; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 256 + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(out + c0 + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 4)   // 16-byte vector reductions: 4x fewer L2 atomic transactions
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c0 + i), "f"(__uint_as_float(v[i])),
+                         "f"(__uint_as_float(v[i + 1])), "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                         : "memory");
         }
       }
     }
@@ -244,6 +275,7 @@ extern "C" int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_
   p.n_tiles = (int)((n_points + TILE - 1) / TILE);
   p.grad = grad_blob;
   p.n_jobs = kNumJobs;
+  p.debug = getenv("RSN_WGRAD_DEBUG") ? atoi(getenv("RSN_WGRAD_DEBUG")) : 0;
   // CTAs per job proportional to the job's bytes per tile (the kernel is HBM-bound), one wave of <= #SM CTAs
   const int sms = rsn_num_sms();
   int units = 0;

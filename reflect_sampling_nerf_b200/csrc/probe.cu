@@ -161,3 +161,73 @@ extern "C" int rsn_probe_umma_mnmajor(const void* u_blocks, const void* v_blocks
   RSN_LAUNCH_CHECK("probe_mnmajor_kernel");
   return 0;
 }
+
+// ---- tcgen05.mma issue-rate probe: cycles per M128 x N x K16 bf16 MMA for the four operand major-ness
+// combinations (operands: whatever is in shared memory; only the timing matters).  `cheap` selects the issue
+// path: 0 = both 64-bit descriptors rebuilt per MMA, 1 = constant high word + 32-bit add (mma_bf16_ss_lo).
+namespace {
+__global__ void __launch_bounds__(160, 1) probe_rate_kernel(int a_major, int b_major, int cheap, int N, int iters,
+                                                            long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 6 * 16384 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  __syncthreads();
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(&bar_mma, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_slot, 512);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc = instr_desc_bf16(128, N, a_major, b_major);
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 2 * 16384;
+    const long long t0 = clock64();
+    if (!cheap) {
+      for (int i = 0; i < iters; ++i) {
+        const int k = i & 3;
+        const uint64_t da = a_major ? smem_desc_sw128(sa + k * 2048, 16384, 1024) : smem_desc_sw128(sa + k * 32, 16, 1024);
+        const uint64_t db = b_major ? smem_desc_sw128(sb + k * 2048, 16384, 1024) : smem_desc_sw128(sb + k * 32, 16, 1024);
+        mma_bf16_ss(tmem, da, db, idesc, i != 0);
+      }
+    } else {
+      const uint32_t a_lo = desc_lo(sa, a_major ? 16384 : 16), b_lo = desc_lo(sb, b_major ? 16384 : 16);
+      const uint32_t as = a_major ? 128 : 2, bs = b_major ? 128 : 2;
+      for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss_lo(tmem, a_lo + k * as, b_lo + k * bs, desc_hi_sw128(1024), idesc, (i | k) != 0);
+      }
+    }
+    mma_commit(&bar_mma);
+    mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" int rsn_probe_umma_rate(int a_major, int b_major, int64_t n, int64_t iters, int64_t* cycles_out,
+                                   cudaStream_t stream) {
+  RSN_ARG(n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && iters % 4 == 0, "rsn_probe_umma_rate: bad arguments");
+  size_t smem = 6 * 16384 + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // a_major bit 1: cheap issue path; bits 8..: number of CTAs (CTA 0 reports)
+  const int grid = (a_major >> 8) ? (a_major >> 8) : 1;
+  probe_rate_kernel<<<grid, 160, smem, stream>>>(a_major & 1, b_major & 1, (a_major >> 1) & 1, (int)n, (int)iters,
+                                                 (long long*)cycles_out);
+  RSN_LAUNCH_CHECK("probe_rate_kernel");
+  return 0;
+}
