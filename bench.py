@@ -209,7 +209,9 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        ms = sum(per_step)
+        timed.last_per_step = per_step
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -219,6 +221,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     ms_step, launches, prof = timed(False, args.steps, args.warmup)
+    step_ms = [round(x, 2) for x in timed.last_per_step]
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     ms_e2e, _, _ = timed(True, max(2, args.steps // 2), 1)
@@ -258,7 +261,7 @@ def run_b200(args):
                        "parallelism": f"dp{world} (rays sharded, no data-path collective)"},
             "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
+            "gpu_launches": launches, "step_ms_rank0": step_ms, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -195,7 +195,7 @@ def wgrad_layout():
 
 
 def field_forward_train(wblob: Tensor, bias: Tensor, mode: int, origins: Optional[Tensor], dirs: Tensor,
-                        area: Tensor, bins: Optional[Tensor]):
+                        area: Tensor, bins: Optional[Tensor], stash: Optional[Tensor] = None):
     """Forward pass that also leaves the activation stash + aux for the backward kernels.
     mode 0: bins [N,S+1]; mode 1 (infinity colour): one point per ray.  -> sigma [N,S], feat [N,S,16], stash, aux"""
     dirs, area = _f32c(dirs), _f32c(area.reshape(-1))
@@ -209,7 +209,11 @@ def field_forward_train(wblob: Tensor, bias: Tensor, mode: int, origins: Optiona
     sigma = torch.empty(n, s, device=dev, dtype=torch.float32)
     feat = torch.empty(n, s, N_FEAT, device=dev, dtype=torch.float32)
     aux = torch.empty(n, s, 8, device=dev, dtype=torch.float32)
-    stash = torch.empty(_lib.lib().rsn_field_stash_bytes(n * s), device=dev, dtype=torch.uint8)
+    nbytes = _lib.lib().rsn_field_stash_bytes(n * s)
+    if stash is None:
+        stash = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    elif stash.numel() < nbytes or stash.dtype != torch.uint8 or stash.device != dev:
+        raise ValueError("field_forward_train: stash workspace too small")
     prof = PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -12,6 +12,7 @@ autograd-engine callback queued from the first pass's backward; with data parall
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -26,7 +27,7 @@ def _flush_grads(field) -> None:
     blob, field._grad_blob = field._grad_blob, None
     if blob is None:
         return
-    if field.dp_world_size > 1:
+    if field.dp_world_size > 1 and not os.environ.get("RSN_DEBUG_SKIP_ALLREDUCE"):
         dist.all_reduce(blob, op=dist.ReduceOp.SUM)
         blob.mul_(1.0 / field.dp_world_size)          # DDP averages (pipeline.py:75)
     offs, shapes, _ = ops.wgrad_layout()
@@ -41,13 +42,33 @@ def _flush_grads(field) -> None:
             p.grad.add_(g)
 
 
+def _stash_workspace(field, n_points: int, device) -> Tensor:
+    """The activation stash of the k-th field pass of a step lives in a persistent workspace (10.7 GB for a C2
+    primary pass): a step's stashes are dead once its backward has run, and re-allocating ~28 GB per step makes
+    the caching allocator thrash for the first several steps."""
+    nbytes = _lib.lib().rsn_field_stash_bytes(n_points)
+    pool = field.__dict__.setdefault("_stash_pool", [])
+    k = field.__dict__.get("_stash_cursor", 0)
+    field.__dict__["_stash_cursor"] = k + 1
+    if k >= len(pool):
+        pool.append(None)
+    buf = pool[k]
+    if buf is None or buf.numel() < nbytes or buf.device != device:
+        pool[k] = None
+        buf = torch.empty(int(nbytes * 1.25) if k >= 2 else nbytes, dtype=torch.uint8, device=device)   # reflected passes vary
+        pool[k] = buf
+    return buf
+
+
 class _FieldPass(torch.autograd.Function):
     """One fused field evaluation over all samples of a ray batch (mode 0) or the infinity colour (mode 1)."""
 
     @staticmethod
     def forward(ctx, field, mode: int, primary: bool, origins, dirs, area, bins, *params):
         wblob, bias = field.packed()
-        sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, mode, origins, dirs, area, bins)
+        n_pts = dirs.shape[0] * (bins.shape[1] - 1 if bins is not None else 1)
+        stash = _stash_workspace(field, n_pts, dirs.device)
+        sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, mode, origins, dirs, area, bins, stash)
         n, s = sigma.shape
         if primary:
             wblob_t, wd = field.packed_t()
@@ -102,6 +123,7 @@ def _render(field, primary, o, d, area, eu_bins, detach_density: bool):
 def get_outputs_train(model, ray_bundle) -> Dict[str, Tensor]:
     """reflect_sampling_nerf_model.py:142-344 in training mode, with autograd."""
     field = model.field
+    field.__dict__["_stash_cursor"] = 0          # stash workspaces are reused pass by pass, step after step
     o, d = ray_bundle.origins, ray_bundle.directions
     area, nears, fars = ray_bundle.pixel_area, ray_bundle.nears, ray_bundle.fars
     n, dev = o.shape[0], o.device
