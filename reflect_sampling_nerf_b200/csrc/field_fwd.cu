@@ -14,9 +14,9 @@
 //   warp 0      weight producer: streams the pre-packed bf16 weight blob (L2 resident, 1.27 MB) through a
 //               3 x 32 KB shared-memory ring with cp.async.bulk (TMA engine) + mbarrier complete_tx
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M128, N<=256, K16, bf16 -> fp32 in TMEM)
-//   warps 2-5   epilogue: tcgen05.ld the accumulator row of "their" point, bias + ReLU, bf16, write the
+//   warps 6-9   epilogue: tcgen05.ld the accumulator row of "their" point, bias + ReLU, bf16, write the
 //               next layer's A operand IN PLACE into the swizzled activation blocks; heads, IDE, outputs
-//   warps 6-9   prologue for the NEXT tile: frustum gaussian, contraction, IPE -> bf16 A operand
+//   warps 2-5   prologue for the NEXT tile: frustum gaussian, contraction, IPE -> bf16 A operand
 // The two 256-column TMEM accumulator buffers alternate by layer, and every layer's epilogue publishes
 // its output per 64-column group (mbarrier act_ready[g]) so that the next layer's K-block g is issued as
 // soon as that group is written: MMA of layer l+1 overlaps the epilogue of layer l.
@@ -27,6 +27,7 @@
 #include "umma.cuh"
 #include "field_layout.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -46,6 +47,12 @@ __constant__ float c_freq[16] = {
     0x1.33f9760000000p+4f,  0x1.428a320000000p+5f,  0x1.51cb4e0000000p+6f,  0x1.61c5140000000p+7f,
     0x1.7280340000000p+8f,  0x1.8405f60000000p+9f,  0x1.965fde0000000p+10f, 0x1.a998080000000p+11f,
     0x1.bdb8d20000000p+12f, 0x1.d2cd4c0000000p+13f, 0x1.e8e1020000000p+14f, 0x1.0000000000000p+16f};
+// Bias vector of the current launch (N_BIAS floats).  Every epilogue thread of a warp reads the same bias element
+// at the same time (its own row, the same column): the uniform-address case the constant cache serves in a few
+// cycles, where the same load from global memory pays an L2 round trip on the layer-critical path (L1 is empty:
+// the kernel takes the whole carve-out as shared memory).  Refilled device-to-device, stream-ordered, by every
+// rsn_field_forward call, so it carries no state between calls.
+__constant__ float4 c_bias4[N_BIAS / 4];
 const float h_freq[16] = {
     0x1.0000000000000p+0f,  0x1.0c1b780000000p+1f,  0x1.18c9880000000p+2f,  0x1.26111c0000000p+3f,
     0x1.33f9760000000p+4f,  0x1.428a320000000p+5f,  0x1.51cb4e0000000p+6f,  0x1.61c5140000000p+7f,
@@ -67,6 +74,7 @@ struct FwdParams {
   float* feat;              // [P][16]
   uint8_t* stash;           // training: [n_tiles][STASH_BLOCKS][16 KB] activation block images, or NULL
   float* aux;               // training: [P][8] = mid rgb (3), raw normal head (3), 2 spare, or NULL
+  int debug;                // RSN_FWD_DEBUG (timing experiments only): 1 = no bias, 2 = no trig in the prologue
 };
 
 struct Barriers {
@@ -270,14 +278,14 @@ __device__ __forceinline__ void ide_features(const float d[3], float rho, float 
 // ---------------------------------------------------------------------------------------------- epilogue
 // 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> activation block `blk`.
 template <bool RELU>
-__device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, const float* __restrict__ bias,
-                                               uint32_t blk_saddr, int row) {
+__device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
+                                               bool nobias = false) {
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
   float4 b[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
+  for (int i = 0; i < 16; ++i) b[i] = nobias ? make_float4(0.f, 0.f, 0.f, 0.f) : c_bias4[(bias_off >> 2) + i];
   tmem_ld_wait();
   const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
 #pragma unroll
@@ -480,8 +488,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp >= 6) {
     // ===================================================================== epilogue warps (thread = point row)
+    // (highest warp ids: the per-SMSP arbiter favours them over the prologue warps on the layer-critical path)
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
@@ -523,8 +532,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           } else {
             guard();
           }
-          epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_BASE + l * 256 + g * 64,
-                               s_act + g * BLOCK_BYTES, row);
+          epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
+                               s_act + g * BLOCK_BYTES, row, (p.debug & 1) != 0);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_H + 4 * l + g));
         }
         buf ^= 1;
@@ -535,7 +544,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         for (int g = 0; g < 4; ++g) {
           guard();
-          epilogue_group<false>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_BOTT + g * 64,
+          epilogue_group<false>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BOTT + g * 64,
                                 s_act + g * BLOCK_BYTES, row);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_BOTT + g));
         }
@@ -544,7 +553,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         float hb[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + BIAS_HEAD) + i);
+          const float4 t4 = c_bias4[BIAS_HEAD / 4 + i];
           hb[i * 4 + 0] = t4.x, hb[i * 4 + 1] = t4.y, hb[i * 4 + 2] = t4.z, hb[i * 4 + 3] = t4.w;
         }
         tmem_ld_wait();
@@ -617,7 +626,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         for (int g = 0; g < 2; ++g) {
           guard();
-          epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, p.bias + BIAS_MID + g * 64,
+          epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64,
                                s_act + g * BLOCK_BYTES, row);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_MIDH + g));
         }
@@ -628,7 +637,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         uint32_t rv[16];
         tmem_ld16(tlane + (uint32_t)buf * 256, rv);
-        const float4 rb = __ldg(reinterpret_cast<const float4*>(p.bias + BIAS_RGB));
+        const float4 rb = c_bias4[BIAS_RGB / 4];
         tmem_ld_wait();
         tc_fence_before();
         const float mid[3] = {sigmoid_acc(__uint_as_float(rv[0]) + rb.x), sigmoid_acc(__uint_as_float(rv[1]) + rb.y),
@@ -650,7 +659,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     }
   } else {
     // ===================================================================== prologue warps (next tile's IPE)
-    const int row = (warp - 6) * 32 + lane;
+    const int row = (warp - 2) * 32 + lane;
     for (int it = 0; it < n_my_tiles; ++it) {
       const int eb = it & 1;
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -679,6 +688,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           }
         }
       }
+      if (p.debug & 2) xm[0] = xm[1] = xm[2] = 0.f, dg[0] = dg[1] = dg[2] = 100.f;
       mbar_wait(&bars.enc_empty[eb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
       const uint32_t enc_blk = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
       encode_row(enc_blk, row, xm, dg, p.stash != nullptr);
@@ -689,8 +699,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          bulk_s2g_u32(se + (warp - 6) * 4096, enc_blk + (uint32_t)(warp - 6) * 4096u, 4096);
-          bulk_s2g_u32(se + BLOCK_BYTES + (warp - 6) * 4096, enc_blk + BLOCK_BYTES + (uint32_t)(warp - 6) * 4096u, 4096);
+          bulk_s2g_u32(se + (warp - 2) * 4096, enc_blk + (uint32_t)(warp - 2) * 4096u, 4096);
+          bulk_s2g_u32(se + BLOCK_BYTES + (warp - 2) * 4096, enc_blk + BLOCK_BYTES + (uint32_t)(warp - 2) * 4096u, 4096);
           bulk_commit();
           bulk_wait_read<0>();
         }
@@ -751,6 +761,7 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
   p.feat = feat;
   p.stash = (uint8_t*)stash;
   p.aux = aux;
+  p.debug = getenv("RSN_FWD_DEBUG") ? atoi(getenv("RSN_FWD_DEBUG")) : 0;
   RSN_ARG(((uintptr_t)stash & 15) == 0, "rsn_field_forward: stash must be 16-byte aligned");
   const size_t smem = SMEM_TOTAL + 1024;
   static bool attr_set = false;
@@ -758,6 +769,7 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
     RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  RSN_CUDA(cudaMemcpyToSymbolAsync(c_bias4, bias, N_BIAS * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
   const int grid = std::min(p.n_tiles, rsn_num_sms());
   field_fwd_kernel<<<grid, NUM_THREADS, smem, stream>>>(p);
   RSN_LAUNCH_CHECK("field_fwd_kernel");
