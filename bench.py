@@ -226,18 +226,33 @@ def run_b200(args):
     sampler.join(timeout=2)
     ms_e2e, _, _ = timed(True, max(2, args.steps // 2), 1)
 
-    # roofline of the dominant kernel: the fused field forward (bf16 tensor)
-    roof = None
+    # roofline: every field kernel from its own CUDA-event launch durations; `roofline` = the one with the largest
+    # share of the step (tensor-bound kernels against the sustained cuBLAS bf16 peak, HBM-bound against the copy peak)
+    roof, roof_all = None, []
     if prof:
-        tot_ms = sum(a.elapsed_time(b) for (_, a, b, _) in prof)
-        tot_flop = sum(f for (_, _, _, f) in prof)
-        peak = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
-            if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 1400.0
-        ach = tot_flop / (tot_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "field_fwd_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "launches": len(prof), "avg_launch_ms": tot_ms / len(prof),
-                "share_of_step": tot_ms / (ms_step * args.steps),
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"}
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) \
+            if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else None
+        tf_peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+        bw_peak = peaks["hbm_gbs"] if peaks else 6650.0
+        src = "MEASURED_PEAKS.json (bf16_tflops_sustained: kernels timed inside a long step; hbm_gbs)" if peaks \
+            else "B200_PROFILING.md fallback"
+        # ncu --set full dram__bytes_read+write per launch of a C2 primary pass (profiles/r01_*_ncu.txt)
+        ncu_traffic = {"field_chain_kernel<backward>": 19.93e9, "field_wgrad_kernel": 24.70e9, "field_fwd_kernel": 0.095e9}
+        by = {}
+        for (name, a, b, flop, nbytes) in prof:
+            d = by.setdefault(name, [0.0, 0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b); d[1] += flop; d[2] += nbytes; d[3] += 1
+        for name, (ms, flop, nbytes, cnt) in by.items():
+            tf, gb = flop / ms / 1e9, nbytes / ms / 1e6
+            hbm_bound = (gb / bw_peak) > (tf / tf_peak)
+            roof_all.append({"kernel": name, "bound": "hbm" if hbm_bound else "tensor",
+                             "achieved": gb if hbm_bound else tf, "peak": bw_peak if hbm_bound else tf_peak,
+                             "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                             "frac": (gb / bw_peak) if hbm_bound else (tf / tf_peak),
+                             "tflops": tf, "gbs": gb, "traffic": ncu_traffic.get(name),
+                             "launches": cnt, "avg_launch_ms": ms / cnt, "share_of_step": ms / (ms_step * args.steps)})
+        roof_all.sort(key=lambda r: -r["share_of_step"])
+        roof = dict(roof_all[0], peak_source=src)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -261,7 +276,7 @@ def run_b200(args):
                        "parallelism": f"dp{world} (rays sharded, no data-path collective)"},
             "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "step_ms_rank0": step_ms, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
+            "gpu_launches": launches, "step_ms_rank0": step_ms, "clocks": sampler.summary(), "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -9,7 +9,7 @@ from ctypes import c_float, c_int, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsn_b200.so")
+LIB_PATH = os.environ.get("RSN_B200_LIB") or os.path.join(_HERE, "librsn_b200.so")   # env override: kernel experiments
 _lib = None
 
 P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float

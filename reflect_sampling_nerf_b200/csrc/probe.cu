@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(160, 1) probe_rate_kernel(int a_major, int b_m
                                                             long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_mma;
+  __shared__ uint64_t bar_mma, bar_scratch;
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 6 * 16384 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(160, 1) probe_rate_kernel(int a_major, int b_m
   if (warp == 4) {
     if (lane == 0) {
       mbar_init(&bar_mma, 1);
+      mbar_init(&bar_scratch, 1);   // phases just keep completing; nobody waits on it
       fence_barrier_init();
     }
     __syncwarp();
@@ -200,12 +201,17 @@ __global__ void __launch_bounds__(160, 1) probe_rate_kernel(int a_major, int b_m
         mma_bf16_ss(tmem, da, db, idesc, i != 0);
       }
     } else {
+      // cheap >> 1: bits 0-3 = commit every 4*c MMAs to a scratch barrier (0 = never), bits 4-7 = switch between
+      // the two 256-column accumulators every 4*s MMAs (0 = never)
+      const int commit_every = ((cheap >> 1) & 15) * 4, switch_every = ((cheap >> 5) & 15) * 4;
       const uint32_t a_lo = desc_lo(sa, a_major ? 16384 : 16), b_lo = desc_lo(sb, b_major ? 16384 : 16);
       const uint32_t as = a_major ? 128 : 2, bs = b_major ? 128 : 2;
       for (int i = 0; i < iters; i += 4) {
+        const uint32_t tm = tmem + ((switch_every && ((i / switch_every) & 1)) ? 256u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          mma_bf16_ss_lo(tmem, a_lo + k * as, b_lo + k * bs, desc_hi_sw128(1024), idesc, (i | k) != 0);
+          mma_bf16_ss_lo(tm, a_lo + k * as, b_lo + k * bs, desc_hi_sw128(1024), idesc, i >= 2 * (switch_every ? switch_every : 4));
+        if (commit_every && ((i + 4) % commit_every) == 0) mma_commit(&bar_scratch);
       }
     }
     mma_commit(&bar_mma);
@@ -224,9 +230,11 @@ extern "C" int rsn_probe_umma_rate(int a_major, int b_major, int64_t n, int64_t 
   RSN_ARG(n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && iters % 4 == 0, "rsn_probe_umma_rate: bad arguments");
   size_t smem = 6 * 16384 + 1024;
   RSN_CUDA(cudaFuncSetAttribute(probe_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // a_major bit 1: cheap issue path; bits 8..: number of CTAs (CTA 0 reports)
-  const int grid = (a_major >> 8) ? (a_major >> 8) : 1;
-  probe_rate_kernel<<<grid, 160, smem, stream>>>(a_major & 1, b_major & 1, (a_major >> 1) & 1, (int)n, (int)iters,
+  // a_major bit 1: cheap issue path; bits 8-15: number of CTAs (CTA 0 reports); bits 16-19 / 20-23: commit / switch
+  // the accumulator every 4*x MMAs (cheap path only)
+  const int grid = ((a_major >> 8) & 255) ? ((a_major >> 8) & 255) : 1;
+  const int cheap = ((a_major >> 1) & 1) | (((a_major >> 16) & 255) << 1);
+  probe_rate_kernel<<<grid, 160, smem, stream>>>(a_major & 1, b_major & 1, cheap, (int)n, (int)iters,
                                                  (long long*)cycles_out);
   RSN_LAUNCH_CHECK("probe_rate_kernel");
   return 0;

@@ -18,6 +18,35 @@ UNIFORM, RECIPROCAL = 0, 1
 # the dominant kernel on the launching stream; None (default) = no events recorded.
 PROFILE = None
 FLOP_PER_POINT = {0: 1230592, 1: 1225472}   # SURVEY.md §8d (forward; primary figure used for every sample pass)
+# algorithmic (FLOPs, HBM bytes) per point of the four field kernels
+KERNEL_WORK = {
+    "field_fwd_kernel": (1230592, 68),
+    "field_fwd_kernel[train]": (1230592, 68 + 32 + 41 * 128),
+    "field_chain_kernel<normals>": (1019392, 34 * 128 + 12),
+    "field_chain_kernel<backward>": (1179904, 34 * 128 + 39 * 128 + 160),
+    "field_chain_kernel<backward+area>": (1229056, 38 * 128 + 39 * 128 + 164),
+    "field_wgrad_kernel": (1230592, 95 * 128),
+}
+
+
+class _Prof:
+    """CUDA-event bracket around one kernel launch on the launching stream, active only while PROFILE is a list."""
+
+    def __init__(self, name: str, n_points: int):
+        self.name, self.n, self.on = name, n_points, PROFILE is not None
+
+    def __enter__(self):
+        if self.on:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on and PROFILE is not None:
+            self.e1.record()
+            flop, nbytes = KERNEL_WORK[self.name]
+            PROFILE.append((self.name, self.e0, self.e1, self.n * flop, self.n * nbytes))
+        return False
 
 
 def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
@@ -157,15 +186,9 @@ def field_forward(wblob: Tensor, bias: Tensor, origins: Tensor, dirs: Tensor, pi
         raise ValueError("field_forward: origins/dirs must be [N,3] and pixel_area [N] for bins [N,S+1]")
     sigma = torch.empty(n, s, device=bins.device, dtype=torch.float32)
     feat = torch.empty(n, s, N_FEAT, device=bins.device, dtype=torch.float32)
-    prof = PROFILE
-    if prof is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    _lib.call("rsn_field_forward", _lib.ptr(wblob), _lib.ptr(bias), MODE_SAMPLES, _lib.ptr(origins), _lib.ptr(dirs),
-              _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), _lib.stream())
-    if prof is not None:
-        e1.record()
-        prof.append(("field_fwd_kernel", e0, e1, n * s * FLOP_PER_POINT[0]))
+    with _Prof("field_fwd_kernel", n * s):
+        _lib.call("rsn_field_forward", _lib.ptr(wblob), _lib.ptr(bias), MODE_SAMPLES, _lib.ptr(origins),
+                  _lib.ptr(dirs), _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), _lib.stream())
     return sigma, feat
 
 
@@ -214,24 +237,19 @@ def field_forward_train(wblob: Tensor, bias: Tensor, mode: int, origins: Optiona
         stash = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     elif stash.numel() < nbytes or stash.dtype != torch.uint8 or stash.device != dev:
         raise ValueError("field_forward_train: stash workspace too small")
-    prof = PROFILE
-    if prof is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    _lib.call("rsn_field_forward_train", _lib.ptr(wblob), _lib.ptr(bias), mode, _lib.ptr(origins), _lib.ptr(dirs),
-              _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), _lib.ptr(stash), _lib.ptr(aux),
-              _lib.stream())
-    if prof is not None:
-        e1.record()
-        prof.append(("field_fwd_kernel", e0, e1, n * s * FLOP_PER_POINT[mode]))
+    with _Prof("field_fwd_kernel[train]", n * s):
+        _lib.call("rsn_field_forward_train", _lib.ptr(wblob), _lib.ptr(bias), mode, _lib.ptr(origins), _lib.ptr(dirs),
+                  _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), _lib.ptr(stash),
+                  _lib.ptr(aux), _lib.stream())
     return sigma, feat, stash, aux
 
 
 def field_normals(wblob_t: Tensor, wd_bf16: Tensor, stash: Tensor, n: int, s: int) -> Tensor:
     """K6: -normalize(d raw_density / d contracted mean) of every sample of the pass that produced `stash`."""
     normals = torch.empty(n, s, 3, device=stash.device, dtype=torch.float32)
-    _lib.call("rsn_field_normals", _lib.ptr(wblob_t), _lib.ptr(wd_bf16), _lib.ptr(stash), n, s, _lib.ptr(normals),
-              _lib.stream())
+    with _Prof("field_chain_kernel<normals>", n * s):
+        _lib.call("rsn_field_normals", _lib.ptr(wblob_t), _lib.ptr(wd_bf16), _lib.ptr(stash), n, s,
+                  _lib.ptr(normals), _lib.stream())
     return normals
 
 
@@ -241,12 +259,14 @@ def field_backward(wblob_t: Tensor, stash: Tensor, mode: int, origins, dirs, are
     """K5 dgrad chain: fills dy_stash; returns dL/d pixel_area (mode 0) / dL/d sqradius (mode 1) per POINT [n,s]
     when want_area."""
     g_area = torch.empty(n, s, device=stash.device, dtype=torch.float32) if want_area else None
-    _lib.call("rsn_field_backward", _lib.ptr(wblob_t), _lib.ptr(stash), mode, _lib.ptr(origins), _lib.ptr(dirs),
-              _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(g_sigma), _lib.ptr(g_feat), _lib.ptr(feat), _lib.ptr(aux),
-              _lib.ptr(dy_stash), _lib.ptr(g_area), _lib.stream())
+    with _Prof("field_chain_kernel<backward+area>" if want_area else "field_chain_kernel<backward>", n * s):
+        _lib.call("rsn_field_backward", _lib.ptr(wblob_t), _lib.ptr(stash), mode, _lib.ptr(origins), _lib.ptr(dirs),
+                  _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(g_sigma), _lib.ptr(g_feat), _lib.ptr(feat),
+                  _lib.ptr(aux), _lib.ptr(dy_stash), _lib.ptr(g_area), _lib.stream())
     return g_area
 
 
 def field_wgrad(stash: Tensor, dy_stash: Tensor, n_points: int, grad_blob: Tensor) -> None:
     """K5 wgrad: accumulates dW / db of every Linear over the pass into grad_blob (fp32, wgrad_layout())."""
-    _lib.call("rsn_field_wgrad", _lib.ptr(stash), _lib.ptr(dy_stash), n_points, _lib.ptr(grad_blob), _lib.stream())
+    with _Prof("field_wgrad_kernel", n_points):
+        _lib.call("rsn_field_wgrad", _lib.ptr(stash), _lib.ptr(dy_stash), n_points, _lib.ptr(grad_blob), _lib.stream())

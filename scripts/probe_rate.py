@@ -12,3 +12,11 @@ for cheap in (0, 1):
         r = [run(a, b, n, cheap) for a, b in ((0, 0), (1, 0), (0, 1), (1, 1))]
         print(f"issue={'lo-add ' if cheap else 'rebuild'} N={n:3d}  K/K {r[0]:.1f}  MN/K {r[1]:.1f}  K/MN {r[2]:.1f}  MN/MN {r[3]:.1f} cycles/MMA")
 print(f"148 CTAs, K/K N=256 lo-add: {run(0, 0, 256, 1, 148):.1f}")
+def run2(n, commit, switch, iters=4096):
+    _lib.call("rsn_probe_umma_rate", 0 | (1 << 1) | (1 << 8) | (commit << 16) | (switch << 20), 0, n, iters, out.data_ptr(), _lib.stream())
+    torch.cuda.synchronize()
+    return out.item() / iters
+for n in (256, 128):
+    for commit in (0, 1, 2, 4):
+        for switch in (0, 1, 2, 4):
+            print(f"N={n} commit every {4*commit:2d} MMAs, switch accumulator every {4*switch:2d} MMAs: {run2(n, commit, switch):.1f} cycles/MMA")
