@@ -1,0 +1,85 @@
+"""BASELINE.json full sizes (C2: 16,384 rays x 128 samples; C5 per-GPU shard: 8,192 rays x 256 samples + 128
+reflected) through size-independent properties: the oracle cannot run these sizes in seconds, so the checks are
+invariants of the domain -- sorted bins inside [near, far], weights in [0,1] summing to the accumulation,
+median depth inside the ray segment, tile-position independence of the fused field (the same ray gives the same
+result wherever it lands in the batch), and linearity of the wgrad accumulation."""
+import pytest
+import torch
+
+from reflect_sampling_nerf_b200 import _lib, ops, packing
+from reflect_sampling_nerf_b200.plugin_field_init import random_field_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _rays(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    o = -4.0 * d + 0.3 * torch.randn(n, 3, generator=g)
+    return o.cuda(), d.cuda(), torch.full((n,), 3.2e-6).cuda()
+
+
+@pytest.mark.parametrize("n,s_c,s_f", [(16384, 128, 128), (8192, 256, 128)])
+def test_sampling_and_compositing_invariants_at_full_size(n, s_c, s_f):
+    torch.manual_seed(0)
+    nears, fars = torch.full((n, 1), 2.0).cuda(), torch.full((n, 1), 6.0).cuda()
+    sp, eu = ops.sample_spaced(nears, fars, s_c, ops.UNIFORM, torch.rand(n, s_c + 1).cuda())
+    assert bool((eu[:, 1:] >= eu[:, :-1]).all()) and float(eu.min()) >= 2.0 and float(eu.max()) <= 6.0
+    sigma = torch.nn.functional.softplus(torch.randn(n, s_c).cuda() + 0.5) * torch.rand(n, 1).cuda() * 20
+    feat = torch.rand(n, s_c, 16).cuda()
+    w, acc, depth, comp = ops.composite(sigma, eu, feat)
+    assert float(w.min()) >= 0.0 and float(w.max()) <= 1.0
+    torch.testing.assert_close(w.sum(-1), acc, rtol=1e-5, atol=1e-6)
+    assert float(acc.max()) <= 1.0 + 1e-5
+    assert bool((depth >= eu[:, 0]).all()) and bool((depth <= eu[:, -1]).all())
+    assert bool((comp <= acc[:, None] + 1e-5).all())            # features in [0,1] => composite <= accumulation
+    sp2, eu2, inds = ops.pdf_resample(w, sp, nears, fars, s_f, ops.UNIFORM, rand=torch.rand(n, s_f + 1).cuda(),
+                                      return_inds=True)
+    assert bool((sp2[:, 1:] >= sp2[:, :-1]).all()) and float(sp2.min()) >= 0.0 and float(sp2.max()) <= 1.0
+    assert bool((eu2[:, 1:] >= eu2[:, :-1]).all()) and float(eu2.min()) >= 2.0 and float(eu2.max()) <= 6.0
+    assert int(inds.min()) >= 0 and int(inds.max()) <= s_c + 1 and bool((inds[:, 1:] >= inds[:, :-1]).all())
+
+
+def test_field_is_independent_of_tile_position_at_full_size():
+    n, s = 16384, 128
+    sd = random_field_state()
+    wblob, bias = [t.cuda() for t in packing.pack_field(sd)]
+    o, d, pa = _rays(n, 3)
+    bins = (2.0 + 4.0 * torch.linspace(0, 1, s + 1))[None].expand(n, s + 1).contiguous().cuda()
+    sigma, feat = ops.field_forward(wblob, bias, o, d, pa, bins)
+    assert bool(torch.isfinite(sigma).all()) and bool(torch.isfinite(feat).all())
+    perm = torch.randperm(n, device="cuda")
+    sigma_p, feat_p = ops.field_forward(wblob, bias, o[perm], d[perm], pa[perm], bins[perm])
+    assert torch.equal(sigma_p, sigma[perm]) and torch.equal(feat_p, feat[perm])      # bit-exact, any tile / CTA
+    assert float(sigma.min()) >= 0 and float(feat[..., :9].min()) >= 0 and float(feat[..., :3].max()) <= 2.0
+    torch.testing.assert_close(feat[..., 9:12].norm(dim=-1), torch.ones(n, s, device="cuda"), rtol=1e-4, atol=1e-4)
+
+
+def test_training_kernels_linearity_and_determinism_at_full_size():
+    n, s = 16384, 128
+    sd = random_field_state()
+    wblob, bias = [t.cuda() for t in packing.pack_field(sd)]
+    wblob_t, wd = [t.cuda() for t in packing.pack_field_t(sd)]
+    o, d, pa = _rays(n, 5)
+    bins = (2.0 + 4.0 * torch.linspace(0, 1, s + 1))[None].expand(n, s + 1).contiguous().cuda()
+    sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, 0, o, d, pa, bins)
+    sigma_e, feat_e = ops.field_forward(wblob, bias, o, d, pa, bins)
+    assert torch.equal(sigma, sigma_e) and torch.equal(feat, feat_e)                  # stash does not perturb results
+    normals = ops.field_normals(wblob_t, wd, stash, n, s)
+    torch.testing.assert_close(normals.norm(dim=-1), torch.ones(n, s, device="cuda"), rtol=1e-4, atol=1e-4)
+    g_sigma = torch.randn(n, s, device="cuda") * 0.01
+    g_feat = torch.randn(n, s, 16, device="cuda") * 0.01
+    dy = torch.empty(_lib.lib().rsn_field_dy_stash_bytes(n * s), dtype=torch.uint8, device="cuda")
+    total = ops.wgrad_layout()[2]
+
+    def grads(scale):
+        ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma * scale, g_feat * scale, feat, aux, dy, False)
+        blob = torch.zeros(total, device="cuda")
+        ops.field_wgrad(stash, dy, n * s, blob)
+        return blob
+
+    g1, g2 = grads(1.0), grads(2.0)
+    assert bool(torch.isfinite(g1).all())
+    # the backward is linear in the upstream gradient (power-of-two scale: exact in bf16 up to atomics order)
+    rel = float((g2 - 2 * g1).norm() / g2.norm())
+    assert rel < 1e-4, rel
