@@ -145,6 +145,11 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the rsn_b200 kernels have no CPU fallback")
+    # NCCL prints its version banner on stdout at communicator creation: keep stdout clean for the ONE JSON line by
+    # pointing fd 1 at stderr for the duration of the run and writing the result to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -278,7 +283,8 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "step_ms_rank0": step_ms, "clocks": sampler.summary(), "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu_base,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
