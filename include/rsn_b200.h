@@ -138,6 +138,10 @@ int rsn_probe_umma_kmajor(const void* x_blocks, const void* w_blocks, int64_t n_
 int rsn_probe_umma_mnmajor(const void* u_blocks, const void* v_blocks, int64_t m_blocks, int64_t n_blocks,
                            float* out, rsn_stream_t stream);
 
+/* CTA-pair probe: out [256, n_out] = X [256, 64 k_blocks] * W [n_out, 64 k_blocks]^T with tcgen05.mma.cta_group::2;
+ * x_blocks = two tiles of k_blocks block images, w_blocks = k_blocks images of n_out rows. */
+int rsn_probe_umma_2cta(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks, float* out,
+                        rsn_stream_t stream);
 /* Issue-rate probe: cycles for `iters` back-to-back M128 x n x K16 bf16 tcgen05.mma with K-major (0) or
  * MN-major (1) A / B operands; *cycles_out is a DEVICE int64. */
 int rsn_probe_umma_rate(int a_major, int b_major, int64_t n, int64_t iters, int64_t* cycles_out, rsn_stream_t stream);

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "rsn_field_bias_count": ([], c_int64),
     "rsn_ipe_freqs": ([P], c_int),
     "rsn_probe_umma_kmajor": ([P, P, I64, I64, I64, P, P], c_int),
+    "rsn_probe_umma_2cta": ([P, P, I64, I64, P, P], c_int),
     "rsn_probe_umma_rate": ([I32, I32, I64, I64, P, P], c_int),
     "rsn_probe_umma_mnmajor": ([P, P, I64, I64, P, P], c_int),
 }

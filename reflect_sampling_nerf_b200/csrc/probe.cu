@@ -239,3 +239,85 @@ extern "C" int rsn_probe_umma_rate(int a_major, int b_major, int64_t n, int64_t 
   RSN_LAUNCH_CHECK("probe_rate_kernel");
   return 0;
 }
+
+// ---- CTA-pair probe: D[256, N] = X[256, K] * W[N, K]^T with tcgen05.mma.cta_group::2.  CTA r of the pair stages its
+// own 128 rows of X and rows [r N/2, (r+1) N/2) of W; the leader issues; both read their 128 x N result from TMEM.
+namespace {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160, 1)
+    probe_2cta_kernel(const uint8_t* __restrict__ x_blocks, const uint8_t* __restrict__ w_blocks, int N, int KB,
+                      float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_load, bar_peer, bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* sx = smem;
+  uint8_t* sw = smem + (size_t)KB * 16384;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t half_bytes = (uint32_t)(N / 2) * 128u;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(&bar_load, 1);
+      mbar_init(&bar_peer, 1);
+      mbar_init(&bar_mma, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta(&tmem_base_slot, 512);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == 4 && lane == 0) {
+    mbar_expect_tx(&bar_load, (uint32_t)KB * (16384u + half_bytes));
+    for (int kb = 0; kb < KB; ++kb) {
+      bulk_g2s(sx + (size_t)kb * 16384, x_blocks + ((size_t)rank * KB + kb) * 16384, 16384, &bar_load);
+      bulk_g2s(sw + (size_t)kb * half_bytes, w_blocks + (size_t)kb * N * 128 + (size_t)rank * half_bytes, half_bytes, &bar_load);
+    }
+    mbar_wait(&bar_load, 0);
+    if (rank == 1) {
+      mbar_arrive_remote(&bar_peer, 0);      // my operands are in my shared memory
+    } else {
+      mbar_wait_cluster(&bar_peer, 0);
+      tc_fence_after();
+      const uint32_t idesc = instr_desc_bf16(256, N, 0, 0);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss_lo_2cta(tmem, desc_lo(smem_u32(sx + (size_t)kb * 16384), 16) + 2 * k,
+                              desc_lo(smem_u32(sw + (size_t)kb * half_bytes), 16) + 2 * k, desc_hi_sw128(1024), idesc,
+                              (kb | k) != 0);
+      mma_commit_2cta(&bar_mma);
+    }
+  }
+  if (warp < 4) {
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) out[((size_t)rank * 128 + row) * N + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 4) tmem_dealloc_2cta(tmem, 512);
+}
+}  // namespace
+
+extern "C" int rsn_probe_umma_2cta(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks, float* out,
+                                   cudaStream_t stream) {
+  RSN_ARG(n_out >= 16 && n_out <= 256 && n_out % 16 == 0, "rsn_probe_umma_2cta: n_out in [16,256], multiple of 16");
+  RSN_ARG(k_blocks >= 1 && k_blocks <= 4, "rsn_probe_umma_2cta: k_blocks in [1,4]");
+  size_t smem = (size_t)k_blocks * (16384 + n_out * 64) + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_2cta_kernel<<<2, 160, smem, stream>>>((const uint8_t*)x_blocks, (const uint8_t*)w_blocks, (int)n_out,
+                                              (int)k_blocks, out);
+  RSN_LAUNCH_CHECK("probe_2cta_kernel");
+  return 0;
+}

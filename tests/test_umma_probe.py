@@ -34,3 +34,18 @@ def test_mnmajor_tile_gemm(NB):
     torch.cuda.synchronize()
     ref = u.float().T @ v.float()
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("N,KB", [(256, 4), (256, 1), (128, 2), (16, 4), (64, 3)])
+def test_cta_pair_tile_gemm(N, KB):
+    """tcgen05.mma.cta_group::2: M = 256 over a CTA pair, each CTA staging its 128 rows of X and N/2 rows of W."""
+    g = torch.Generator().manual_seed(N * 7 + KB)
+    x = torch.randn(256, KB * 64, generator=g).bfloat16()
+    w = torch.randn(N, KB * 64, generator=g).bfloat16()
+    xb = torch.stack([pack_blocks(x[:128]), pack_blocks(x[128:])]).cuda()      # [2 tiles][KB][128][128 B]
+    wb = pack_blocks(w).cuda()
+    out = torch.full((256, N), float("nan"), device="cuda")
+    _lib.call("rsn_probe_umma_2cta", xb.data_ptr(), wb.data_ptr(), N, KB, out.data_ptr(), _lib.stream())
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().T
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-2)
