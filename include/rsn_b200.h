@@ -146,6 +146,9 @@ int rsn_probe_umma_2cta(const void* x_blocks, const void* w_blocks, int64_t n_ou
  * MN-major (1) A / B operands; *cycles_out is a DEVICE int64. */
 int rsn_probe_umma_rate(int a_major, int b_major, int64_t n, int64_t iters, int64_t* cycles_out, rsn_stream_t stream);
 
+/* Same for the CTA pair: cycles for `iters` back-to-back M256 x n x K16 cta_group::2 MMAs on n_pairs clusters. */
+int rsn_probe_umma_rate_2cta(int64_t n, int64_t iters, int64_t n_pairs, int64_t* cycles_out, rsn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "rsn_ipe_freqs": ([P], c_int),
     "rsn_probe_umma_kmajor": ([P, P, I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_2cta": ([P, P, I64, I64, P, P], c_int),
+    "rsn_probe_umma_rate_2cta": ([I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_rate": ([I32, I32, I64, I64, P, P], c_int),
     "rsn_probe_umma_mnmajor": ([P, P, I64, I64, P, P], c_int),
 }

@@ -77,8 +77,10 @@ struct FwdParams {
   int debug;                // RSN_FWD_DEBUG (timing experiments only): 1 = no bias, 2 = no trig in the prologue
 };
 
+constexpr int MAX_STAGES = 6;
 struct Barriers {
-  uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
+  uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
+  uint64_t w_peer[MAX_STAGES];   // CTA pair, leader only: the peer CTA's half of the stage has landed
   uint64_t enc_full[2], enc_empty[2];
   uint64_t act_ready[4];
   uint64_t ide_ready;
@@ -312,38 +314,65 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------- kernel
+// PAIR = true: the kernel runs as 2-CTA clusters (tcgen05 cta_group::2).  CTA r of a pair owns its own 128-point
+// tile (prologue, epilogue, activations, TMEM accumulators) and stages rows [r N/2, (r+1) N/2) of every weight
+// chunk; the leader (r = 0) issues M = 256 MMAs for both.  Per SM and layer this halves the weight bytes written
+// into shared memory and the B-operand bytes read back by the tensor core (384 KB -> 256 KB of shared-memory
+// traffic against 2048 MMA cycles at 128 B/cycle): the single-CTA form is shared-memory-bandwidth bound.
+template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ Barriers bars;
+  constexpr int NS = PAIR ? 6 : NUM_STAGES;                       // weight ring: 6 x 16 KB or 3 x 32 KB
+  constexpr uint32_t STB = PAIR ? W_STAGE_BYTES / 2 : W_STAGE_BYTES;
+  constexpr uint32_t ARRIVALS = PAIR ? 8 : TILE;                  // PAIR: one arrival per warp, both CTAs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t s_act = smem_u32(smem + SMEM_ACT);
   const uint32_t s_enc = smem_u32(smem + SMEM_ENC);
   const uint32_t s_w = smem_u32(smem + SMEM_W);
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < NUM_STAGES; ++i) {
+      for (int i = 0; i < NS; ++i) {
         mbar_init(&bars.w_full[i], 1);
         mbar_init(&bars.w_empty[i], 1);
+        mbar_init(&bars.w_peer[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&bars.enc_full[i], TILE);
+        mbar_init(&bars.enc_full[i], ARRIVALS);
         mbar_init(&bars.enc_empty[i], 1);
         mbar_init(&bars.acc_full[i], 1);
       }
-      for (int i = 0; i < 4; ++i) mbar_init(&bars.act_ready[i], TILE);
-      mbar_init(&bars.ide_ready, TILE);
+      for (int i = 0; i < 4; ++i) mbar_init(&bars.act_ready[i], ARRIVALS);
+      mbar_init(&bars.ide_ready, ARRIVALS);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(&bars.tmem_slot, 512);
+    if (PAIR) tmem_alloc_2cta(&bars.tmem_slot, 512); else tmem_alloc(&bars.tmem_slot, 512);
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_slot;
-  const int n_my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // tiles of this CTA: single CTA: blockIdx.x + it * gridDim.x; pair q of Q: 2 (q + it Q) + rank (the last may be void)
+  const int n_units = PAIR ? (p.n_tiles + 1) / 2 : p.n_tiles;
+  const int unit0 = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int n_workers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int n_my_tiles = (n_units > unit0) ? (n_units - unit0 + n_workers - 1) / n_workers : 0;
+  auto tile_of = [&](int it) -> int { return PAIR ? 2 * (unit0 + it * n_workers) + (int)rank : unit0 + it * n_workers; };
+  // signal a barrier of the MMA issuer (in the leader CTA of a pair)
+  auto arrive_issuer = [&](uint64_t* bar) {
+    if (!PAIR) {
+      mbar_arrive(bar);
+    } else {
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0);
+      }
+    }
+  };
 
   if (warp == 0) {
     // ===================================================================== weight producer
@@ -355,15 +384,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         for (int c = 0; c < N_FWD_CHUNKS; ++c) {
           const uint32_t bytes = fwd_chunk_bytes(c);
           mbar_wait(&bars.w_empty[stage], phase ^ 1);
-          mbar_expect_tx(&bars.w_full[stage], bytes);
-          bulk_g2s(smem + SMEM_W + stage * W_STAGE_BYTES, p.wblob + off, bytes, &bars.w_full[stage]);
+          if (!PAIR) {
+            mbar_expect_tx(&bars.w_full[stage], bytes);
+            bulk_g2s(smem + SMEM_W + stage * STB, p.wblob + off, bytes, &bars.w_full[stage]);
+          } else {
+            mbar_expect_tx(&bars.w_full[stage], bytes / 2);
+            const uint32_t half = (uint32_t)fwd_chunk_rows(c) * 64u;     // (rows / 2) * 128 bytes per K-block
+            for (int kb = 0; kb < fwd_chunk_nkb(c); ++kb)
+              bulk_g2s(smem + SMEM_W + stage * STB + kb * half, p.wblob + off + kb * 2 * half + rank * half, half,
+                       &bars.w_full[stage]);
+          }
           off += bytes;
-          if (++stage == NUM_STAGES) {
+          if (++stage == NS) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
+    }
+  } else if (warp == 1 && PAIR && rank == 1) {
+    // ===================================================================== peer relay: "my half of the stage landed"
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_my_tiles; ++it)
+        for (int c = 0; c < N_FWD_CHUNKS; ++c) {
+          mbar_wait(&bars.w_full[stage], phase);
+          mbar_arrive_remote(&bars.w_peer[stage], 0);
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -372,23 +424,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       uint32_t wphase = 0;
       uint32_t ar_phase = 0;  // bit g: parity of the next completion of act_ready[g]
       int buf = 0;
-      constexpr uint32_t ID256 = instr_desc_bf16(128, 256, 0, 0);
-      constexpr uint32_t ID128 = instr_desc_bf16(128, 128, 0, 0);
-      constexpr uint32_t ID16 = instr_desc_bf16(128, 16, 0, 0);
+      constexpr int MM = PAIR ? 256 : 128;
+      constexpr uint32_t ID256 = instr_desc_bf16(MM, 256, 0, 0);
+      constexpr uint32_t ID128 = instr_desc_bf16(MM, 128, 0, 0);
+      constexpr uint32_t ID16 = instr_desc_bf16(MM, 16, 0, 0);
+      constexpr uint32_t BDIV = PAIR ? 2 : 1;     // a CTA of a pair holds half of the rows of every B K-block
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) mma_commit_2cta(bar); else mma_commit(bar);
+      };
+      // Barriers the operand producers of BOTH CTAs arrive on.  The issuing thread never reads the peer's operands
+      // itself (the peer's tensor core does, after the peer's own fence.proxy.async), so the plain CTA-scope wait
+      // is enough -- and a cluster-scope acquire on every poll costs ~2.5k cycles per layer (measured).
+      auto wait_in = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
       auto ring_wait = [&]() -> uint32_t {
         mbar_wait(&bars.w_full[stage], wphase);
+        if (PAIR) mbar_wait(&bars.w_peer[stage], wphase);
         tc_fence_after();
-        return s_w + (uint32_t)stage * W_STAGE_BYTES;
+        return s_w + (uint32_t)stage * STB;
       };
       auto ring_release = [&]() {
-        mma_commit(&bars.w_empty[stage]);
-        if (++stage == NUM_STAGES) {
+        commit(&bars.w_empty[stage]);
+        if (++stage == NS) {
           stage = 0;
           wphase ^= 1;
         }
       };
       auto wait_act = [&](int g) {
-        mbar_wait(&bars.act_ready[g], (ar_phase >> g) & 1u);
+        wait_in(&bars.act_ready[g], (ar_phase >> g) & 1u);
         ar_phase ^= (1u << g);
         tc_fence_after();
       };
@@ -396,10 +458,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       constexpr uint32_t HI = desc_hi_sw128(1024);
       auto issue_kb = [&](uint32_t a_addr, uint32_t b_addr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool& acc) {
         const uint32_t a_lo = desc_lo(a_addr, 16), b_lo = desc_lo(b_addr, 16);
-        mma_bf16_ss_lo(tmem_d, a_lo, b_lo, HI, idesc, acc ? 1u : 0u);
-        mma_bf16_ss_lo(tmem_d, a_lo + 2, b_lo + 2, HI, idesc, 1u);
-        mma_bf16_ss_lo(tmem_d, a_lo + 4, b_lo + 4, HI, idesc, 1u);
-        if (ksteps == 4) mma_bf16_ss_lo(tmem_d, a_lo + 6, b_lo + 6, HI, idesc, 1u);
+        auto mma = [&](uint32_t k2, uint32_t accum) {
+          if (PAIR) mma_bf16_ss_lo_2cta(tmem_d, a_lo + k2, b_lo + k2, HI, idesc, accum);
+          else mma_bf16_ss_lo(tmem_d, a_lo + k2, b_lo + k2, HI, idesc, accum);
+        };
+        mma(0, acc ? 1u : 0u);
+        mma(2, 1u);
+        mma(4, 1u);
+        if (ksteps == 4) mma(6, 1u);
         acc = true;
       };
       for (int it = 0; it < n_my_tiles; ++it) {
@@ -411,7 +477,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
           if (l == 0) {
-            mbar_wait(&bars.enc_full[eb], (uint32_t)(it >> 1) & 1u);
+            wait_in(&bars.enc_full[eb], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
           }
           if (l == 0 || l == 4) {
@@ -430,7 +496,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
               ring_release();
             }
           }
-          mma_commit(&bars.acc_full[buf]);
+          commit(&bars.acc_full[buf]);
           buf ^= 1;
         }
         // ---- layer 8: bottleneck (N=256) + heads (N=16, other buffer, columns 240..255)
@@ -446,10 +512,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           const uint32_t w = ring_wait();
           bool acc_h = false;
           for (int kb = 0; kb < 4; ++kb)
-            issue_kb(s_act + kb * BLOCK_BYTES, w + kb * (N_HEAD * 128), 4, ID16,
+            issue_kb(s_act + kb * BLOCK_BYTES, w + kb * (N_HEAD * 128 / BDIV), 4, ID16,
                      tmem + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, acc_h);
           ring_release();
-          mma_commit(&bars.acc_full[buf]);
+          commit(&bars.acc_full[buf]);
           buf ^= 1;
         }
         // ---- layer 9: mid MLP, A = [bottleneck 256 | IDE 48], N = 128
@@ -461,16 +527,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
             wait_act(2 * c + 1);
             const uint32_t w = ring_wait();
             issue_kb(s_act + (2 * c) * BLOCK_BYTES, w, 4, ID128, tm, acc);
-            issue_kb(s_act + (2 * c + 1) * BLOCK_BYTES, w + 128 * 128, 4, ID128, tm, acc);
+            issue_kb(s_act + (2 * c + 1) * BLOCK_BYTES, w + 128 * 128 / BDIV, 4, ID128, tm, acc);
             ring_release();
           }
-          mbar_wait(&bars.ide_ready, (uint32_t)it & 1u);
+          wait_in(&bars.ide_ready, (uint32_t)it & 1u);
           tc_fence_after();
           const uint32_t w = ring_wait();
           issue_kb(enc_a, w, IDE_KSTEPS, ID128, tm, acc);
           ring_release();
-          mma_commit(&bars.acc_full[buf]);
-          mma_commit(&bars.enc_empty[eb]);
+          commit(&bars.acc_full[buf]);
+          commit(&bars.enc_empty[eb]);
           buf ^= 1;
         }
         // ---- layer 10: rgb head, A = mid hidden 128, N = 16
@@ -481,9 +547,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           wait_act(1);
           const uint32_t w = ring_wait();
           issue_kb(s_act, w, 4, ID16, tm, acc);
-          issue_kb(s_act + BLOCK_BYTES, w + N_HEAD * 128, 4, ID16, tm, acc);
+          issue_kb(s_act + BLOCK_BYTES, w + N_HEAD * 128 / BDIV, 4, ID16, tm, acc);
           ring_release();
-          mma_commit(&bars.acc_full[buf]);
+          commit(&bars.acc_full[buf]);
           buf ^= 1;
         }
       }
@@ -498,10 +564,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     int buf = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
       const int eb = it & 1;
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = tile_of(it);
       const int pt = tile * TILE + row;
       const bool valid = pt < p.n_points;
-      uint8_t* const st = p.stash ? p.stash + (size_t)tile * STASH_BLOCKS * BLOCK_BYTES : nullptr;
+      uint8_t* const st = (p.stash && tile < p.n_tiles) ? p.stash + (size_t)tile * STASH_BLOCKS * BLOCK_BYTES : nullptr;
       auto sblk = [&](int b) -> uint8_t* { return st ? st + (size_t)b * BLOCK_BYTES : nullptr; };
       auto wait_acc = [&]() {
         mbar_wait(&bars.acc_full[buf], (af_phase >> buf) & 1u);
@@ -517,7 +583,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           fence_proxy_async();
         }
         tc_fence_before();
-        mbar_arrive(bar);
+        arrive_issuer(bar);
       };
       // The slice about to be overwritten was handed to the TMA engine 4 bulk groups ago (layer l-1, same g),
       // except in layer 0, where blocks 0/1 were last stored by the previous tile's mid layer, 2 groups ago.
@@ -662,8 +728,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     const int row = (warp - 2) * 32 + lane;
     for (int it = 0; it < n_my_tiles; ++it) {
       const int eb = it & 1;
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = tile_of(it);
       const int pt = tile * TILE + row;
+      const bool stash_on = p.stash && tile < p.n_tiles;
       float xm[3] = {0.f, 0.f, 0.f}, dg[3] = {0.f, 0.f, 0.f};
       if (pt < p.n_points) {
         if (p.mode == 0) {
@@ -691,8 +758,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       if (p.debug & 2) xm[0] = xm[1] = xm[2] = 0.f, dg[0] = dg[1] = dg[2] = 100.f;
       mbar_wait(&bars.enc_empty[eb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
       const uint32_t enc_blk = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
-      encode_row(enc_blk, row, xm, dg, p.stash != nullptr);
-      if (p.stash) {
+      encode_row(enc_blk, row, xm, dg, stash_on);
+      if (stash_on) {
         // stash the two enc blocks (this warp's rows) and wait until the TMA engine has READ them: the epilogue
         // warps overwrite block 0 with the IDE later in the tile
         uint8_t* se = p.stash + ((size_t)tile * STASH_BLOCKS + STASH_ENC) * BLOCK_BYTES;
@@ -708,14 +775,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       } else {
         fence_proxy_async();
       }
-      mbar_arrive(&bars.enc_full[eb]);
+      arrive_issuer(&bars.enc_full[eb]);
     }
   }
 
   if (p.stash && lane == 0 && warp >= 2) bulk_wait_all<0>();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_2cta(tmem, 512); else tmem_dealloc(tmem, 512);
+  }
 }
 
 }  // namespace
@@ -766,12 +835,34 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
   const size_t smem = SMEM_TOTAL + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   RSN_CUDA(cudaMemcpyToSymbolAsync(c_bias4, bias, N_BIAS * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
-  const int grid = std::min(p.n_tiles, rsn_num_sms());
-  field_fwd_kernel<<<grid, NUM_THREADS, smem, stream>>>(p);
+  // CTA pairs (cta_group::2) are opt-in (RSN_FWD_PAIR=1): validated bit-for-bit against the single-CTA form, but with
+  // one tile in flight per CTA the two cross-CTA hops per layer (commit multicast -> peer epilogue -> remote arrive
+  // -> issuer) cost what the halved shared-memory traffic saves: 2.86 ms vs 2.63 ms at C2.
+  const bool pair = p.n_tiles > 1 && getenv("RSN_FWD_PAIR") && atoi(getenv("RSN_FWD_PAIR")) == 1;
+  if (!pair) {
+    const int grid = std::min(p.n_tiles, rsn_num_sms());
+    field_fwd_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
+  } else {
+    const int pairs = std::min((p.n_tiles + 1) / 2, rsn_num_sms() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RSN_CUDA(cudaLaunchKernelEx(&cfg, field_fwd_kernel<true>, p));
+  }
   RSN_LAUNCH_CHECK("field_fwd_kernel");
   return 0;
 }

@@ -47,6 +47,11 @@ constexpr uint32_t BT_L4E = BT_LBASE + 7 * 131072;     // [128 enc (99 used)][25
 constexpr uint32_t BT_L0 = BT_L4E + 65536;             // [128 enc (99 used)][256]                 4 x 16 KB
 constexpr uint32_t BWD_BLOB_BYTES = BT_L0 + 65536;     // 1,294,336
 
+// rows (output features) and K-blocks of forward chunk c: a CTA pair (cta_group::2) stages rows [r N/2, (r+1) N/2)
+// of every K-block in CTA r
+__host__ __device__ constexpr int fwd_chunk_rows(int c) { return c < 36 ? 256 : c == 36 ? 16 : c < 40 ? 128 : 16; }
+__host__ __device__ constexpr int fwd_chunk_nkb(int c) { return c < 36 ? 1 : c == 36 ? 4 : c < 39 ? 2 : c == 39 ? 1 : 2; }
+
 // ---- bias vector (fp32) -----------------------------------------------------------------------------
 constexpr int BIAS_BASE = 0;          // 8 x 256
 constexpr int BIAS_BOTT = 2048;       // 256

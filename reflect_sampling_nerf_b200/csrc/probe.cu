@@ -321,3 +321,57 @@ extern "C" int rsn_probe_umma_2cta(const void* x_blocks, const void* w_blocks, i
   RSN_LAUNCH_CHECK("probe_2cta_kernel");
   return 0;
 }
+
+// ---- issue-rate probe for the CTA pair: cycles per M256 x N x K16 cta_group::2 MMA (leader's clock)
+namespace {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160, 1) probe_rate2_kernel(int N, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < 6 * 16384 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  __syncthreads();
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(&bar_mma, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta(&tmem_base_slot, 512);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  if (warp == 4 && lane == 0 && rank == 0) {
+    const uint32_t idesc = instr_desc_bf16(256, N, 0, 0);
+    const uint32_t a_lo = desc_lo(smem_u32(smem), 16), b_lo = desc_lo(smem_u32(smem) + 2 * 16384, 16);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        mma_bf16_ss_lo_2cta(tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi_sw128(1024), idesc, (i | k) != 0);
+    }
+    mma_commit_2cta(&bar_mma);
+    mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  if (rank == 1 && warp == 4 && lane == 0) mbar_wait(&bar_mma, 0);
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 4) tmem_dealloc_2cta(tmem, 512);
+}
+}  // namespace
+
+extern "C" int rsn_probe_umma_rate_2cta(int64_t n, int64_t iters, int64_t n_pairs, int64_t* cycles_out, cudaStream_t stream) {
+  RSN_ARG(n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && iters % 4 == 0 && n_pairs >= 1, "rsn_probe_umma_rate_2cta: bad arguments");
+  size_t smem = 6 * 16384 + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_rate2_kernel<<<(int)(2 * n_pairs), 160, smem, stream>>>((int)n, (int)iters, (long long*)cycles_out);
+  RSN_LAUNCH_CHECK("probe_rate2_kernel");
+  return 0;
+}

@@ -20,3 +20,8 @@ for n in (256, 128):
     for commit in (0, 1, 2, 4):
         for switch in (0, 1, 2, 4):
             print(f"N={n} commit every {4*commit:2d} MMAs, switch accumulator every {4*switch:2d} MMAs: {run2(n, commit, switch):.1f} cycles/MMA")
+for n in (256, 128, 16):
+    for pairs in (1, 74):
+        _lib.call("rsn_probe_umma_rate_2cta", n, 4096, pairs, out.data_ptr(), _lib.stream())
+        torch.cuda.synchronize()
+        print(f"cta_group::2 M=256 N={n} on {pairs} pair(s): {out.item() / 4096:.1f} cycles/MMA")

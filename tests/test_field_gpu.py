@@ -96,3 +96,17 @@ def test_inf_color_matches_oracle():
     with torch.no_grad():
         ref = field.inf_color(w, sq)
     torch.testing.assert_close(rgb, ref, rtol=0, atol=1e-2)
+
+
+def test_cta_pair_form_is_bit_identical(monkeypatch):
+    """The cta_group::2 form of the forward kernel (RSN_FWD_PAIR=1) against the default single-CTA form: same
+    arithmetic in the same order => identical bits, including an odd tile count (void second tile of the last pair)."""
+    field, o, d, pa, bins = _setup(37, 24, 5, "uniform", 8.1e-7)      # 888 points = 7 tiles
+    wblob, bias = [t.cuda() for t in packing.pack_field(field.state_dict())]
+    args = (wblob, bias, o.cuda(), d.cuda(), pa.cuda(), bins.cuda())
+    monkeypatch.delenv("RSN_FWD_PAIR", raising=False)
+    s0, f0 = ops.field_forward(*args)
+    monkeypatch.setenv("RSN_FWD_PAIR", "1")
+    s1, f1 = ops.field_forward(*args)
+    torch.cuda.synchronize()
+    assert torch.equal(s0, s1) and torch.equal(f0, f1)
