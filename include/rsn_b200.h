@@ -128,6 +128,12 @@ int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_t n_points,
 int rsn_field_wgrad_layout(int64_t* host_offsets, int64_t* host_shapes, int64_t* total_floats);
 
 int64_t rsn_field_blob_bytes(void);
+/* Packs the 32 fp32 parameter tensors of the field (HOST array of DEVICE pointers, order documented in
+ * csrc/pack.cu: base weights 0-7, base biases 8-15, bottleneck, mid, rgb, density, normals, roughness, diff,
+ * tint -- weight then bias each; names of reflect_sampling_nerf_field.py:54-86) into the forward blob, the
+ * transposed blob, the bias vector and the bf16 density row.  Derived state: call after every optimizer step. */
+int rsn_pack_field(const float* const* params, void* wblob, void* wblob_t, float* bias, void* wd_bf16,
+                   rsn_stream_t stream);
 int64_t rsn_field_bias_count(void);
 /* The 16 IPE frequencies 2**linspace(0,16,16) the kernels use (HOST pointer; for the table test). */
 int rsn_ipe_freqs(float* host_out16);

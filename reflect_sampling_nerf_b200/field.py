@@ -71,7 +71,6 @@ class ReflectSamplingNeRFNerfField(nn.Module):
         self._packed: Optional[Tuple[Tensor, Tensor]] = None
         self._packed_key = None
         self._packed_t: Optional[Tuple[Tensor, Tensor]] = None
-        self._packed_t_key = None
         # training state (see train_path.py): gradient blob of the wgrad kernel for the backward in flight,
         # the reusable dY stash, and the data-parallel world size for the flat gradient all-reduce
         self._grad_blob: Optional[Tensor] = None
@@ -82,22 +81,21 @@ class ReflectSamplingNeRFNerfField(nn.Module):
     def _version_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def packed(self) -> Tuple[Tensor, Tensor]:
-        """(bf16 operand blob, fp32 bias vector) for the current parameter values."""
+    def _repack(self) -> None:
         key = self._version_key()
         if self._packed is None or key != self._packed_key:
             with torch.no_grad():
-                self._packed = packing.pack_field(dict(self.named_parameters()))
-            self._packed_key = key
+                wblob, bias, wblob_t, wd = ops.pack_field(dict(self.named_parameters()))   # one kernel (csrc/pack.cu)
+            self._packed, self._packed_t, self._packed_key = (wblob, bias), (wblob_t, wd), key
+
+    def packed(self) -> Tuple[Tensor, Tensor]:
+        """(bf16 operand blob, fp32 bias vector) for the current parameter values."""
+        self._repack()
         return self._packed
 
     def packed_t(self) -> Tuple[Tensor, Tensor]:
         """(transposed bf16 operand blob of the dgrad chains, bf16 density-head row)."""
-        key = self._version_key()
-        if self._packed_t is None or key != self._packed_t_key:
-            with torch.no_grad():
-                self._packed_t = packing.pack_field_t(dict(self.named_parameters()))
-            self._packed_t_key = key
+        self._repack()
         return self._packed_t
 
     # ------------------------------------------------------------------------------------ evaluation

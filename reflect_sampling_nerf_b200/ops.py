@@ -270,3 +270,24 @@ def field_wgrad(stash: Tensor, dy_stash: Tensor, n_points: int, grad_blob: Tenso
     """K5 wgrad: accumulates dW / db of every Linear over the pass into grad_blob (fp32, wgrad_layout())."""
     with _Prof("field_wgrad_kernel", n_points):
         _lib.call("rsn_field_wgrad", _lib.ptr(stash), _lib.ptr(dy_stash), n_points, _lib.ptr(grad_blob), _lib.stream())
+
+
+PACK_ORDER = ([f"mlp_base.layers.{l}.weight" for l in range(8)] + [f"mlp_base.layers.{l}.bias" for l in range(8)]
+              + [f"{m}.{k}" for m in ("field_output_bottleneck.net", "mlp_mid.layers.0", "field_output_mid.net",
+                                      "field_output_density.net", "field_output_normals.net",
+                                      "field_output_roughness.net", "field_output_diff.net", "field_output_tint.net")
+                 for k in ("weight", "bias")])
+
+
+def pack_field(named_params) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """One-launch packing of the field's fp32 parameters (dict name -> CUDA tensor) into
+    (forward blob, bias vector, transposed blob, bf16 density row) -- csrc/pack.cu."""
+    tensors = [_f32c(named_params[k].detach()) for k in PACK_ORDER]
+    dev = tensors[0].device
+    ptrs = (_ct.c_void_p * len(tensors))(*[_lib.ptr(t) for t in tensors])
+    wblob = torch.empty(_lib.lib().rsn_field_blob_bytes(), dtype=torch.uint8, device=dev)
+    wblob_t = torch.empty(_lib.lib().rsn_field_blob_t_bytes(), dtype=torch.uint8, device=dev)
+    bias = torch.empty(_lib.lib().rsn_field_bias_count(), dtype=torch.float32, device=dev)
+    wd = torch.empty(256, dtype=torch.bfloat16, device=dev)
+    _lib.call("rsn_pack_field", ptrs, _lib.ptr(wblob), _lib.ptr(wblob_t), _lib.ptr(bias), _lib.ptr(wd), _lib.stream())
+    return wblob, bias, wblob_t, wd

@@ -110,3 +110,15 @@ def test_cta_pair_form_is_bit_identical(monkeypatch):
     s1, f1 = ops.field_forward(*args)
     torch.cuda.synchronize()
     assert torch.equal(s0, s1) and torch.equal(f0, f1)
+
+
+def test_pack_kernel_matches_host_packing():
+    """csrc/pack.cu (one launch) against the tensor-op packers of packing.py: identical bytes."""
+    torch.manual_seed(9)
+    sd = {k: v.cuda() for k, v in R.OracleField().state_dict().items()}
+    wblob, bias, wblob_t, wd = ops.pack_field(sd)
+    rb, rbias = packing.pack_field(sd)
+    rbt, rwd = packing.pack_field_t(sd)
+    torch.cuda.synchronize()
+    assert torch.equal(wblob, rb) and torch.equal(bias, rbias)
+    assert torch.equal(wblob_t, rbt) and torch.equal(wd, rwd)
