@@ -69,10 +69,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
     if ((int)blockIdx.x >= p.jobs[i].cta_begin && (int)blockIdx.x < p.jobs[i].cta_begin + p.jobs[i].n_ctas) j = i;
   const WJob job = p.jobs[j];
   const int split = (int)blockIdx.x - job.cta_begin;
-  const int t0 = (int)(((int64_t)p.n_tiles * split) / job.n_ctas);
-  const int t1 = (int)(((int64_t)p.n_tiles * (split + 1)) / job.n_ctas);
+  // tiles split, split + n_ctas, ...: the CTAs of a job stream neighbouring tiles at the same time
+  const bool interleave = !(p.debug & 8);
+  const int t0 = interleave ? split : (int)(((int64_t)p.n_tiles * split) / job.n_ctas);
+  const int t1 = interleave ? p.n_tiles : (int)(((int64_t)p.n_tiles * (split + 1)) / job.n_ctas);
+  const int tstep = interleave ? job.n_ctas : 1;
   const int mb = job.m_blocks, nb = job.n_blocks;
-  const int n_slabs = (t1 - t0) * (TILE / SLAB_ROWS);
+  const int n_slabs = (t1 > t0 ? (t1 - t0 + tstep - 1) / tstep : 0) * (TILE / SLAB_ROWS);
 
   if (warp == 1) {
     if (lane == 0) {
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
     if (lane == 0 && (p.debug & 3) != 1) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = t0; t < t1; ++t) {
+      for (int t = t0; t < t1; t += tstep) {
         const uint8_t* dyt = p.dy + ((size_t)t * DY_BLOCKS + job.a_blk) * BLOCK_BYTES;
         const uint8_t* xt = p.x + ((size_t)t * STASH_BLOCKS + job.b_blk) * BLOCK_BYTES;
         for (int s = 0; s < TILE / SLAB_ROWS; ++s) {
