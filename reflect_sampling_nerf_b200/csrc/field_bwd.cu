@@ -32,12 +32,12 @@ using namespace rsnf;
 
 constexpr int KIND_NORMALS = 0, KIND_BACKWARD = 1;
 constexpr int B_THREADS = 224;
-constexpr int NUM_WSTAGES = 3, NUM_MSTAGES = 3;
+constexpr int NUM_WSTAGES = 3, NUM_MSTAGES = 2;   // the second ring only carries the two stashed enc blocks
 constexpr int SM_ACT = 0;                                  // 4 blocks: dY, rewritten in place step by step
 constexpr int SM_SEED = 4 * BLOCK_BYTES;                   // 1 block: d(rgb head) cols 0-15, d(heads) cols 16-31
 constexpr int SM_W = SM_SEED + BLOCK_BYTES;                // weight ring
-constexpr int SM_M = SM_W + NUM_WSTAGES * W_STAGE_BYTES;   // mask / encoding ring
-constexpr int SM_TOTAL = SM_M + NUM_MSTAGES * BLOCK_BYTES; // 229,376
+constexpr int SM_M = SM_W + NUM_WSTAGES * W_STAGE_BYTES;   // stashed-encoding ring (IPE Jacobians)
+constexpr int SM_TOTAL = SM_M + NUM_MSTAGES * BLOCK_BYTES; // 212,992
 
 __constant__ float c_freq_b[16] = {
     0x1.0000000000000p+0f,  0x1.0c1b780000000p+1f,  0x1.18c9880000000p+2f,  0x1.26111c0000000p+3f,
@@ -90,9 +90,10 @@ __device__ __forceinline__ uint4 lds128b(uint32_t saddr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
   return v;
 }
-// 0xFFFF in each half whose bf16 value is > 0 (post-ReLU activations are >= +0)
-__device__ __forceinline__ uint32_t relu_mask2(uint32_t h) {
-  return ((h & 0x00007fffu) ? 0x0000ffffu : 0u) | ((h & 0x7fff0000u) ? 0xffff0000u : 0u);
+// Stashed ReLU bit masks (csrc/field_layout.cuh): bit i / 16 + i of word w = columns 32 w + 2 i / + 1 of the group.
+// 0xFFFF in each half of packed word i whose column was > 0 in the forward.
+__device__ __forceinline__ uint32_t relu_mask_word(uint32_t bits, int i) {
+  return ((bits >> i) & 0x00010001u) * 0xffffu;
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -100,15 +101,10 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 // 64 accumulator columns of this row -> (optional ReLU mask from the stashed activation block) -> bf16 ->
 // activation block in place, and (optional) the same chunk into the dY stash.
 template <bool MASK>
-__device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_saddr, uint32_t mask_saddr, int row) {
+__device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_saddr, uint2 mbits, int row) {
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
-  uint4 hm[8];
-  if (MASK) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) hm[c] = lds128b(mask_saddr + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
-  }
   tmem_ld_wait();
   const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
 #pragma unroll
@@ -117,10 +113,12 @@ __device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_
     uint4 pk = make_uint4(pack2(__uint_as_float(x[0]), __uint_as_float(x[1])), pack2(__uint_as_float(x[2]), __uint_as_float(x[3])),
                           pack2(__uint_as_float(x[4]), __uint_as_float(x[5])), pack2(__uint_as_float(x[6]), __uint_as_float(x[7])));
     if (MASK) {
-      pk.x &= relu_mask2(hm[c].x);
-      pk.y &= relu_mask2(hm[c].y);
-      pk.z &= relu_mask2(hm[c].z);
-      pk.w &= relu_mask2(hm[c].w);
+      const uint32_t bits = (c >> 2) ? mbits.y : mbits.x;
+      const int i0 = (c & 3) * 4;
+      pk.x &= relu_mask_word(bits, i0 + 0);
+      pk.y &= relu_mask_word(bits, i0 + 1);
+      pk.z &= relu_mask_word(bits, i0 + 2);
+      pk.w &= relu_mask_word(bits, i0 + 3);
     }
     sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), pk);
   }
@@ -284,13 +282,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
       }
     }
   } else if (warp == 6) {
-    // ===================================================================== stashed-activation producer
+    // ===================================================================== stashed-encoding producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-        const uint8_t* xt = p.x_stash + (size_t)tile * STASH_BLOCKS * BLOCK_BYTES;
+        const uint8_t* xt = p.x_stash + (size_t)tile * STASH_TILE_BYTES;
         auto push = [&](int blk) {
           mbar_wait(&bars.m_empty[stage], phase ^ 1);
           mbar_expect_tx(&bars.m_full[stage], BLOCK_BYTES);
@@ -300,18 +298,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
             phase ^= 1;
           }
         };
-        if (KIND == KIND_BACKWARD) {
-          push(STASH_MIDH);
-          push(STASH_MIDH + 1);
-        }
-        for (int l = 7; l >= 0; --l) {   // masks of h_l, in the order the epilogues consume them
-          if (l == 3 && with_enc) {
-            push(STASH_ENC);
-            push(STASH_ENC + 1);
-          }
-          for (int g = 0; g < 4; ++g) push(STASH_H + 4 * l + g);
-        }
-        if (with_enc) {
+        if (with_enc) {       // before the layer-4 epilogue and again before the layer-0 epilogue
+          push(STASH_ENC);
+          push(STASH_ENC + 1);
           push(STASH_ENC);
           push(STASH_ENC + 1);
         }
@@ -473,6 +462,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
         }
       };
       float red[3] = {0.f, 0.f, 0.f};   // d mean (NORMALS) or dL/d diag (BACKWARD), summed over both enc GEMMs
+      // ReLU bit masks of this row (8 bytes per layer and group), fetched before the accumulator wait of the step
+      const uint2* const mrow = reinterpret_cast<const uint2*>(p.x_stash + (size_t)tile * STASH_TILE_BYTES + STASH_MASK_OFF);
+      auto load_masks = [&](int layer, int ngroups, uint2 (&mk)[4]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g < ngroups) mk[g] = __ldg(mrow + mask_entry(layer, g, row));
+      };
 
       if (KIND == KIND_BACKWARD) {
         // ---- seed: head pre-activation gradients of this point -> seed block (and the dY stash)
@@ -526,11 +522,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
         }
         publish(&bars.seed_ready, s_seed, dblk(DY_SEED));
         // ---- E0: d mid_hidden * (mid_hidden > 0) -> dY_mid (act blocks 0,1)
+        uint2 mk0[4];
+        load_masks(8, 2, mk0);
         wait_acc();
         for (int g = 0; g < 2; ++g) {
-          const uint32_t ms = mask_wait();
-          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, ms, row);
-          mask_release();
+          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, mk0[g], row);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, dblk(DY_MID + g));
         }
         buf ^= 1;
@@ -538,30 +534,33 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
         wait_acc();
         for (int g = 0; g < 4; ++g) {
           warp_store_guard<1>(lane);   // blocks 0/1 were handed to the TMA engine by E0, 2 groups ago
-          dgrad_group<false>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, 0, row);
+          dgrad_group<false>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, make_uint2(0u, 0u), row);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, dblk(DY_BOTT + g));
         }
         buf ^= 1;
       } else {
         // ---- NORMALS seed: dY_7 = w_density * (h7 > 0)
+        uint2 mk7[4];
+        load_masks(7, 4, mk7);
         for (int g = 0; g < 4; ++g) {
-          const uint32_t ms = mask_wait();
           const uint32_t row_saddr = s_act + g * BLOCK_BYTES + (uint32_t)row * 128u;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const uint32_t off = (uint32_t)((c ^ (row & 7)) << 4);
-            const uint4 hm = lds128b(ms + (uint32_t)row * 128u + off);
             const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.wd_bf16) + g * 8 + c);
-            sts128b(row_saddr + off, make_uint4(wv.x & relu_mask2(hm.x), wv.y & relu_mask2(hm.y),
-                                                wv.z & relu_mask2(hm.z), wv.w & relu_mask2(hm.w)));
+            const uint32_t bits = (c >> 2) ? mk7[g].y : mk7[g].x;
+            const int i0 = (c & 3) * 4;
+            sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4),
+                    make_uint4(wv.x & relu_mask_word(bits, i0), wv.y & relu_mask_word(bits, i0 + 1),
+                               wv.z & relu_mask_word(bits, i0 + 2), wv.w & relu_mask_word(bits, i0 + 3)));
           }
-          mask_release();
           publish(&bars.act_ready[g]);
         }
       }
       // ---- chain: (BACKWARD: E2 = d emb) then layers 7..1; each: acc * (h_{l-1} > 0) -> dY_{l-1}
       const int first = (KIND == KIND_BACKWARD) ? 8 : 7;
       for (int l = first; l >= 1; --l) {
+        uint2 mk[4];
+        load_masks(l - 1, 4, mk);       // this step masks with h_{l-1}
         wait_acc();
         if (l == 4 && with_enc) {
           // encoding part of layer 4 (other accumulator, columns 0..111): consume before the hidden part
@@ -580,11 +579,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
           mask_release();
         }
         for (int g = 0; g < 4; ++g) {
-          const uint32_t ms = mask_wait();
           guard();
           // output = dY_{l-1}: stash block DY_H + 4 (l-1) + g
-          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, ms, row);
-          mask_release();
+          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, mk[g], row);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES,
                   (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr);
         }

@@ -279,9 +279,12 @@ __device__ __forceinline__ void ide_features(const float d[3], float rho, float 
 
 // ---------------------------------------------------------------------------------------------- epilogue
 // 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> activation block `blk`.
-template <bool RELU>
+// MASKS (training): also emit the ReLU bit masks of the group (a separate instantiation, so that the inference path keeps
+// its branch-free schedule: a runtime test of the mask pointer inside the chunk loop cost 0.47 ms of 2.62 at C2)
+template <bool RELU, bool MASKS = false>
 __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
-                                               bool nobias = false) {
+                                               bool nobias = false, uint2* mask_out = nullptr) {
+  uint32_t mbits[2] = {0u, 0u};
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
@@ -307,8 +310,20 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
       }
       const int chunk = h * 4 + c;
       sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      if (RELU && MASKS) {
+        // ReLU mask bits of the 8 columns just packed: one packed compare (0xFFFF per half > 0) and one LOP3 per
+        // word; word i of the 32-column half contributes bits i and 16 + i
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = c * 4 + j;
+          __nv_bfloat162 hv;
+          *reinterpret_cast<uint32_t*>(&hv) = pk[j];
+          mbits[h] |= __hgt2_mask(hv, __nv_bfloat162(__float2bfloat16(0.f), __float2bfloat16(0.f))) & (0x00010001u << i);
+        }
+      }
     }
   }
+  if (RELU && MASKS) *mask_out = make_uint2(mbits[0], mbits[1]);
 }
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __expf(-x)); }
@@ -567,7 +582,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       const int tile = tile_of(it);
       const int pt = tile * TILE + row;
       const bool valid = pt < p.n_points;
-      uint8_t* const st = (p.stash && tile < p.n_tiles) ? p.stash + (size_t)tile * STASH_BLOCKS * BLOCK_BYTES : nullptr;
+      uint8_t* const st = (p.stash && tile < p.n_tiles) ? p.stash + (size_t)tile * STASH_TILE_BYTES : nullptr;
       auto sblk = [&](int b) -> uint8_t* { return st ? st + (size_t)b * BLOCK_BYTES : nullptr; };
       auto wait_acc = [&]() {
         mbar_wait(&bars.acc_full[buf], (af_phase >> buf) & 1u);
@@ -598,8 +613,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           } else {
             guard();
           }
-          epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
-                               s_act + g * BLOCK_BYTES, row, (p.debug & 1) != 0);
+          if (st)
+            epilogue_group<true, true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
+                                       s_act + g * BLOCK_BYTES, row, false,
+                                       reinterpret_cast<uint2*>(st + STASH_MASK_OFF) + mask_entry(l, g, row));
+          else
+            epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
+                                 s_act + g * BLOCK_BYTES, row, (p.debug & 1) != 0);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_H + 4 * l + g));
         }
         buf ^= 1;
@@ -692,8 +712,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         for (int g = 0; g < 2; ++g) {
           guard();
-          epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64,
-                               s_act + g * BLOCK_BYTES, row);
+          if (st)
+            epilogue_group<true, true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64, s_act + g * BLOCK_BYTES,
+                                       row, false, reinterpret_cast<uint2*>(st + STASH_MASK_OFF) + mask_entry(8, g, row));
+          else
+            epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64, s_act + g * BLOCK_BYTES, row);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_MIDH + g));
         }
         buf ^= 1;
@@ -762,7 +785,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       if (stash_on) {
         // stash the two enc blocks (this warp's rows) and wait until the TMA engine has READ them: the epilogue
         // warps overwrite block 0 with the IDE later in the tile
-        uint8_t* se = p.stash + ((size_t)tile * STASH_BLOCKS + STASH_ENC) * BLOCK_BYTES;
+        uint8_t* se = p.stash + (size_t)tile * STASH_TILE_BYTES + (size_t)STASH_ENC * BLOCK_BYTES;
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -799,7 +822,7 @@ extern "C" int64_t rsn_field_blob_bytes(void) { return (int64_t)FWD_BLOB_BYTES; 
 extern "C" int64_t rsn_field_bias_count(void) { return (int64_t)N_BIAS; }
 
 extern "C" int64_t rsn_field_stash_bytes(int64_t n_points) {
-  return ((n_points + TILE - 1) / TILE) * (int64_t)STASH_BLOCKS * BLOCK_BYTES;
+  return ((n_points + TILE - 1) / TILE) * (int64_t)STASH_TILE_BYTES;
 }
 
 extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int mode, const float* origins,

@@ -67,6 +67,15 @@ constexpr int STASH_BOTT = 34;   // 4 blocks: bottleneck (no activation)
 constexpr int STASH_IDE = 38;    // 1 block: IDE (columns 34..63 zero)
 constexpr int STASH_MIDH = 39;   // 2 blocks: mid hidden (post-ReLU)
 constexpr int STASH_BLOCKS = 41;
+// ... followed by the ReLU bit masks of the 8 hidden layers and the mid hidden layer: [9 layers][4 groups][128 rows]
+// x 8 bytes; bit i (i < 16) of word w (w = 0, 1) of a row's entry = column 32 w + 2 i of the 64-column group is > 0,
+// bit 16 + i = column 32 w + 2 i + 1.  The dgrad chains read these 288 B per point instead of the 4.4 KB of
+// activations they mask with.
+constexpr int MASK_LAYERS = 9;     // 0..7 = h_l, 8 = mid hidden (groups 0,1)
+constexpr int STASH_MASK_OFF = STASH_BLOCKS * BLOCK_BYTES;
+constexpr int STASH_MASK_BYTES = MASK_LAYERS * 4 * TILE * 8;               // 36,864
+constexpr int STASH_TILE_BYTES = STASH_MASK_OFF + STASH_MASK_BYTES;        // 708,608 per 128-point tile
+__host__ __device__ constexpr int mask_entry(int layer, int group, int row) { return ((layer * 4 + group) * TILE + row); }
 
 // ---- dgrad stash: per tile, DY_BLOCKS block images of the pre-activation gradients (written by the dgrad chain)
 constexpr int DY_SEED = 0;       // 1 block: columns 0-15 d(rgb head pre-activation), 16-31 d(heads pre-activation)

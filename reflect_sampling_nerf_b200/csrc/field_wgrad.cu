@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
       uint32_t phase = 0;
       for (int t = t0; t < t1; t += tstep) {
         const uint8_t* dyt = p.dy + ((size_t)t * DY_BLOCKS + job.a_blk) * BLOCK_BYTES;
-        const uint8_t* xt = p.x + ((size_t)t * STASH_BLOCKS + job.b_blk) * BLOCK_BYTES;
+        const uint8_t* xt = p.x + (size_t)t * STASH_TILE_BYTES + (size_t)job.b_blk * BLOCK_BYTES;
         for (int s = 0; s < TILE / SLAB_ROWS; ++s) {
           mbar_wait(&bars.empty[stage], phase ^ 1);
           mbar_expect_tx(&bars.full[stage], (uint32_t)(mb + nb) * SLAB_BLOCK_BYTES);

@@ -21,10 +21,10 @@ FLOP_PER_POINT = {0: 1230592, 1: 1225472}   # SURVEY.md §8d (forward; primary f
 # algorithmic (FLOPs, HBM bytes) per point of the four field kernels
 KERNEL_WORK = {
     "field_fwd_kernel": (1230592, 68),
-    "field_fwd_kernel[train]": (1230592, 68 + 32 + 41 * 128),
-    "field_chain_kernel<normals>": (1019392, 34 * 128 + 12),
-    "field_chain_kernel<backward>": (1179904, 34 * 128 + 39 * 128 + 160),
-    "field_chain_kernel<backward+area>": (1229056, 38 * 128 + 39 * 128 + 164),
+    "field_fwd_kernel[train]": (1230592, 68 + 32 + 41 * 128 + 288),
+    "field_chain_kernel<normals>": (1019392, 288 + 4 * 128 + 12),
+    "field_chain_kernel<backward>": (1179904, 288 + 39 * 128 + 160),
+    "field_chain_kernel<backward+area>": (1229056, 288 + 4 * 128 + 39 * 128 + 164),
     "field_wgrad_kernel": (1230592, 95 * 128),
 }
 

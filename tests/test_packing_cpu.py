@@ -32,7 +32,7 @@ def test_layout_constants_match_library():
     assert lib.rsn_field_blob_bytes() == packing.FWD_BLOB_BYTES
     assert lib.rsn_field_blob_t_bytes() == packing.BWD_BLOB_BYTES
     assert lib.rsn_field_bias_count() == packing.N_BIAS
-    assert lib.rsn_field_stash_bytes(129) == 2 * 41 * 16384
+    assert lib.rsn_field_stash_bytes(129) == 2 * (41 * 16384 + 9 * 4 * 128 * 8)
     assert lib.rsn_field_dy_stash_bytes(128) == 39 * 16384
     offs, shapes, total = ops.wgrad_layout()
     assert len(shapes) == 14 and total == sum(m * n for m, n in shapes) + sum(m for (m, n), o in zip(shapes, offs[1::2]) if o >= 0)

@@ -21,7 +21,9 @@ def test_wgrad_matches_matmul(n_tiles):
     x = (torch.randn(pts, STASH_BLOCKS * 64, generator=g) * 0.5).bfloat16()
     dy = (torch.randn(pts, DY_BLOCKS * 64, generator=g) * 0.1).bfloat16()
     # stash layout: [tile][block][16 KB]; pack_blocks gives [K/64 blocks][rows][128] for a [rows, K] matrix
-    xs = torch.stack([pack_blocks(x[t * 128:(t + 1) * 128]) for t in range(n_tiles)]).cuda()
+    # (each forward-stash tile is followed by 36,864 bytes of ReLU bit masks the wgrad does not read)
+    xs = torch.stack([torch.cat([pack_blocks(x[t * 128:(t + 1) * 128]).reshape(-1),
+                                 torch.zeros(36864, dtype=torch.uint8)]) for t in range(n_tiles)]).cuda()
     dys = torch.stack([pack_blocks(dy[t * 128:(t + 1) * 128]) for t in range(n_tiles)]).cuda()
     offs, shapes, total = ops.wgrad_layout()
     assert len(shapes) == len(JOBS)
