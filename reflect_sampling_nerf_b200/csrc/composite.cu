@@ -204,6 +204,164 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vectorised forms for C = 4 Q channels (Q = 1, 2, 4; the model composites all 16 feature channels at once).
+// The per-sample weights of a ray go through a warp-private shared-memory row; the features are then read as
+// float4 with lane <-> (sample, channel quad), so one warp instruction covers 512 contiguous bytes, instead of
+// one lane walking its samples' channels with 4-byte loads.  The backward makes a single pass over the features.
+template <int K, int Q>
+__global__ void __launch_bounds__(256) composite_fwd_vec_kernel(
+    const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
+    int64_t bin_stride, const float4* __restrict__ feat4, float* __restrict__ weights, float* __restrict__ acc_out,
+    float* __restrict__ depth_out, float4* __restrict__ feat_out4, int64_t n_rays, int S, int s_pad) {
+  extern __shared__ float sm_rows[];
+  const int lane = threadIdx.x & 31;
+  float* ws = sm_rows + (threadIdx.x >> 5) * s_pad;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rays; r += nwarps) {
+    const float* sg = sigma + r * S;
+    const float* st = starts + r * bin_stride;
+    const float* en = ends + r * bin_stride;
+    double tau_carry = 0.0, cw_carry = 0.0;
+    float acc = 0.f;
+    int median = S;
+    for (int base = 0; base < S; base += 32 * K) {
+      float dd[K], w[K], tn[K];
+      weights_round<K>(sg, st, en, base, S, lane, tau_carry, dd, w, tn);
+      const int s0 = base + lane * K;
+      double local = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (s0 + k < S) {
+          weights[r * S + s0 + k] = w[k];
+          ws[s0 + k] = w[k];
+          acc += w[k];
+        }
+        local += (double)w[k];
+      }
+      const double incl = warp_incl_scan(local, lane);
+      double cw = cw_carry + (incl - local);
+      int mine = S;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        cw += (double)w[k];
+        if (mine == S && s0 + k < S && (float)cw >= 0.5f) mine = s0 + k;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(RSN_FULL, mine, o));
+      median = min(median, mine);
+      cw_carry += __shfl_sync(RSN_FULL, incl, 31);
+    }
+    acc = warp_sum(acc);
+    __syncwarp();
+    const float4* f4 = feat4 + (int64_t)r * S * Q;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int idx = lane; idx < S * Q; idx += 32) {
+      const float4 v = __ldg(f4 + idx);
+      const float wv = ws[idx / Q];
+      a.x += wv * v.x, a.y += wv * v.y, a.z += wv * v.z, a.w += wv * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o >= Q; o >>= 1) {
+      a.x += __shfl_xor_sync(RSN_FULL, a.x, o), a.y += __shfl_xor_sync(RSN_FULL, a.y, o);
+      a.z += __shfl_xor_sync(RSN_FULL, a.z, o), a.w += __shfl_xor_sync(RSN_FULL, a.w, o);
+    }
+    if (lane < Q) feat_out4[r * Q + lane] = a;
+    if (lane == 0) {
+      acc_out[r] = acc;
+      const int mi = min(median, S - 1);
+      depth_out[r] = (__ldg(st + mi) + __ldg(en + mi)) / 2.f;
+    }
+    __syncwarp();
+  }
+}
+
+template <int K, int Q>
+__global__ void __launch_bounds__(256) composite_bwd_vec_kernel(
+    const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
+    int64_t bin_stride, const float4* __restrict__ feat4, const float* __restrict__ g_weights,
+    const float* __restrict__ g_acc, const float4* __restrict__ g_feat_out4, float* __restrict__ g_sigma,
+    float4* __restrict__ g_feat4, int64_t n_rays, int S, int s_pad) {
+  extern __shared__ float sm_rows[];
+  const int lane = threadIdx.x & 31;
+  float* ws = sm_rows + (threadIdx.x >> 5) * 3 * s_pad;   // weights
+  float* tns = ws + s_pad;                                // transmittance behind the sample
+  float* gws = tns + s_pad;                               // dL/dw_s (explicit + accumulation + features)
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rays; r += nwarps) {
+    const float* sg = sigma + r * S;
+    const float* st = starts + r * bin_stride;
+    const float* en = ends + r * bin_stride;
+    const float ga = g_acc ? __ldg(g_acc + r) : 0.f;
+    const float4 go = g_feat_out4 ? __ldg(g_feat_out4 + r * Q + (lane % Q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    double tau_carry = 0.0;
+    for (int base = 0; base < S; base += 32 * K) {
+      float dd[K], w[K], tn[K];
+      weights_round<K>(sg, st, en, base, S, lane, tau_carry, dd, w, tn);
+      const int s0 = base + lane * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (s0 + k < S) ws[s0 + k] = w[k], tns[s0 + k] = tn[k];
+    }
+    __syncwarp();
+    // one pass over the features: dL/dw_s and dL/dfeat
+    const float4* f4 = feat4 + (int64_t)r * S * Q;
+    float4* gf4 = g_feat4 ? g_feat4 + (int64_t)r * S * Q : nullptr;
+#pragma unroll 4
+    for (int idx0 = 0; idx0 < S * Q; idx0 += 32) {
+      const int idx = idx0 + lane;
+      const bool ok = idx < S * Q;
+      const int smp = ok ? idx / Q : 0;
+      const float4 v = ok ? __ldg(f4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float dot = go.x * v.x + go.y * v.y + go.z * v.z + go.w * v.w;
+#pragma unroll
+      for (int o = 1; o < Q; o <<= 1) dot += __shfl_xor_sync(RSN_FULL, dot, o);
+      if (ok) {
+        const float wv = ws[smp];
+        if ((lane % Q) == 0) gws[smp] = ga + (g_weights ? __ldg(g_weights + r * S + smp) : 0.f) + dot;
+        if (gf4) gf4[idx] = make_float4(go.x * wv, go.y * wv, go.z * wv, go.w * wv);
+      }
+    }
+    __syncwarp();
+    // dL/d(dd_j) = gw_j T_{j+1} - sum_{s>j} gw_s w_s ;  dL/dsigma_j = dL/d(dd_j) * delta_j
+    double total = 0.0;
+    for (int s = lane; s < S; s += 32) total += (double)(gws[s] * ws[s]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(RSN_FULL, total, o);
+    double pre_carry = 0.0;
+    for (int base = 0; base < S; base += 32 * K) {
+      const int s0 = base + lane * K;
+      float gw[K], w[K];
+      double local = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool ok = s0 + k < S;
+        gw[k] = ok ? gws[s0 + k] : 0.f;
+        w[k] = ok ? ws[s0 + k] : 0.f;
+        local += (double)(gw[k] * w[k]);
+      }
+      const double incl = warp_incl_scan(local, lane);
+      double pre = pre_carry + (incl - local);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        pre += (double)(gw[k] * w[k]);
+        if (s0 + k < S) {
+          const float delta = __ldg(en + s0 + k) - __ldg(st + s0 + k);
+          g_sigma[r * S + s0 + k] = (gw[k] * tns[s0 + k] - (float)(total - pre)) * delta;
+        }
+      }
+      pre_carry += __shfl_sync(RSN_FULL, incl, 31);
+    }
+    __syncwarp();
+  }
+}
+
+constexpr int VEC_MAX_SAMPLES = 1024;   // 8 warps x 3 rows x 4 KB of dynamic shared memory in the backward
+
 template <int C>
 int launch_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_stride, const float* feat,
                float* weights, float* acc, float* depth, float* feat_out, int64_t n_rays, int S,
@@ -211,6 +369,22 @@ int launch_fwd(const float* sigma, const float* starts, const float* ends, int64
   const int threads = 256;
   int64_t want = (n_rays * 32 + threads - 1) / threads;
   int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
+  if (C >= 4 && C % 4 == 0 && S <= VEC_MAX_SAMPLES && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)feat_out & 15) == 0) {
+    constexpr int Q = C >= 4 ? C / 4 : 1;
+    const int s_pad = (S + 3) & ~3;
+    const size_t smem = (size_t)(threads / 32) * s_pad * sizeof(float);
+    blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 8);
+#define RSN_FWDV(K)                                                                                              \
+  composite_fwd_vec_kernel<K, Q><<<blocks, threads, smem, stream>>>(sigma, starts, ends, bin_stride,             \
+                                                                    (const float4*)feat, weights, acc, depth,    \
+                                                                    (float4*)feat_out, n_rays, S, s_pad)
+    if (S <= 32) RSN_FWDV(1);
+    else if (S <= 64) RSN_FWDV(2);
+    else RSN_FWDV(4);
+#undef RSN_FWDV
+    RSN_LAUNCH_CHECK("composite_fwd_vec_kernel");
+    return 0;
+  }
 #define RSN_FWD(K)                                                                                        \
   composite_fwd_kernel<K, C><<<blocks, threads, 0, stream>>>(sigma, starts, ends, bin_stride, feat, weights, \
                                                              acc, depth, feat_out, n_rays, S)
@@ -229,6 +403,31 @@ int launch_bwd(const float* sigma, const float* starts, const float* ends, int64
   const int threads = 256;
   int64_t want = (n_rays * 32 + threads - 1) / threads;
   int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
+  if (C >= 4 && C % 4 == 0 && S <= VEC_MAX_SAMPLES && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)g_feat_out & 15) == 0 &&
+      ((uintptr_t)g_feat & 15) == 0) {
+    constexpr int Q = C >= 4 ? C / 4 : 1;
+    const int s_pad = (S + 3) & ~3;
+    const size_t smem = (size_t)(threads / 32) * 3 * s_pad * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(composite_bwd_vec_kernel<1, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * VEC_MAX_SAMPLES * 4);
+      cudaFuncSetAttribute(composite_bwd_vec_kernel<2, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * VEC_MAX_SAMPLES * 4);
+      cudaFuncSetAttribute(composite_bwd_vec_kernel<4, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * VEC_MAX_SAMPLES * 4);
+      attr_set = true;
+    }
+    blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 8);
+#define RSN_BWDV(K)                                                                                                \
+  composite_bwd_vec_kernel<K, Q><<<blocks, threads, smem, stream>>>(sigma, starts, ends, bin_stride,               \
+                                                                    (const float4*)feat, g_weights, g_acc,         \
+                                                                    (const float4*)g_feat_out, g_sigma,            \
+                                                                    (float4*)g_feat, n_rays, S, s_pad)
+    if (S <= 32) RSN_BWDV(1);
+    else if (S <= 64) RSN_BWDV(2);
+    else RSN_BWDV(4);
+#undef RSN_BWDV
+    RSN_LAUNCH_CHECK("composite_bwd_vec_kernel");
+    return 0;
+  }
 #define RSN_BWD(K)                                                                                          \
   composite_bwd_kernel<K, C><<<blocks, threads, 0, stream>>>(sigma, starts, ends, bin_stride, feat, g_weights, \
                                                              g_acc, g_feat_out, g_sigma, g_feat, n_rays, S)

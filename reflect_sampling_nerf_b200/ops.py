@@ -26,6 +26,9 @@ KERNEL_WORK = {
     "field_chain_kernel<backward>": (1179904, 288 + 39 * 128 + 160),
     "field_chain_kernel<backward+area>": (1229056, 288 + 4 * 128 + 39 * 128 + 164),
     "field_wgrad_kernel": (1230592, 95 * 128),
+    # K8 at C = 16 channels, per SAMPLE: sigma 4 + bin 4 + feat 64 in, weight 4 out | + dL/dw 4 in, dL/dsigma 4 + dL/dfeat 64 out
+    "composite_fwd_kernel": (0, 76),
+    "composite_bwd_kernel": (0, 144),
 }
 
 
@@ -140,9 +143,10 @@ class _Composite(torch.autograd.Function):
         acc = torch.empty(n, device=dev, dtype=torch.float32)
         depth = torch.empty(n, device=dev, dtype=torch.float32)
         feat_out = torch.empty(n, c, device=dev, dtype=torch.float32)
-        _lib.call("rsn_composite_fwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1,
-                  _lib.ptr(feat), c, _lib.ptr(weights), _lib.ptr(acc), _lib.ptr(depth),
-                  _lib.ptr(feat_out) if c else None, n, s, _lib.stream())
+        with _Prof("composite_fwd_kernel", n * s if c == 16 else 0):
+            _lib.call("rsn_composite_fwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1,
+                      _lib.ptr(feat), c, _lib.ptr(weights), _lib.ptr(acc), _lib.ptr(depth),
+                      _lib.ptr(feat_out) if c else None, n, s, _lib.stream())
         ctx.save_for_backward(sigma, bins, feat if feat is not None else sigma.new_empty(0))
         ctx.c = c
         ctx.mark_non_differentiable(depth)
@@ -157,9 +161,10 @@ class _Composite(torch.autograd.Function):
         g_sigma = torch.empty_like(sigma)
         g_feat = torch.empty_like(feat) if need_feat else None
         g_w, g_acc, g_feat_out = _f32c(g_w), _f32c(g_acc), _f32c(g_feat_out) if c else None
-        _lib.call("rsn_composite_bwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1,
-                  _lib.ptr(feat) if c else None, c, _lib.ptr(g_w), _lib.ptr(g_acc), _lib.ptr(g_feat_out),
-                  _lib.ptr(g_sigma), _lib.ptr(g_feat), n, s, _lib.stream())
+        with _Prof("composite_bwd_kernel", n * s if c == 16 else 0):
+            _lib.call("rsn_composite_bwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1,
+                      _lib.ptr(feat) if c else None, c, _lib.ptr(g_w), _lib.ptr(g_acc), _lib.ptr(g_feat_out),
+                      _lib.ptr(g_sigma), _lib.ptr(g_feat), n, s, _lib.stream())
         return g_sigma, None, g_feat
 
 
