@@ -126,6 +126,10 @@ int64_t rsn_field_dy_stash_bytes(int64_t n_points);
 int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_t n_points, float* grad_blob,
                     rsn_stream_t stream);
 int rsn_field_wgrad_layout(int64_t* host_offsets, int64_t* host_shapes, int64_t* total_floats);
+/* Gradient blob -> flat fp32 gradient vector laid out parameter after parameter in rsn_pack_field order
+ * (rsn_field_flat_layout: HOST array of 32 float offsets, returns the vector length, 617,742).  One launch. */
+int rsn_unpack_grads(const float* grad_blob, float* flat_grads, rsn_stream_t stream);
+int64_t rsn_field_flat_layout(int64_t* host_offsets32);
 
 int64_t rsn_field_blob_bytes(void);
 /* Packs the 32 fp32 parameter tensors of the field (HOST array of DEVICE pointers, order documented in

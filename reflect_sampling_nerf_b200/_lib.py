@@ -30,6 +30,8 @@ _SIGNATURES = {
     "rsn_field_dy_stash_bytes": ([I64], c_int64),
     "rsn_field_wgrad": ([P, P, I64, P, P], c_int),
     "rsn_field_wgrad_layout": ([P, P, P], c_int),
+    "rsn_unpack_grads": ([P, P, P], c_int),
+    "rsn_field_flat_layout": ([P], c_int64),
     "rsn_pack_field": ([P, P, P, P, P, P], c_int),
     "rsn_field_blob_bytes": ([], c_int64),
     "rsn_field_bias_count": ([], c_int64),

@@ -13,6 +13,8 @@
 #include "umma.cuh"
 #include "field_layout.cuh"
 
+extern "C" int rsn_field_wgrad_layout(int64_t* host_offsets, int64_t* host_shapes, int64_t* total_floats);
+
 namespace {
 
 using namespace rsnf;
@@ -165,5 +167,101 @@ extern "C" int rsn_pack_field(const float* const* params, void* wblob, void* wbl
   const int threads = 256, blocks = (b.chunks + threads - 1) / threads;
   pack_kernel<<<blocks, threads, 0, stream>>>(b.p);
   RSN_LAUNCH_CHECK("pack_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Gradient blob of rsn_field_wgrad -> flat fp32 gradient vector in the parameter order of rsn_pack_field
+// (weights row-major [out, in]); the Python side hands out views of the flat vector as the parameters' .grad.
+// One launch instead of ~70 slicing / concatenation / clone kernels per step.
+namespace {
+
+struct UnpackPiece {
+  int dst0;          // first element of this piece in the flat vector
+  int rows, cols;    // destination sub-matrix rows x cols (cols = 1 for bias pieces)
+  int dst_ld, dst_col0;
+  int src0, src_ld;  // blob float offset of element (0, 0) and the row stride in the blob
+  int elem0;         // running element count (for the thread -> piece lookup)
+};
+constexpr int MAX_UNPACK = 48;
+struct UnpackParams {
+  const float* blob;
+  float* flat;
+  int n_pieces, n_elems;
+  UnpackPiece pieces[MAX_UNPACK];
+};
+
+__global__ void __launch_bounds__(256) unpack_kernel(const __grid_constant__ UnpackParams p) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.n_elems; e += gridDim.x * blockDim.x) {
+    int pi = 0;
+    while (pi + 1 < p.n_pieces && p.pieces[pi + 1].elem0 <= e) ++pi;
+    const UnpackPiece& q = p.pieces[pi];
+    const int local = e - q.elem0;
+    const int r = local / q.cols, c = local % q.cols;
+    p.flat[q.dst0 + (size_t)r * q.dst_ld + q.dst_col0 + c] = p.blob[q.src0 + (size_t)r * q.src_ld + c];
+  }
+}
+
+}  // namespace
+
+// Flat-vector offsets (in floats) of the 32 parameters in rsn_pack_field order; returns the total length.
+extern "C" int64_t rsn_field_flat_layout(int64_t* host_offsets32) {
+  static const int rows[32] = {256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256,
+                               256, 256, 128, 128, 3, 3, 1, 1, 3, 3, 1, 1, 3, 3, 3, 3};
+  static const int cols[32] = {99, 256, 256, 256, 355, 256, 256, 256, 1, 1, 1, 1, 1, 1, 1, 1,
+                               256, 1, 290, 1, 128, 1, 256, 1, 256, 1, 256, 1, 256, 1, 256, 1};
+  int64_t off = 0;
+  for (int i = 0; i < 32; ++i) {
+    if (host_offsets32) host_offsets32[i] = off;
+    off += (int64_t)rows[i] * cols[i];
+  }
+  return off;
+}
+
+extern "C" int rsn_unpack_grads(const float* grad_blob, float* flat_grads, cudaStream_t stream) {
+  RSN_ARG(grad_blob && flat_grads, "rsn_unpack_grads: null pointer");
+  int64_t offs[64], shapes[64], total = 0;
+  const int n_jobs = rsn_field_wgrad_layout(offs, shapes, &total);
+  RSN_ARG(n_jobs == 14, "rsn_unpack_grads: unexpected wgrad job table");
+  int64_t po[32];
+  rsn_field_flat_layout(po);
+  UnpackParams u = {};
+  u.blob = grad_blob;
+  u.flat = flat_grads;
+  int elems = 0;
+  auto add = [&](int param, int rows, int cols, int dst_ld, int dst_col0, int64_t src0, int src_ld) {
+    UnpackPiece& q = u.pieces[u.n_pieces++];
+    q = UnpackPiece{(int)po[param], rows, cols, dst_ld, dst_col0, (int)src0, src_ld, elems};
+    elems += rows * cols;
+  };
+  auto dw = [&](int j) { return offs[2 * j]; };
+  auto db = [&](int j) { return offs[2 * j + 1]; };
+  auto ld = [&](int j) { return (int)shapes[2 * j + 1]; };
+  // base layers: job index of layer l (layer 4 = jobs 4 (enc part) + 5 (hidden part))
+  const int base_job[8] = {0, 1, 2, 3, 5, 6, 7, 8};
+  for (int l = 0; l < 8; ++l) {
+    if (l == 0) add(0, 256, 99, 99, 0, dw(0), ld(0));
+    else if (l == 4) {
+      add(4, 256, 99, 355, 0, dw(4), ld(4));
+      add(4, 256, 256, 355, 99, dw(5), ld(5));
+    } else add(l, 256, 256, 256, 0, dw(base_job[l]), ld(base_job[l]));
+    add(8 + l, 256, 1, 1, 0, db(base_job[l]), 1);
+  }
+  add(16, 256, 256, 256, 0, dw(9), ld(9));
+  add(17, 256, 1, 1, 0, db(9), 1);                                     // bottleneck
+  add(18, 128, 34, 290, 0, dw(13), ld(13));
+  add(18, 128, 256, 290, 34, dw(12), ld(12));
+  add(19, 128, 1, 1, 0, db(12), 1);                                    // mid
+  add(20, 3, 128, 128, 0, dw(11), ld(11));
+  add(21, 3, 1, 1, 0, db(10), 1);                                      // rgb (seed rows 0-2)
+  const int head_param[5] = {22, 24, 26, 28, 30}, head_r0[5] = {0, 1, 4, 5, 8}, head_n[5] = {1, 3, 1, 3, 3};
+  for (int h = 0; h < 5; ++h) {                                        // small heads: seed rows 16 + r0 ..
+    add(head_param[h], head_n[h], 256, 256, 0, dw(10) + (int64_t)(16 + head_r0[h]) * ld(10), ld(10));
+    add(head_param[h] + 1, head_n[h], 1, 1, 0, db(10) + 16 + head_r0[h], 1);
+  }
+  RSN_ARG(u.n_pieces <= MAX_UNPACK, "rsn_unpack_grads: piece table overflow");
+  u.n_elems = elems;
+  unpack_kernel<<<(elems + 255) / 256, 256, 0, stream>>>(u);
+  RSN_LAUNCH_CHECK("unpack_kernel");
   return 0;
 }

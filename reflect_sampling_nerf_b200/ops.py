@@ -296,3 +296,17 @@ def pack_field(named_params) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     wd = torch.empty(256, dtype=torch.bfloat16, device=dev)
     _lib.call("rsn_pack_field", ptrs, _lib.ptr(wblob), _lib.ptr(wblob_t), _lib.ptr(bias), _lib.ptr(wd), _lib.stream())
     return wblob, bias, wblob_t, wd
+
+
+@functools.lru_cache(maxsize=1)
+def flat_layout():
+    """(offsets of the 32 parameters of PACK_ORDER in the flat gradient vector, total length)."""
+    offs = (_ct.c_int64 * 32)()
+    total = _lib.lib().rsn_field_flat_layout(offs)
+    return [int(o) for o in offs], int(total)
+
+
+def unpack_grads_flat(grad_blob: Tensor, flat: Tensor) -> Tensor:
+    """Gradient blob of field_wgrad -> flat fp32 gradient vector (one launch, csrc/pack.cu)."""
+    _lib.call("rsn_unpack_grads", _lib.ptr(grad_blob), _lib.ptr(flat), _lib.stream())
+    return flat

@@ -30,9 +30,30 @@ def _flush_grads(field) -> None:
     if field.dp_world_size > 1 and not os.environ.get("RSN_DEBUG_SKIP_ALLREDUCE"):
         dist.all_reduce(blob, op=dist.ReduceOp.SUM)
         blob.mul_(1.0 / field.dp_world_size)          # DDP averages (pipeline.py:75)
-    offs, shapes, _ = ops.wgrad_layout()
+    params = dict(field.named_parameters())
+    if blob.is_cuda:
+        # one kernel: blob -> flat gradient vector; the parameters' .grad are views of it
+        offs, total = ops.flat_layout()
+        fresh = all(params[k].grad is None for k in ops.PACK_ORDER)
+        flat = field.__dict__.get("_flat_grad")
+        if flat is None or flat.device != blob.device or not fresh:
+            flat = torch.empty(total, device=blob.device)      # (accumulating into existing grads: private buffer)
+            if fresh:
+                field.__dict__["_flat_grad"] = flat
+        ops.unpack_grads_flat(blob, flat)
+        for k, off in zip(ops.PACK_ORDER, offs):
+            p = params[k]
+            if not p.requires_grad:
+                continue
+            g = flat[off: off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
+        return
+    offs, shapes, _ = ops.wgrad_layout()                    # host reference path (CPU tensors: the gloo test)
     grads = packing.unpack_grads(blob, offs, shapes)
-    for name, p in field.named_parameters():
+    for name, p in params.items():
         g = grads.get(name)
         if g is None or not p.requires_grad:
             continue                                   # field_output_low never receives a gradient (App. B Q18)

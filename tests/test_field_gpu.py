@@ -122,3 +122,19 @@ def test_pack_kernel_matches_host_packing():
     torch.cuda.synchronize()
     assert torch.equal(wblob, rb) and torch.equal(bias, rbias)
     assert torch.equal(wblob_t, rbt) and torch.equal(wd, rwd)
+
+
+def test_unpack_kernel_matches_host_unpacking():
+    """rsn_unpack_grads (one launch) against packing.unpack_grads on a random gradient blob."""
+    offs, shapes, total = ops.wgrad_layout()
+    blob = torch.randn(total, device="cuda")
+    poffs, ptotal = ops.flat_layout()
+    assert ptotal == 618513 - 771                      # every parameter except the unused field_output_low
+    flat = torch.full((ptotal,), float("nan"), device="cuda")
+    ops.unpack_grads_flat(blob, flat)
+    ref = packing.unpack_grads(blob, offs, shapes)
+    torch.cuda.synchronize()
+    assert not torch.isnan(flat).any()
+    for name, off in zip(ops.PACK_ORDER, poffs):
+        g = ref[name]
+        assert torch.equal(flat[off: off + g.numel()].view(g.shape), g), name
