@@ -70,6 +70,20 @@ int rsn_composite_bwd(const float* sigma, const float* starts, const float* ends
                       const float* grad_accumulation, const float* grad_feat_out, float* grad_sigma,
                       float* grad_feat, int64_t n_rays, int64_t n_samples, rsn_stream_t stream);
 
+/* 16-channel form (the model's feature row) with the two per-sample normal losses of
+ * reflect_sampling_nerf_model.py:403-407 fused in: per ray pred_normal_loss = sum_s w_s |normals_s - feat_s[9:12]|^2 and
+ * orientation_loss = sum_s w_s max(0, feat_s[13])^2 with w the (detached) compositing weights; normals [N,S,3].
+ * The backward adds their gradients into grad_feat columns 9-11 and 13 (grad_* per-ray inputs may be NULL = 0). */
+int rsn_composite16_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
+                        const float* feat, const float* normals, float* weights, float* accumulation,
+                        float* depth_median, float* feat_out, float* pred_normal_loss, float* orientation_loss,
+                        int64_t n_rays, int64_t n_samples, rsn_stream_t stream);
+int rsn_composite16_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
+                        const float* feat, const float* normals, const float* grad_weights,
+                        const float* grad_accumulation, const float* grad_feat_out,
+                        const float* grad_pred_normal_loss, const float* grad_orientation_loss, float* grad_sigma,
+                        float* grad_feat, int64_t n_rays, int64_t n_samples, rsn_stream_t stream);
+
 /* ---- K3+K4+K5+K7: fused field forward --------------------------------------------------------------
  * Replaces, for one pass over the samples of a ray batch (mode 0), field.get_blob -> contract ->
  * get_density -> get_pred_normals / get_roughness / get_diff / get_tint -> IntegratedSHEncoding -> get_mid:

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "rsn_field_blob_bytes": ([], c_int64),
     "rsn_field_bias_count": ([], c_int64),
     "rsn_ipe_freqs": ([P], c_int),
+    "rsn_composite16_fwd": ([P, P, P, I64, P, P, P, P, P, P, P, P, I64, I64, P], c_int),
+    "rsn_composite16_bwd": ([P, P, P, I64, P, P, P, P, P, P, P, P, P, I64, I64, P], c_int),
     "rsn_probe_umma_kmajor": ([P, P, I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_2cta": ([P, P, I64, I64, P, P], c_int),
     "rsn_probe_umma_rate_2cta": ([I64, I64, I64, P, P], c_int),

@@ -214,7 +214,8 @@ template <int K, int Q>
 __global__ void __launch_bounds__(256) composite_fwd_vec_kernel(
     const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
     int64_t bin_stride, const float4* __restrict__ feat4, float* __restrict__ weights, float* __restrict__ acc_out,
-    float* __restrict__ depth_out, float4* __restrict__ feat_out4, int64_t n_rays, int S, int s_pad) {
+    float* __restrict__ depth_out, float4* __restrict__ feat_out4, int64_t n_rays, int S, int s_pad,
+    const float* __restrict__ normals, float* __restrict__ pnl_out, float* __restrict__ ol_out) {
   extern __shared__ float sm_rows[];
   const int lane = threadIdx.x & 31;
   float* ws = sm_rows + (threadIdx.x >> 5) * s_pad;
@@ -258,11 +259,29 @@ __global__ void __launch_bounds__(256) composite_fwd_vec_kernel(
     __syncwarp();
     const float4* f4 = feat4 + (int64_t)r * S * Q;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lsum = 0.f;   // Q == 4 with normals: quad 2 accumulates w |n - n_pred|^2, quad 3 accumulates w max(0, n.d)^2
 #pragma unroll 4
     for (int idx = lane; idx < S * Q; idx += 32) {
       const float4 v = __ldg(f4 + idx);
       const float wv = ws[idx / Q];
       a.x += wv * v.x, a.y += wv * v.y, a.z += wv * v.z, a.w += wv * v.w;
+      if (Q == 4 && normals) {
+        const int quad = lane & 3;
+        if (quad == 2) {          // feature columns 8..11 = tint_b, pred_normal xyz
+          const float* nn = normals + ((int64_t)r * S + idx / Q) * 3;
+          const float d0 = __ldg(nn) - v.y, d1 = __ldg(nn + 1) - v.z, d2 = __ldg(nn + 2) - v.w;
+          lsum += wv * (d0 * d0 + d1 * d1 + d2 * d2);
+        } else if (quad == 3) {   // feature columns 12..15 = sigmoid roughness, n.d, raw density, softplus roughness
+          const float pz = fmaxf(v.y, 0.f);
+          lsum += wv * pz * pz;
+        }
+      }
+    }
+    if (Q == 4 && normals) {
+#pragma unroll
+      for (int o = 16; o >= 4; o >>= 1) lsum += __shfl_xor_sync(RSN_FULL, lsum, o);
+      if (lane == 2) pnl_out[r] = lsum;
+      if (lane == 3) ol_out[r] = lsum;
     }
 #pragma unroll
     for (int o = 16; o >= Q; o >>= 1) {
@@ -284,7 +303,8 @@ __global__ void __launch_bounds__(256) composite_bwd_vec_kernel(
     const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
     int64_t bin_stride, const float4* __restrict__ feat4, const float* __restrict__ g_weights,
     const float* __restrict__ g_acc, const float4* __restrict__ g_feat_out4, float* __restrict__ g_sigma,
-    float4* __restrict__ g_feat4, int64_t n_rays, int S, int s_pad) {
+    float4* __restrict__ g_feat4, int64_t n_rays, int S, int s_pad, const float* __restrict__ normals,
+    const float* __restrict__ g_pnl, const float* __restrict__ g_ol) {
   extern __shared__ float sm_rows[];
   const int lane = threadIdx.x & 31;
   float* ws = sm_rows + (threadIdx.x >> 5) * 3 * s_pad;   // weights
@@ -323,7 +343,20 @@ __global__ void __launch_bounds__(256) composite_bwd_vec_kernel(
       if (ok) {
         const float wv = ws[smp];
         if ((lane % Q) == 0) gws[smp] = ga + (g_weights ? __ldg(g_weights + r * S + smp) : 0.f) + dot;
-        if (gf4) gf4[idx] = make_float4(go.x * wv, go.y * wv, go.z * wv, go.w * wv);
+        if (gf4) {
+          float4 g = make_float4(go.x * wv, go.y * wv, go.z * wv, go.w * wv);
+          if (Q == 4 && normals) {   // per-sample normal losses: the weight is a constant there (detached upstream)
+            const int quad = lane & 3;
+            if (quad == 2 && g_pnl) {
+              const float* nn = normals + ((int64_t)r * S + smp) * 3;
+              const float c = 2.f * wv * __ldg(g_pnl + r);
+              g.y += c * (v.y - __ldg(nn)), g.z += c * (v.z - __ldg(nn + 1)), g.w += c * (v.w - __ldg(nn + 2));
+            } else if (quad == 3 && g_ol) {
+              g.y += 2.f * wv * __ldg(g_ol + r) * fmaxf(v.y, 0.f);
+            }
+          }
+          gf4[idx] = g;
+        }
       }
     }
     __syncwarp();
@@ -365,7 +398,7 @@ constexpr int VEC_MAX_SAMPLES = 1024;   // 8 warps x 3 rows x 4 KB of dynamic sh
 template <int C>
 int launch_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_stride, const float* feat,
                float* weights, float* acc, float* depth, float* feat_out, int64_t n_rays, int S,
-               cudaStream_t stream) {
+               cudaStream_t stream, const float* normals = nullptr, float* pnl = nullptr, float* ol = nullptr) {
   const int threads = 256;
   int64_t want = (n_rays * 32 + threads - 1) / threads;
   int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
@@ -377,7 +410,8 @@ int launch_fwd(const float* sigma, const float* starts, const float* ends, int64
 #define RSN_FWDV(K)                                                                                              \
   composite_fwd_vec_kernel<K, Q><<<blocks, threads, smem, stream>>>(sigma, starts, ends, bin_stride,             \
                                                                     (const float4*)feat, weights, acc, depth,    \
-                                                                    (float4*)feat_out, n_rays, S, s_pad)
+                                                                    (float4*)feat_out, n_rays, S, s_pad, normals, \
+                                                                    pnl, ol)
     if (S <= 32) RSN_FWDV(1);
     else if (S <= 64) RSN_FWDV(2);
     else RSN_FWDV(4);
@@ -385,6 +419,7 @@ int launch_fwd(const float* sigma, const float* starts, const float* ends, int64
     RSN_LAUNCH_CHECK("composite_fwd_vec_kernel");
     return 0;
   }
+  if (normals) return rsn_fail(-1, "rsn_composite16_fwd: needs n_samples <= %d and 16-byte aligned feat", VEC_MAX_SAMPLES);
 #define RSN_FWD(K)                                                                                        \
   composite_fwd_kernel<K, C><<<blocks, threads, 0, stream>>>(sigma, starts, ends, bin_stride, feat, weights, \
                                                              acc, depth, feat_out, n_rays, S)
@@ -399,7 +434,8 @@ int launch_fwd(const float* sigma, const float* starts, const float* ends, int64
 template <int C>
 int launch_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_stride, const float* feat,
                const float* g_weights, const float* g_acc, const float* g_feat_out, float* g_sigma, float* g_feat,
-               int64_t n_rays, int S, cudaStream_t stream) {
+               int64_t n_rays, int S, cudaStream_t stream, const float* normals = nullptr, const float* g_pnl = nullptr,
+               const float* g_ol = nullptr) {
   const int threads = 256;
   int64_t want = (n_rays * 32 + threads - 1) / threads;
   int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
@@ -420,7 +456,8 @@ int launch_bwd(const float* sigma, const float* starts, const float* ends, int64
   composite_bwd_vec_kernel<K, Q><<<blocks, threads, smem, stream>>>(sigma, starts, ends, bin_stride,               \
                                                                     (const float4*)feat, g_weights, g_acc,         \
                                                                     (const float4*)g_feat_out, g_sigma,            \
-                                                                    (float4*)g_feat, n_rays, S, s_pad)
+                                                                    (float4*)g_feat, n_rays, S, s_pad, normals,    \
+                                                                    g_pnl, g_ol)
     if (S <= 32) RSN_BWDV(1);
     else if (S <= 64) RSN_BWDV(2);
     else RSN_BWDV(4);
@@ -428,6 +465,7 @@ int launch_bwd(const float* sigma, const float* starts, const float* ends, int64
     RSN_LAUNCH_CHECK("composite_bwd_vec_kernel");
     return 0;
   }
+  if (normals) return rsn_fail(-1, "rsn_composite16_bwd: needs n_samples <= %d and 16-byte aligned buffers", VEC_MAX_SAMPLES);
 #define RSN_BWD(K)                                                                                          \
   composite_bwd_kernel<K, C><<<blocks, threads, 0, stream>>>(sigma, starts, ends, bin_stride, feat, g_weights, \
                                                              g_acc, g_feat_out, g_sigma, g_feat, n_rays, S)
@@ -474,4 +512,33 @@ extern "C" int rsn_composite_bwd(const float* sigma, const float* starts, const 
   RSN_ARG(n_channels == 0 || feat, "rsn_composite_bwd: feat required when n_channels > 0");
   RSN_DISPATCH_C(launch_bwd, sigma, starts, ends, bin_row_stride, feat, grad_weights, grad_accumulation,
                  grad_feat_out, grad_sigma, grad_feat, n_rays, (int)n_samples, stream);
+}
+
+// The model's 16-channel form with the two per-sample normal losses fused in (their sample weights are the detached
+// compositing weights, reflect_sampling_nerf_model.py:403-407): per ray
+//   pred_normal_loss[r] = sum_s w_s |normals_s - feat_s[9:12]|^2      orientation_loss[r] = sum_s w_s max(0, feat_s[13])^2
+extern "C" int rsn_composite16_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
+                                   const float* feat, const float* normals, float* weights, float* accumulation,
+                                   float* depth_median, float* feat_out, float* pred_normal_loss,
+                                   float* orientation_loss, int64_t n_rays, int64_t n_samples, cudaStream_t stream) {
+  RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_composite16_fwd: bad shape");
+  if (n_rays == 0) return 0;
+  RSN_ARG(sigma && starts && ends && feat && normals && weights && accumulation && depth_median && feat_out &&
+              pred_normal_loss && orientation_loss, "rsn_composite16_fwd: null pointer");
+  return launch_fwd<16>(sigma, starts, ends, bin_row_stride, feat, weights, accumulation, depth_median, feat_out, n_rays,
+                        (int)n_samples, stream, normals, pred_normal_loss, orientation_loss);
+}
+
+extern "C" int rsn_composite16_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
+                                   const float* feat, const float* normals, const float* grad_weights,
+                                   const float* grad_accumulation, const float* grad_feat_out,
+                                   const float* grad_pred_normal_loss, const float* grad_orientation_loss,
+                                   float* grad_sigma, float* grad_feat, int64_t n_rays, int64_t n_samples,
+                                   cudaStream_t stream) {
+  RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_composite16_bwd: bad shape");
+  if (n_rays == 0) return 0;
+  RSN_ARG(sigma && starts && ends && feat && normals && grad_sigma && grad_feat, "rsn_composite16_bwd: null pointer");
+  return launch_bwd<16>(sigma, starts, ends, bin_row_stride, feat, grad_weights, grad_accumulation, grad_feat_out,
+                        grad_sigma, grad_feat, n_rays, (int)n_samples, stream, normals, grad_pred_normal_loss,
+                        grad_orientation_loss);
 }

@@ -248,15 +248,29 @@ class ReflectSamplingNeRFModel(_BaseModel):
         wc, wf = outputs["weights_coarse"], outputs["weights_fine"]
         sqd = lambda a, b: torch.sum((a - b) ** 2, dim=-1, keepdim=True)   # noqa: E731
         pos = lambda v: torch.clamp_min(v, 0.0) ** 2                       # noqa: E731
+        # the training path computes the four per-sample normal / orientation sums inside the compositing kernels
+        # (ops.composite16); they are used only for the very outputs dict they were computed with
+        fused = self.__dict__.pop("_fused_normal_losses", None)
+        fused = fused[1] if fused is not None and fused[0] is outputs.get("weights_fine") else None
+
+        def normal_term(key, generic):
+            return fused[key].sum() if fused is not None else generic()
+
         loss = {
             "loss_mid_coarse": self.rgb_loss(image, outputs["mid_rgb_coarse"]),
             "loss_mid_fine": self.rgb_loss(image, outputs["mid_rgb_fine"]),
             "loss_reflect_mid_coarse": self.rgb_loss(image, outputs["mid_reflect_coarse"]),
             "loss_reflect_mid_fine": self.rgb_loss(image, outputs["mid_reflect_fine"]),
-            "predicted_normal_loss_coarse": torch.sum(wc * sqd(outputs["normals_coarse"], outputs["pred_normals_coarse"])),
-            "predicted_normal_loss_fine": torch.sum(wf * sqd(outputs["normals_fine"], outputs["pred_normals_fine"])),
-            "orientation_loss_coarse": torch.sum(wc * pos(outputs["n_dot_d_coarse"])),
-            "orientation_loss_fine": torch.sum(wf * pos(outputs["n_dot_d_fine"])),
+            "predicted_normal_loss_coarse": normal_term(
+                "predicted_normal_loss_coarse",
+                lambda: torch.sum(wc * sqd(outputs["normals_coarse"], outputs["pred_normals_coarse"]))),
+            "predicted_normal_loss_fine": normal_term(
+                "predicted_normal_loss_fine",
+                lambda: torch.sum(wf * sqd(outputs["normals_fine"], outputs["pred_normals_fine"]))),
+            "orientation_loss_coarse": normal_term(
+                "orientation_loss_coarse", lambda: torch.sum(wc * pos(outputs["n_dot_d_coarse"]))),
+            "orientation_loss_fine": normal_term(
+                "orientation_loss_fine", lambda: torch.sum(wf * pos(outputs["n_dot_d_fine"]))),
         }
         for k in loss:   # misc.scale_dict
             if k in self.config.loss_coefficients:

@@ -168,6 +168,48 @@ class _Composite(torch.autograd.Function):
         return g_sigma, None, g_feat
 
 
+class _Composite16(torch.autograd.Function):
+    """The model's form: 16 feature channels + the two per-sample normal losses fused in (rsn_composite16_*).
+    sigma [N,S], bins [N,S+1], feat [N,S,16], normals [N,S,3] (constant)
+    -> weights [N,S], accumulation [N], median depth [N], feat_out [N,16], pred_normal_loss [N], orientation_loss [N]"""
+
+    @staticmethod
+    def forward(ctx, sigma: Tensor, bins: Tensor, feat: Tensor, normals: Tensor):
+        sigma, bins, feat, normals = _f32c(sigma), _f32c(bins), _f32c(feat), _f32c(normals)
+        n, s = sigma.shape
+        if feat.shape != (n, s, 16) or normals.shape != (n, s, 3) or bins.shape != (n, s + 1):
+            raise ValueError("composite16: expects sigma [N,S], bins [N,S+1], feat [N,S,16], normals [N,S,3]")
+        dev = sigma.device
+        weights = torch.empty(n, s, device=dev, dtype=torch.float32)
+        acc, depth, pnl, ol = (torch.empty(n, device=dev, dtype=torch.float32) for _ in range(4))
+        feat_out = torch.empty(n, 16, device=dev, dtype=torch.float32)
+        with _Prof("composite_fwd_kernel", n * s):
+            _lib.call("rsn_composite16_fwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1, _lib.ptr(feat),
+                      _lib.ptr(normals), _lib.ptr(weights), _lib.ptr(acc), _lib.ptr(depth), _lib.ptr(feat_out),
+                      _lib.ptr(pnl), _lib.ptr(ol), n, s, _lib.stream())
+        ctx.save_for_backward(sigma, bins, feat, normals)
+        ctx.mark_non_differentiable(depth)
+        return weights, acc, depth, feat_out, pnl, ol
+
+    @staticmethod
+    def backward(ctx, g_w, g_acc, _g_depth, g_feat_out, g_pnl, g_ol):
+        sigma, bins, feat, normals = ctx.saved_tensors
+        n, s = sigma.shape
+        g_sigma, g_feat = torch.empty_like(sigma), torch.empty_like(feat)
+        # keep the contiguous copies alive until the launch is enqueued (a freed temporary's block is handed to the
+        # next allocation at once)
+        g_w, g_acc, g_feat_out, g_pnl, g_ol = (_f32c(t) for t in (g_w, g_acc, g_feat_out, g_pnl, g_ol))
+        with _Prof("composite_bwd_kernel", n * s):
+            _lib.call("rsn_composite16_bwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1, _lib.ptr(feat),
+                      _lib.ptr(normals), _lib.ptr(g_w), _lib.ptr(g_acc), _lib.ptr(g_feat_out), _lib.ptr(g_pnl),
+                      _lib.ptr(g_ol), _lib.ptr(g_sigma), _lib.ptr(g_feat), n, s, _lib.stream())
+        return g_sigma, None, g_feat, None
+
+
+def composite16(sigma: Tensor, bins: Tensor, feat: Tensor, normals: Tensor):
+    return _Composite16.apply(sigma, bins, feat, normals)
+
+
 def composite(sigma: Tensor, bins: Tensor, feat: Optional[Tensor] = None):
     """Alpha compositing of one ray batch (K8).  Returns (weights, accumulation, median_depth, feat_out)."""
     return _Composite.apply(sigma, bins, feat)

@@ -137,8 +137,11 @@ def field_pass(field, mode: int, primary: bool, origins, dirs, area, bins):
 
 def _render(field, primary, o, d, area, eu_bins, detach_density: bool):
     sigma, feat, normals = field_pass(field, ops.MODE_SAMPLES, primary, o, d, area, eu_bins)
+    if primary:   # the per-sample normal losses (model.py:403-407) ride on the compositing kernel
+        w, acc, depth, comp, pnl, ol = ops.composite16(sigma, eu_bins, feat, normals)
+        return feat, normals, w, acc[:, None], depth[:, None], comp, (pnl, ol)
     w, acc, depth, comp = ops.composite(sigma.detach() if detach_density else sigma, eu_bins, feat)
-    return feat, normals, w, acc[:, None], depth[:, None], comp
+    return feat, normals, w, acc[:, None], depth[:, None], comp, None
 
 
 def get_outputs_train(model, ray_bundle) -> Dict[str, Tensor]:
@@ -153,12 +156,12 @@ def get_outputs_train(model, ray_bundle) -> Dict[str, Tensor]:
     # A. coarse (model.py:148-177)
     su, sp = model.sampler_uniform, model.sampler_pdf
     sp_c, eu_c = ops.sample_spaced(nears, fars, su.num_samples, su.kind, su.noise(n, dev))
-    feat_c, nrm_c, w_c, acc_c, depth_c, comp_c = _render(field, True, o, d, area, eu_c, False)
+    feat_c, nrm_c, w_c, acc_c, depth_c, comp_c, nl_c = _render(field, True, o, d, area, eu_c, False)
     rgb_c = clip01(comp_c[:, ops.F_RGB] + (1.0 - acc_c))
     # B. fine (model.py:182-211)
     sp_f, eu_f = ops.pdf_resample(w_c.detach(), sp_c, nears, fars, sp.num_samples, sp.kind, rand=sp.noise(n, dev),
                                   train=True)
-    feat_f, nrm_f, w_f, acc_f, depth_f, comp_f = _render(field, True, o, d, area, eu_f, False)
+    feat_f, nrm_f, w_f, acc_f, depth_f, comp_f, nl_f = _render(field, True, o, d, area, eu_f, False)
     rgb_f = clip01(comp_f[:, ops.F_RGB] + (1.0 - acc_f))
     # C. per-ray quantities of the bounce (model.py:215-229): everything detached except the roughness
     diff_r = (comp_f[:, ops.F_DIFF] + (1.0 - acc_f)).detach()
@@ -180,6 +183,10 @@ def get_outputs_train(model, ray_bundle) -> Dict[str, Tensor]:
         "n_dot_d_coarse": feat_c[..., ops.F_NDOTD, None], "n_dot_d_fine": feat_f[..., ops.F_NDOTD, None],
         "diff": diff_r, "tint": tint_r, "roughness": rough, "mask": mask,
     }
+    # fused per-ray sums of the normal losses, valid for exactly this outputs dict (get_loss_dict checks the identity)
+    model.__dict__["_fused_normal_losses"] = (outputs["weights_fine"], {
+        "predicted_normal_loss_coarse": nl_c[0], "orientation_loss_coarse": nl_c[1],
+        "predicted_normal_loss_fine": nl_f[0], "orientation_loss_fine": nl_f[1]})
     idx = torch.nonzero(mask).reshape(-1)
     m = idx.numel()
     if m == 0:
@@ -196,13 +203,13 @@ def get_outputs_train(model, ray_bundle) -> Dict[str, Tensor]:
     # E. reflected coarse (model.py:292-313): weights detached => the reflected passes never train the density
     sr, sq = model.sampler_reciprocal, model.sampler_reflect_pdf
     sp_rc, eu_rc = ops.sample_spaced(nears2, fars2, sr.num_samples, sr.kind, sr.noise(m, dev))
-    _, _, w_rc, acc_rc, _, comp_rc = _render(field, False, o2, w_r, area2, eu_rc, True)
+    _, _, w_rc, acc_rc, _, comp_rc, _ = _render(field, False, o2, w_r, area2, eu_rc, True)
     refl_c = comp_rc[:, ops.F_RGB] + bg * (1.0 - acc_rc.detach())
     outputs["mid_reflect_coarse"] = fallback.index_put((idx,), clip01(diff_r[idx] + tint_r[idx] * refl_c))
     # F. reflected fine (model.py:317-341)
     sp_rf, eu_rf = ops.pdf_resample(w_rc.detach(), sp_rc, nears2, fars2, sq.num_samples, sq.kind,
                                     rand=sq.noise(m, dev), train=True)
-    _, _, w_rf, acc_rf, depth_rf, comp_rf = _render(field, False, o2, w_r, area2, eu_rf, True)
+    _, _, w_rf, acc_rf, depth_rf, comp_rf, _ = _render(field, False, o2, w_r, area2, eu_rf, True)
     refl_f = comp_rf[:, ops.F_RGB] + bg * (1.0 - acc_rf.detach())
     outputs["mid_reflect_fine"] = fallback.index_put((idx,), clip01(diff_r[idx] + tint_r[idx] * refl_f))
     outputs["depth_reflect_fine"] = depth_rf

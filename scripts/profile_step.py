@@ -17,6 +17,17 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         st.step(RayBundle(origins=o, directions=d, pixel_area=a), img)
     torch.cuda.synchronize()
+from torch.autograd import DeviceType
+kern = [e for e in prof.events() if e.device_type == DeviceType.CUDA]
+busy = sum(e.device_time_total for e in kern) / 3 / 1e3
+t_first, t_last = min(e.time_range.start for e in kern), max(e.time_range.end for e in kern)
+print(f"GPU kernel time per step: {busy:.2f} ms; wall per step (first kernel start -> last kernel end)/3: {(t_last - t_first) / 3 / 1e3:.2f} ms; "
+      f"kernels per step: {len(kern) // 3}")
+# largest idle gaps between consecutive kernels
+ks = sorted(kern, key=lambda e: e.time_range.start)
+gaps = sorted(((b.time_range.start - a.time_range.end, a.name[:50], b.name[:50]) for a, b in zip(ks, ks[1:])), reverse=True)[:12]
+for g, a, b in gaps:
+    print(f"  idle {g/1e3:7.3f} ms between {a} -> {b}")
 ev = [e for e in prof.key_averages() if e.device_time_total > 0]
 tot = sum(e.device_time_total for e in ev)
 print(f"total device time per step: {tot/3/1e3:.2f} ms")

@@ -97,3 +97,38 @@ def test_composite_full_size_properties():
     torch.testing.assert_close(acc, w.sum(-1), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(o12, o1 + 2 * o2, rtol=1e-4, atol=1e-5)
     assert float(depth.min()) >= 2 and float(depth.max()) <= 6
+
+
+@pytest.mark.parametrize("S", [24, 64, 128, 200])
+def test_composite16_fused_normal_losses(S):
+    """rsn_composite16_*: 16 channels + the per-sample normal / orientation losses of model.py:403-407 fused in,
+    against the plain compositing op followed by the reference's torch formulas (values and gradients)."""
+    n = 97
+    g = torch.Generator().manual_seed(S)
+    sigma = (torch.rand(n, S, generator=g) * 3).cuda().requires_grad_(True)
+    bins = (2 + 4 * torch.sort(torch.rand(n, S + 1, generator=g), dim=-1)[0]).cuda()
+    feat = torch.rand(n, S, 16, generator=g).cuda()
+    feat[..., 13] = feat[..., 13] * 2 - 1                      # n.d of either sign
+    feat.requires_grad_(True)
+    normals = torch.nn.functional.normalize(torch.randn(n, S, 3, generator=g), dim=-1).cuda()
+    gw, gacc = torch.rand(n, S, generator=g).cuda(), torch.rand(n, generator=g).cuda()
+    gfo = torch.rand(n, 16, generator=g).cuda()
+    c_pn, c_ol = 0.3, 0.7
+
+    w, acc, depth, fo, pnl, ol = ops.composite16(sigma, bins, feat, normals)
+    ((w * gw).sum() + (acc * gacc).sum() + (fo * gfo).sum() + c_pn * pnl.sum() + c_ol * ol.sum()).backward()
+    gs, gf = sigma.grad.clone(), feat.grad.clone()
+    sigma.grad = feat.grad = None
+
+    w2, acc2, depth2, fo2 = ops.composite(sigma, bins, feat)
+    wd = w2.detach()[..., None]
+    pn_loss = torch.sum(wd * torch.sum((normals - feat[..., 9:12]) ** 2, dim=-1, keepdim=True))
+    o_loss = torch.sum(wd * torch.clamp_min(feat[..., 13:14], 0.0) ** 2)
+    ((w2 * gw).sum() + (acc2 * gacc).sum() + (fo2 * gfo).sum() + c_pn * pn_loss + c_ol * o_loss).backward()
+    torch.testing.assert_close(w, w2, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(fo, fo2, rtol=1e-5, atol=1e-6)
+    assert torch.equal(depth, depth2)
+    torch.testing.assert_close(pnl.sum(), pn_loss, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ol.sum(), o_loss, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gs, sigma.grad, rtol=1e-4, atol=1e-5 * float(sigma.grad.abs().max()))
+    torch.testing.assert_close(gf, feat.grad, rtol=1e-5, atol=1e-6)
