@@ -140,6 +140,15 @@ int64_t rsn_field_dy_stash_bytes(int64_t n_points);
 int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_t n_points, float* grad_blob,
                     rsn_stream_t stream);
 int rsn_field_wgrad_layout(int64_t* host_offsets, int64_t* host_shapes, int64_t* total_floats);
+/* rsn_field_backward + rsn_field_wgrad in ONE launch: the dgrad-chain CTAs and the wgrad CTAs share the grid, the
+ * chain publishes each tile's dY blocks with a per-tile flag (workspace: rsn_field_backward_fused_workspace_bytes,
+ * zeroed by the call) and the wgrad picks them up from L2.  Same arguments and results as the two calls. */
+int rsn_field_backward_fused(const void* wblob_t, const void* x_stash, int mode, const float* origins,
+                             const float* dirs, const float* area, const float* bins, int64_t n_rays,
+                             int64_t n_samples, const float* g_sigma, const float* g_feat, const float* feat,
+                             const float* aux, void* dy_stash, float* g_area, float* grad_blob, void* workspace,
+                             rsn_stream_t stream);
+int64_t rsn_field_backward_fused_workspace_bytes(int64_t n_points);
 /* Gradient blob -> flat fp32 gradient vector laid out parameter after parameter in rsn_pack_field order
  * (rsn_field_flat_layout: HOST array of 32 float offsets, returns the vector length, 617,742).  One launch. */
 int rsn_unpack_grads(const float* grad_blob, float* flat_grads, rsn_stream_t stream);

@@ -15,236 +15,8 @@
 //
 // HBM-bound: algorithmic bytes = (m_blocks + n_blocks) * 16 KB per tile and job; 95 blocks = 1.52 MB per tile
 // over the 12 jobs (11.9 KB per point) against 2 * 618k * 128 = 158 MFLOP per tile.
-#include "rsn_common.cuh"
-#include "umma.cuh"
-#include "field_layout.cuh"
-#include <algorithm>
-#include <stdlib.h>
+#include "field_wgrad_body.cuh"
 
-namespace {
-
-using namespace umma;
-using namespace rsnf;
-
-constexpr int W_THREADS = 192;      // warp 0 producer, warp 1 MMA issuer, warps 2-5 db + epilogue
-#ifndef RSN_WGRAD_SLAB_ROWS
-#define RSN_WGRAD_SLAB_ROWS 64
-#endif
-constexpr int SLAB_ROWS = RSN_WGRAD_SLAB_ROWS;   // points per pipeline slab (SLAB_ROWS / 16 K-steps)
-constexpr int SLAB_BLOCK_BYTES = SLAB_ROWS * 128;
-constexpr int SLAB_BYTES = 8 * SLAB_BLOCK_BYTES;   // up to 4 dY + 4 X blocks
-constexpr int W_STAGES = 196608 / SLAB_BYTES;    // 192 KB ring
-constexpr int MAX_JOBS = 16;
-
-struct WJob {
-  int a_blk, m_blocks;   // first dY block of the job inside a dY tile; 2 (M=128) or 4 (M=256)
-  int b_blk, n_blocks;   // first X block inside a stash tile; 1, 2 or 4 (N = 64, 128, 256)
-  int out_off, db_off;   // float offsets into the gradient blob: dW [64 m_blocks][64 n_blocks], db or -1
-  int cta_begin, n_ctas;
-};
-struct WParams {
-  const uint8_t* x;      // forward stash  [n_tiles][STASH_BLOCKS][16 KB]
-  const uint8_t* dy;     // dgrad stash    [n_tiles][DY_BLOCKS][16 KB]
-  int n_tiles;
-  float* grad;
-  int n_jobs;
-  int debug;   // RSN_WGRAD_DEBUG: 1 = MMA only (no loads, no db), 2 = loads only (no MMA)
-  WJob jobs[MAX_JOBS];
-};
-
-struct WBarriers {
-  uint64_t full[W_STAGES], empty[W_STAGES];
-  uint64_t acc_full;
-  uint32_t tmem_slot;
-};
-
-__global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_constant__ WParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ WBarriers bars;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  int j = 0;
-  for (int i = 0; i < p.n_jobs; ++i)
-    if ((int)blockIdx.x >= p.jobs[i].cta_begin && (int)blockIdx.x < p.jobs[i].cta_begin + p.jobs[i].n_ctas) j = i;
-  const WJob job = p.jobs[j];
-  const int split = (int)blockIdx.x - job.cta_begin;
-  // tiles split, split + n_ctas, ...: the CTAs of a job stream neighbouring tiles at the same time
-  const bool interleave = !(p.debug & 8);
-  const int t0 = interleave ? split : (int)(((int64_t)p.n_tiles * split) / job.n_ctas);
-  const int t1 = interleave ? p.n_tiles : (int)(((int64_t)p.n_tiles * (split + 1)) / job.n_ctas);
-  const int tstep = interleave ? job.n_ctas : 1;
-  const int mb = job.m_blocks, nb = job.n_blocks;
-  const int n_slabs = (t1 > t0 ? (t1 - t0 + tstep - 1) / tstep : 0) * (TILE / SLAB_ROWS);
-
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int i = 0; i < W_STAGES; ++i) {
-        mbar_init(&bars.full[i], 1);
-        mbar_init(&bars.empty[i], 1 + 4);   // tcgen05.commit + one arrival per db warp
-      }
-      mbar_init(&bars.acc_full, 1);
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc(&bars.tmem_slot, 512);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = bars.tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0 && (p.debug & 3) != 1) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = t0; t < t1; t += tstep) {
-        const uint8_t* dyt = p.dy + ((size_t)t * DY_BLOCKS + job.a_blk) * BLOCK_BYTES;
-        const uint8_t* xt = p.x + (size_t)t * STASH_TILE_BYTES + (size_t)job.b_blk * BLOCK_BYTES;
-        for (int s = 0; s < TILE / SLAB_ROWS; ++s) {
-          mbar_wait(&bars.empty[stage], phase ^ 1);
-          mbar_expect_tx(&bars.full[stage], (uint32_t)(mb + nb) * SLAB_BLOCK_BYTES);
-          uint8_t* dst = smem + (size_t)stage * SLAB_BYTES;
-          for (int i = 0; i < mb; ++i)
-            bulk_g2s(dst + i * SLAB_BLOCK_BYTES, dyt + (size_t)i * BLOCK_BYTES + s * SLAB_BLOCK_BYTES,
-                     SLAB_BLOCK_BYTES, &bars.full[stage]);
-          for (int i = 0; i < nb; ++i)
-            bulk_g2s(dst + (mb + i) * SLAB_BLOCK_BYTES, xt + (size_t)i * BLOCK_BYTES + s * SLAB_BLOCK_BYTES,
-                     SLAB_BLOCK_BYTES, &bars.full[stage]);
-          if (++stage == W_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && n_slabs > 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t idesc = instr_desc_bf16(128, nb * 64, 1, 1);
-      for (int s = 0; s < n_slabs; ++s) {
-        if ((p.debug & 3) != 1) mbar_wait(&bars.full[stage], phase);
-        tc_fence_after();
-        const uint32_t base = smem_u32(smem + (size_t)stage * SLAB_BYTES);
-        // MN-major operands: LBO = stride between the 64-feature blocks of the slab, SBO = 1024 (8 points);
-        // one K=16 step (16 points) advances the start address by 2048 bytes
-        constexpr uint32_t HI = desc_hi_sw128(1024);
-        const uint32_t a_lo = desc_lo(base, SLAB_BLOCK_BYTES), b_lo = desc_lo(base + mb * SLAB_BLOCK_BYTES, SLAB_BLOCK_BYTES);
-        if ((p.debug & 3) != 2) {
-          // all K-steps of the slab into one accumulator, then the other: interleaving the two accumulators MMA by
-          // MMA is measurably slower (2.6 vs 4.2 ms for the MMA stream alone at C2)
-#pragma unroll
-          for (int ks = 0; ks < SLAB_ROWS / 16; ++ks)
-            mma_bf16_ss_lo(tmem, a_lo + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
-          if (mb == 4) {
-#pragma unroll
-            for (int ks = 0; ks < SLAB_ROWS / 16; ++ks)
-              mma_bf16_ss_lo(tmem + 256, a_lo + (2 * SLAB_BLOCK_BYTES >> 4) + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
-          }
-        }
-        mma_commit(&bars.empty[stage]);
-        if (++stage == W_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      mma_commit(&bars.acc_full);
-    }
-  } else {
-    // ---- db: column sums of the dY slabs while they sit in shared memory; then the dW flush.
-    // Thread -> one 16-byte chunk column (8 features) of one dY block, every 4th row: within a warp the 32 lanes
-    // read the 8 chunks of one row of each of the 4 blocks = conflict-free 128-bit shared loads.
-    const int t = threadIdx.x - 64;
-    const int cc = t & 31, rphase = t >> 5;
-    const int blk = cc >> 3, ch = cc & 7;
-    const bool db_active = blk < mb;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int s = 0; s < ((p.debug & 3) == 1 ? 0 : n_slabs); ++s) {
-      mbar_wait(&bars.full[stage], phase);
-      if (db_active && (p.debug & 3) != 3) {
-        const uint32_t src = smem_u32(smem + (size_t)stage * SLAB_BYTES) + blk * SLAB_BLOCK_BYTES;
-        uint4 v[SLAB_ROWS / 4];
-#pragma unroll
-        for (int i = 0; i < SLAB_ROWS / 4; ++i) {
-          const int r = rphase + 4 * i;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
-                       : "r"(src + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4)));
-        }
-#pragma unroll
-        for (int i = 0; i < SLAB_ROWS / 4; ++i) {
-          acc[0] += __uint_as_float(v[i].x << 16), acc[1] += __uint_as_float(v[i].x & 0xffff0000u);
-          acc[2] += __uint_as_float(v[i].y << 16), acc[3] += __uint_as_float(v[i].y & 0xffff0000u);
-          acc[4] += __uint_as_float(v[i].z << 16), acc[5] += __uint_as_float(v[i].z & 0xffff0000u);
-          acc[6] += __uint_as_float(v[i].w << 16), acc[7] += __uint_as_float(v[i].w & 0xffff0000u);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.empty[stage]);
-      if (++stage == W_STAGES) {
-        stage = 0;
-        phase ^= 1;
-      }
-    }
-    if (n_slabs > 0) {
-      if (db_active && job.db_off >= 0 && (p.debug & 3) != 1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(p.grad + job.db_off + blk * 64 + ch * 8 + i, acc[i]);
-      }
-      mbar_wait(&bars.acc_full, 0);
-      tc_fence_after();
-      const int q = warp & 3;
-      const int row = q * 32 + lane;
-      const int N = nb * 64;
-      for (int h = 0; h < ((p.debug & 4) ? 0 : mb / 2); ++h) {
-        float* out = p.grad + job.out_off + (size_t)(h * 128 + row) * N;
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 256 + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)   // 16-byte vector reductions: 4x fewer L2 atomic transactions
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c0 + i), "f"(__uint_as_float(v[i])),
-                         "f"(__uint_as_float(v[i + 1])), "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
-                         : "memory");
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
-}
-
-// The 12 jobs of one pass.  Gradient blob regions (fp32): dW [64 m_blocks][64 n_blocks] row-major, then db.
-struct JobSpec {
-  int a_blk, m_blocks, b_blk, n_blocks, has_db;
-};
-const JobSpec kJobs[] = {
-    {DY_H + 0, 4, STASH_ENC, 2, 1},             //  0  layer 0            x enc
-    {DY_H + 4, 4, STASH_H + 0, 4, 1},           //  1  layer 1            x h0
-    {DY_H + 8, 4, STASH_H + 4, 4, 1},           //  2  layer 2            x h1
-    {DY_H + 12, 4, STASH_H + 8, 4, 1},          //  3  layer 3            x h2
-    {DY_H + 16, 4, STASH_ENC, 2, 0},            //  4  layer 4 (enc part) x enc
-    {DY_H + 16, 4, STASH_H + 12, 4, 1},         //  5  layer 4 (hidden)   x h3
-    {DY_H + 20, 4, STASH_H + 16, 4, 1},         //  6  layer 5            x h4
-    {DY_H + 24, 4, STASH_H + 20, 4, 1},         //  7  layer 6            x h5
-    {DY_H + 28, 4, STASH_H + 24, 4, 1},         //  8  layer 7            x h6
-    {DY_BOTT, 4, STASH_H + 28, 4, 1},           //  9  bottleneck         x h7
-    {DY_SEED, 2, STASH_H + 28, 4, 1},           // 10  heads (rows 16-31) x h7   (rows 0-15: unused product)
-    {DY_SEED, 2, STASH_MIDH, 2, 0},             // 11  rgb (rows 0-15)    x mid hidden (db from job 10's sums)
-    {DY_MID, 2, STASH_BOTT, 4, 1},              // 12  mid                x bottleneck
-    {DY_MID, 2, STASH_IDE, 1, 0},               // 13  mid (IDE part)     x IDE
-};
-constexpr int kNumJobs = sizeof(kJobs) / sizeof(kJobs[0]);
-static_assert(kNumJobs <= MAX_JOBS, "job table too small");
-
-}  // namespace
 
 extern "C" int64_t rsn_field_dy_stash_bytes(int64_t n_points) {
   return ((n_points + TILE - 1) / TILE) * (int64_t)DY_BLOCKS * BLOCK_BYTES;
@@ -273,31 +45,7 @@ extern "C" int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_
   RSN_ARG(x_stash && dy_stash && grad_blob, "rsn_field_wgrad: null pointer");
   RSN_ARG(((uintptr_t)x_stash & 15) == 0 && ((uintptr_t)dy_stash & 15) == 0, "rsn_field_wgrad: stashes must be 16-byte aligned");
   WParams p;
-  p.x = (const uint8_t*)x_stash;
-  p.dy = (const uint8_t*)dy_stash;
-  p.n_tiles = (int)((n_points + TILE - 1) / TILE);
-  p.grad = grad_blob;
-  p.n_jobs = kNumJobs;
-  p.debug = getenv("RSN_WGRAD_DEBUG") ? atoi(getenv("RSN_WGRAD_DEBUG")) : 0;
-  // CTAs per job proportional to the job's bytes per tile (the kernel is HBM-bound), one wave of <= #SM CTAs
-  const int sms = rsn_num_sms();
-  int units = 0;
-  for (int j = 0; j < kNumJobs; ++j) units += kJobs[j].m_blocks + kJobs[j].n_blocks;
-  int64_t off = 0;
-  int cta = 0;
-  for (int j = 0; j < kNumJobs; ++j) {
-    const int u = kJobs[j].m_blocks + kJobs[j].n_blocks;
-    int n = std::max(1, (u * sms) / units);
-    n = std::min(n, p.n_tiles);
-    WJob& w = p.jobs[j];
-    w.a_blk = kJobs[j].a_blk, w.m_blocks = kJobs[j].m_blocks, w.b_blk = kJobs[j].b_blk, w.n_blocks = kJobs[j].n_blocks;
-    w.out_off = (int)off;
-    off += (int64_t)w.m_blocks * 64 * w.n_blocks * 64;
-    w.db_off = kJobs[j].has_db ? (int)off : -1;
-    if (kJobs[j].has_db) off += w.m_blocks * 64;
-    w.cta_begin = cta, w.n_ctas = n;
-    cta += n;
-  }
+  const int cta = fill_wgrad_params(p, x_stash, dy_stash, n_points, grad_blob, rsn_num_sms());
   const size_t smem = (size_t)W_STAGES * SLAB_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {

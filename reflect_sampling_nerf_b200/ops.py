@@ -26,6 +26,9 @@ KERNEL_WORK = {
     "field_chain_kernel<backward>": (1179904, 288 + 39 * 128 + 160),
     "field_chain_kernel<backward+area>": (1229056, 288 + 4 * 128 + 39 * 128 + 164),
     "field_wgrad_kernel": (1230592, 95 * 128),
+    # fused backward: dgrad + wgrad FLOPs; HBM: masks + dY written once + X read (dY read back from L2)
+    "field_bwd_fused_kernel": (1179904 + 1230592, 288 + 39 * 128 + 160 + 56 * 128),
+    "field_bwd_fused_kernel+area": (1229056 + 1230592, 288 + 4 * 128 + 39 * 128 + 164 + 56 * 128),
     # K8 at C = 16 channels, per SAMPLE: sigma 4 + bin 4 + feat 64 in, weight 4 out | + dL/dw 4 in, dL/dsigma 4 + dL/dfeat 64 out
     "composite_fwd_kernel": (0, 76),
     "composite_bwd_kernel": (0, 144),
@@ -310,6 +313,19 @@ def field_backward(wblob_t: Tensor, stash: Tensor, mode: int, origins, dirs, are
         _lib.call("rsn_field_backward", _lib.ptr(wblob_t), _lib.ptr(stash), mode, _lib.ptr(origins), _lib.ptr(dirs),
                   _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(g_sigma), _lib.ptr(g_feat), _lib.ptr(feat),
                   _lib.ptr(aux), _lib.ptr(dy_stash), _lib.ptr(g_area), _lib.stream())
+    return g_area
+
+
+def field_backward_fused(wblob_t: Tensor, stash: Tensor, mode: int, origins, dirs, area, bins, n: int, s: int,
+                         g_sigma: Optional[Tensor], g_feat: Tensor, feat: Tensor, aux: Tensor, dy_stash: Tensor,
+                         want_area: bool, grad_blob: Tensor) -> Optional[Tensor]:
+    """field_backward + field_wgrad in one launch (csrc/field_bwd_fused.cu): chain CTAs and wgrad CTAs side by side."""
+    g_area = torch.empty(n, s, device=stash.device, dtype=torch.float32) if want_area else None
+    ws = torch.empty(_lib.lib().rsn_field_backward_fused_workspace_bytes(n * s), dtype=torch.uint8, device=stash.device)
+    with _Prof("field_bwd_fused_kernel+area" if want_area else "field_bwd_fused_kernel", n * s):
+        _lib.call("rsn_field_backward_fused", _lib.ptr(wblob_t), _lib.ptr(stash), mode, _lib.ptr(origins), _lib.ptr(dirs),
+                  _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(g_sigma), _lib.ptr(g_feat), _lib.ptr(feat),
+                  _lib.ptr(aux), _lib.ptr(dy_stash), _lib.ptr(g_area), _lib.ptr(grad_blob), _lib.ptr(ws), _lib.stream())
     return g_area
 
 
