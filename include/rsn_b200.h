@@ -165,6 +165,24 @@ int64_t rsn_field_bias_count(void);
 /* The 16 IPE frequencies 2**linspace(0,16,16) the kernels use (HOST pointer; for the table test). */
 int rsn_ipe_freqs(float* host_out16);
 
+/* ---- K9: reflection set-up and composition of the bounce --------------------------------------------------
+ * rsn_reflect_setup replaces reflect_sampling_nerf_model.py:215-229,267-271: from the composited feature row of the fine
+ * pass comp16 [N,16] (rsn_field_forward feature layout), accumulation [N], median depth [N] and the rays, per ray:
+ * diff [N,3] (white-blended), tint [N,3], normal [N,3] (safe-normalised), n_dot_d [N], mask [N] (uint8:
+ * accumulation > 1e-2 and n.d < 0), bounce origins o + depth d and directions normalize(d - 2 (n.d) n).  clamp01 =
+ * eval mode (RGBRenderer clamps).  The compaction of the masked rays stays with the caller (index list).
+ * rsn_reflect_compose_* replace model.py:311-313,337-339: out = base; out[idx] = clip(diff[idx] + tint[idx] *
+ * (comp[m,:3] + bg[m] (1 - acc[m])), 0, 1) and its backward w.r.t. comp, bg and base. */
+int rsn_reflect_setup(const float* comp16, const float* acc, const float* depth, const float* origins, const float* dirs,
+                      int clamp01, float* diff, float* tint, float* normal, float* n_dot_d, uint8_t* mask,
+                      float* bounce_origins, float* bounce_dirs, int64_t n_rays, rsn_stream_t stream);
+int rsn_reflect_compose_fwd(const float* base, const float* diff, const float* tint, const int64_t* idx,
+                            const float* comp, int64_t comp_ld, const float* bg, const float* acc, int clamp_inner,
+                            float* out, int64_t n_rays, int64_t n_bounced, rsn_stream_t stream);
+int rsn_reflect_compose_bwd(const float* grad_out, const float* diff, const float* tint, const int64_t* idx,
+                            const float* comp, int64_t comp_ld, const float* bg, const float* acc, float* grad_comp,
+                            float* grad_bg, float* grad_base, int64_t n_rays, int64_t n_bounced, rsn_stream_t stream);
+
 /* ---- tcgen05 building-block probes (unit tests of csrc/umma.cuh) ---------------------------------- */
 int rsn_probe_umma_kmajor(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks,
                           int64_t n_split, float* out, rsn_stream_t stream);

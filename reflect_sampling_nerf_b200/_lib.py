@@ -40,6 +40,9 @@ _SIGNATURES = {
     "rsn_ipe_freqs": ([P], c_int),
     "rsn_composite16_fwd": ([P, P, P, I64, P, P, P, P, P, P, P, P, I64, I64, P], c_int),
     "rsn_composite16_bwd": ([P, P, P, I64, P, P, P, P, P, P, P, P, P, I64, I64, P], c_int),
+    "rsn_reflect_setup": ([P, P, P, P, P, I32, P, P, P, P, P, P, P, I64, P], c_int),
+    "rsn_reflect_compose_fwd": ([P, P, P, P, P, I64, P, P, I32, P, I64, I64, P], c_int),
+    "rsn_reflect_compose_bwd": ([P, P, P, P, P, I64, P, P, P, P, P, I64, I64, P], c_int),
     "rsn_probe_umma_kmajor": ([P, P, I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_2cta": ([P, P, I64, I64, P, P], c_int),
     "rsn_probe_umma_rate_2cta": ([I64, I64, I64, P, P], c_int),

@@ -191,14 +191,10 @@ class ReflectSamplingNeRFModel(_BaseModel):
                                       train=self.training)
         feat_f, w_f, acc_f, depth_f, comp_f = self._pass(o, d, area, eu_f)
         rgb_f = clip01(ev(comp_f[:, ops.F_RGB] + (1.0 - acc_f)))
-        # C. per-ray quantities of the bounce (model.py:215-229)
-        diff_r = ev(comp_f[:, ops.F_DIFF] + (1.0 - acc_f))        # renderer_rgb, white background
-        tint_r = ev(comp_f[:, ops.F_TINT])                        # renderer_factor: "random" -> unblended
-        nrm = comp_f[:, ops.F_NORMAL]
-        nrm_r = nrm / (torch.linalg.norm(nrm, dim=-1, keepdim=True) + 1e-10)   # NormalsRenderer safe_normalize
-        ndd = torch.sum(nrm_r * d, dim=-1, keepdim=True)
+        # C. per-ray quantities of the bounce (model.py:215-229), one kernel
+        diff_r, tint_r, nrm_r, ndd, mask, o2_all, wr_all = ops.reflect_setup(comp_f, acc_f, depth_f, o, d,
+                                                                             clamp01=not self.training)
         rough = comp_f[:, ops.F_ROUGH_SIGMOID, None]
-        mask = torch.logical_and(acc_f > 1e-2, ndd < 0).reshape(-1)
         white = torch.ones(n, 3, device=dev)
         outputs = {
             "mid_rgb_coarse": rgb_c, "mid_rgb_fine": rgb_f,
@@ -218,8 +214,7 @@ class ReflectSamplingNeRFModel(_BaseModel):
         if m == 0:                                        # App. B Q11
             return outputs
         # D. reflected bundle (model.py:267-290)
-        o2 = o[idx] + depth_f[idx] * d[idx]
-        w_r = torch.nn.functional.normalize(d[idx] - 2 * ndd[idx] * nrm_r[idx], dim=-1)
+        o2, w_r = o2_all[idx], wr_all[idx]
         sqr = 2 * torch.abs(ndd[idx]) * rough[idx] ** 2
         area2 = math.pi * sqr
         nears2 = torch.zeros(m, 1, device=dev)            # zeros * near (App. B Q4)
@@ -229,14 +224,15 @@ class ReflectSamplingNeRFModel(_BaseModel):
         sr, sq = self.sampler_reciprocal, self.sampler_reflect_pdf
         sp_rc, eu_rc = ops.sample_spaced(nears2, fars2, sr.num_samples, sr.kind, sr.noise(m, dev))
         _, w_rc, acc_rc, _, comp_rc = self._pass(o2, w_r, area2, eu_rc)
-        refl_c = ev(comp_rc[:, ops.F_RGB] + bg * (1.0 - acc_rc))
-        outputs["mid_reflect_coarse"][idx] = clip01(diff_r[idx] + tint_r[idx] * refl_c)
+        base = outputs["mid_reflect_coarse"]
+        outputs["mid_reflect_coarse"] = ops.reflect_compose(base, diff_r, tint_r, idx, comp_rc, bg, acc_rc,
+                                                            clamp_inner=not self.training)
         # F. reflected fine (model.py:317-341)
         sp_rf, eu_rf = ops.pdf_resample(w_rc, sp_rc, nears2, fars2, sq.num_samples, sq.kind,
                                         rand=sq.noise(m, dev), train=self.training)
         _, w_rf, acc_rf, depth_rf, comp_rf = self._pass(o2, w_r, area2, eu_rf)
-        refl_f = ev(comp_rf[:, ops.F_RGB] + bg * (1.0 - acc_rf))
-        outputs["mid_reflect_fine"][idx] = clip01(diff_r[idx] + tint_r[idx] * refl_f)
+        outputs["mid_reflect_fine"] = ops.reflect_compose(base, diff_r, tint_r, idx, comp_rf, bg, acc_rf,
+                                                          clamp_inner=not self.training)
         outputs["depth_reflect_fine"] = depth_rf
         return outputs
 

@@ -368,3 +368,53 @@ def unpack_grads_flat(grad_blob: Tensor, flat: Tensor) -> Tensor:
     """Gradient blob of field_wgrad -> flat fp32 gradient vector (one launch, csrc/pack.cu)."""
     _lib.call("rsn_unpack_grads", _lib.ptr(grad_blob), _lib.ptr(flat), _lib.stream())
     return flat
+
+
+# ----------------------------------------------------------------------------------------- K9
+def reflect_setup(comp16: Tensor, acc: Tensor, depth: Tensor, origins: Tensor, dirs: Tensor, clamp01: bool):
+    """Per-ray quantities of the bounce from the composited fine pass (model.py:215-229,267-271), all detached:
+    -> diff [N,3], tint [N,3], normal [N,3], n_dot_d [N,1], mask [N] bool, bounce origins [N,3], bounce dirs [N,3]."""
+    comp16, acc, depth = _f32c(comp16.detach()), _f32c(acc.detach().reshape(-1)), _f32c(depth.detach().reshape(-1))
+    origins, dirs = _f32c(origins), _f32c(dirs)
+    n, dev = comp16.shape[0], comp16.device
+    diff, tint, nrm, o2, wr = (torch.empty(n, 3, device=dev, dtype=torch.float32) for _ in range(5))
+    ndd = torch.empty(n, 1, device=dev, dtype=torch.float32)
+    mask = torch.empty(n, device=dev, dtype=torch.uint8)
+    _lib.call("rsn_reflect_setup", _lib.ptr(comp16), _lib.ptr(acc), _lib.ptr(depth), _lib.ptr(origins), _lib.ptr(dirs),
+              int(clamp01), _lib.ptr(diff), _lib.ptr(tint), _lib.ptr(nrm), _lib.ptr(ndd), _lib.ptr(mask), _lib.ptr(o2),
+              _lib.ptr(wr), n, _lib.stream())
+    return diff, tint, nrm, ndd, mask.bool(), o2, wr
+
+
+class _ReflectCompose(torch.autograd.Function):
+    """out = base; out[idx] = clip(diff[idx] + tint[idx] * (comp[:, :3] + bg * (1 - acc)), 0, 1)   (model.py:311-313)."""
+
+    @staticmethod
+    def forward(ctx, base, diff, tint, idx, comp, bg, acc, clamp_inner: bool):
+        base, diff, tint, comp, bg, acc = (_f32c(t) for t in (base, diff, tint, comp, bg, acc.reshape(-1)))
+        idx = idx.contiguous()
+        n, m = base.shape[0], idx.shape[0]
+        out = torch.empty_like(base)
+        _lib.call("rsn_reflect_compose_fwd", _lib.ptr(base), _lib.ptr(diff), _lib.ptr(tint), _lib.ptr(idx), _lib.ptr(comp),
+                  comp.shape[1], _lib.ptr(bg), _lib.ptr(acc), int(clamp_inner), _lib.ptr(out), n, m, _lib.stream())
+        ctx.save_for_backward(diff, tint, idx, comp, bg, acc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        diff, tint, idx, comp, bg, acc = ctx.saved_tensors
+        g_out = _f32c(g_out)
+        n, m = g_out.shape[0], idx.shape[0]
+        g_base = torch.empty_like(g_out)
+        g3 = torch.empty(m, 3, device=g_out.device, dtype=torch.float32)
+        g_bg = torch.empty_like(g3)
+        _lib.call("rsn_reflect_compose_bwd", _lib.ptr(g_out), _lib.ptr(diff), _lib.ptr(tint), _lib.ptr(idx), _lib.ptr(comp),
+                  comp.shape[1], _lib.ptr(bg), _lib.ptr(acc), _lib.ptr(g3), _lib.ptr(g_bg), _lib.ptr(g_base), n, m,
+                  _lib.stream())
+        g_comp = torch.zeros_like(comp)
+        g_comp[:, :3] = g3
+        return g_base, None, None, None, g_comp, g_bg, None, None
+
+
+def reflect_compose(base, diff, tint, idx, comp, bg, acc, clamp_inner: bool = False) -> Tensor:
+    return _ReflectCompose.apply(base, diff, tint, idx, comp, bg, acc, clamp_inner)

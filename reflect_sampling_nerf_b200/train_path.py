@@ -169,14 +169,9 @@ def get_outputs_train(model, ray_bundle) -> Dict[str, Tensor]:
                                   train=True)
     feat_f, nrm_f, w_f, acc_f, depth_f, comp_f, nl_f = _render(field, True, o, d, area, eu_f, False)
     rgb_f = clip01(comp_f[:, ops.F_RGB] + (1.0 - acc_f))
-    # C. per-ray quantities of the bounce (model.py:215-229): everything detached except the roughness
-    diff_r = (comp_f[:, ops.F_DIFF] + (1.0 - acc_f)).detach()
-    tint_r = comp_f[:, ops.F_TINT].detach()
-    nraw = comp_f[:, ops.F_NORMAL].detach()
-    nrm_r = nraw / (torch.linalg.norm(nraw, dim=-1, keepdim=True) + 1e-10)
-    ndd = torch.sum(nrm_r * d, dim=-1, keepdim=True)
+    # C. per-ray quantities of the bounce (model.py:215-229): everything detached except the roughness (one kernel)
+    diff_r, tint_r, nrm_r, ndd, mask, o2_all, wr_all = ops.reflect_setup(comp_f, acc_f, depth_f, o, d, clamp01=False)
     rough = comp_f[:, ops.F_ROUGH_SIGMOID, None]                       # NOT detached (model.py:225-227)
-    mask = torch.logical_and(acc_f.detach() > 1e-2, ndd < 0).reshape(-1)
     fallback = torch.ones(n, 3, device=dev) * (1.0 - acc_f)           # gradient to accumulation_fine (App. B Q10)
     outputs = {
         "mid_rgb_coarse": rgb_c, "mid_rgb_fine": rgb_f,
@@ -198,8 +193,7 @@ def get_outputs_train(model, ray_bundle) -> Dict[str, Tensor]:
     if m == 0:
         return outputs
     # D. reflected bundle (model.py:267-290): origins / directions detached, sqradius carries grad to the roughness
-    o2 = (o[idx] + depth_f[idx] * d[idx]).detach()
-    w_r = torch.nn.functional.normalize(d[idx] - 2 * ndd[idx] * nrm_r[idx], dim=-1).detach()
+    o2, w_r = o2_all[idx], wr_all[idx]
     sqr = 2 * torch.abs(ndd[idx]) * rough[idx] ** 2
     area2 = math.pi * sqr
     nears2 = torch.zeros(m, 1, device=dev)
@@ -210,14 +204,12 @@ def get_outputs_train(model, ray_bundle) -> Dict[str, Tensor]:
     sr, sq = model.sampler_reciprocal, model.sampler_reflect_pdf
     sp_rc, eu_rc = ops.sample_spaced(nears2, fars2, sr.num_samples, sr.kind, sr.noise(m, dev))
     _, _, w_rc, acc_rc, _, comp_rc, _ = _render(field, False, o2, w_r, area2, eu_rc, True)
-    refl_c = comp_rc[:, ops.F_RGB] + bg * (1.0 - acc_rc.detach())
-    outputs["mid_reflect_coarse"] = fallback.index_put((idx,), clip01(diff_r[idx] + tint_r[idx] * refl_c))
+    outputs["mid_reflect_coarse"] = ops.reflect_compose(fallback, diff_r, tint_r, idx, comp_rc, bg, acc_rc.detach())
     # F. reflected fine (model.py:317-341)
     sp_rf, eu_rf = ops.pdf_resample(w_rc.detach(), sp_rc, nears2, fars2, sq.num_samples, sq.kind,
                                     rand=sq.noise(m, dev), train=True)
     _, _, w_rf, acc_rf, depth_rf, comp_rf, _ = _render(field, False, o2, w_r, area2, eu_rf, True)
-    refl_f = comp_rf[:, ops.F_RGB] + bg * (1.0 - acc_rf.detach())
-    outputs["mid_reflect_fine"] = fallback.index_put((idx,), clip01(diff_r[idx] + tint_r[idx] * refl_f))
+    outputs["mid_reflect_fine"] = ops.reflect_compose(fallback, diff_r, tint_r, idx, comp_rf, bg, acc_rf.detach())
     outputs["depth_reflect_fine"] = depth_rf
     return outputs
 
