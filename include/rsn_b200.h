@@ -189,6 +189,21 @@ int rsn_probe_umma_kmajor(const void* x_blocks, const void* w_blocks, int64_t n_
 int rsn_probe_umma_mnmajor(const void* u_blocks, const void* v_blocks, int64_t m_blocks, int64_t n_blocks,
                            float* out, rsn_stream_t stream);
 
+/* A-from-TMEM probe (tcgen05.mma [d], [a], b-desc): out [128, n_out] = X * W^T with X staged into TMEM by tcgen05.st.
+ * iters > 0 also times `iters` back-to-back MMAs of that form into *cycles_out (DEVICE int64). */
+int rsn_probe_umma_ts(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks, float* out,
+                      int64_t iters, int64_t* cycles_out, rsn_stream_t stream);
+
+/* TMEM read / write throughput seen by n_warps (1..8) epilogue-style warps, 64 columns x 32 lanes per iteration and warp,
+ * optionally while another warp streams mma_iters tcgen05.mma into the other accumulator buffer; cycles_out: DEVICE
+ * int64 [9], cycles of each reader warp for `iters` iterations and ([8]) of the MMA stream.  mode: see csrc/probe.cu. */
+int rsn_probe_tmem_rate(int64_t n_warps, int64_t mode, int64_t iters, int64_t mma_iters, int64_t* cycles_out,
+                        rsn_stream_t stream);
+
+/* Step-by-step cost of the field kernels' epilogue (four warps, one 64-column group per iteration); `steps` is a bit set
+ * of the stages to include (csrc/probe.cu); cycles_out as for rsn_probe_tmem_rate. */
+int rsn_probe_epilogue(int64_t steps, int64_t iters, int64_t mma_iters, int64_t* cycles_out, rsn_stream_t stream);
+
 /* CTA-pair probe: out [256, n_out] = X [256, 64 k_blocks] * W [n_out, 64 k_blocks]^T with tcgen05.mma.cta_group::2;
  * x_blocks = two tiles of k_blocks block images, w_blocks = k_blocks images of n_out rows. */
 int rsn_probe_umma_2cta(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks, float* out,

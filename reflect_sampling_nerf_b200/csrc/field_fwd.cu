@@ -38,7 +38,10 @@ constexpr int NUM_STAGES = 3;
 constexpr int SMEM_ACT = 0;                                    // 4 blocks
 constexpr int SMEM_ENC = 4 * BLOCK_BYTES;                      // 2 buffers x 2 blocks
 constexpr int SMEM_W = SMEM_ENC + 4 * BLOCK_BYTES;             // ring
-constexpr int SMEM_TOTAL = SMEM_W + NUM_STAGES * W_STAGE_BYTES;  // 229,376
+constexpr int SMEM_BARS = SMEM_W + NUM_STAGES * W_STAGE_BYTES;   // 229,376: mbarriers (256 B)
+constexpr int SMEM_BIAS = SMEM_BARS + 256;                       // 2 x 1 KB: fp32 bias of the current / next wide layer
+constexpr int SMEM_TOTAL = SMEM_BIAS + 2 * 1024;                 // 231,680 of the 232,448 a CTA may have
+constexpr int WIDE_LAYERS = 10;                                  // per tile: base 0..7, bottleneck, mid
 constexpr int NUM_THREADS = 320;
 
 // 2 ** torch.linspace(0, 16, 16) in fp32, bit for bit (NeRFEncoding, reflect_sampling_nerf_model.py:98-100)
@@ -74,7 +77,7 @@ struct FwdParams {
   float* feat;              // [P][16]
   uint8_t* stash;           // training: [n_tiles][STASH_BLOCKS][16 KB] activation block images, or NULL
   float* aux;               // training: [P][8] = mid rgb (3), raw normal head (3), 2 spare, or NULL
-  int debug;                // RSN_FWD_DEBUG (timing experiments only): 1 = no bias, 2 = no trig in the prologue
+  int debug;                // RSN_FWD_DEBUG (timing experiments only): 2 = no trig in the prologue
 };
 
 constexpr int MAX_STAGES = 6;
@@ -85,8 +88,10 @@ struct Barriers {
   uint64_t act_ready[4];
   uint64_t ide_ready;
   uint64_t acc_full[2];
+  uint64_t bias_full[2];         // single CTA: the bias slot (wide layer j -> slot j & 1) has landed
   uint32_t tmem_slot;
 };
+static_assert(sizeof(Barriers) <= 256, "Barriers must fit their shared-memory slot");
 
 // ---------------------------------------------------------------------------------------------- helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -281,16 +286,27 @@ __device__ __forceinline__ void ide_features(const float d[3], float rho, float 
 // 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> activation block `blk`.
 // MASKS (training): also emit the ReLU bit masks of the group (a separate instantiation, so that the inference path keeps
 // its branch-free schedule: a runtime test of the mask pointer inside the chunk loop cost 0.47 ms of 2.62 at C2)
-template <bool RELU, bool MASKS = false>
+// SBIAS: the 64 biases come from shared memory (bias_saddr; every lane reads the same 16 bytes: one broadcast
+// wavefront per load) instead of constant memory (bias_off).  The constant path is an INDEXED load (the layer is a
+// run-time value) of a 10 KB table that cycles once per tile: 32 LDC per group, 0.5 ms of 2.66 at C2 (measured by
+// replacing the bias with a register constant).
+template <bool RELU, bool MASKS = false, bool SBIAS = false>
 __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
-                                               bool nobias = false, uint2* mask_out = nullptr) {
+                                               uint32_t bias_saddr = 0, uint2* mask_out = nullptr) {
   uint32_t mbits[2] = {0u, 0u};
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
   float4 b[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) b[i] = nobias ? make_float4(0.f, 0.f, 0.f, 0.f) : c_bias4[(bias_off >> 2) + i];
+  for (int i = 0; i < 16; ++i) {
+    if (SBIAS)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(b[i].x), "=f"(b[i].y), "=f"(b[i].z), "=f"(b[i].w)
+                   : "r"(bias_saddr + (uint32_t)i * 16u));
+    else
+      b[i] = c_bias4[(bias_off >> 2) + i];
+  }
   tmem_ld_wait();
   const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
 #pragma unroll
@@ -336,9 +352,9 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __ex
 // traffic against 2048 MMA cycles at 128 B/cycle): the single-CTA form is shared-memory-bandwidth bound.
 template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ Barriers bars;
+  extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the window starts here
+  Barriers& bars = *reinterpret_cast<Barriers*>(smem + SMEM_BARS);
+  constexpr bool SBIAS = !PAIR;   // the pair form keeps the constant-memory bias (its issuer serves two CTAs)
   constexpr int NS = PAIR ? 6 : NUM_STAGES;                       // weight ring: 6 x 16 KB or 3 x 32 KB
   constexpr uint32_t STB = PAIR ? W_STAGE_BYTES / 2 : W_STAGE_BYTES;
   constexpr uint32_t ARRIVALS = PAIR ? 8 : TILE;                  // PAIR: one arrival per warp, both CTAs
@@ -347,6 +363,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
   const uint32_t s_act = smem_u32(smem + SMEM_ACT);
   const uint32_t s_enc = smem_u32(smem + SMEM_ENC);
   const uint32_t s_w = smem_u32(smem + SMEM_W);
+  const uint32_t s_bias = smem_u32(smem + SMEM_BIAS);
+  if ((smem_u32(smem) & 1023u) != 0u) {   // the swizzled operand blocks need 1024-byte alignment
+    if (threadIdx.x == 0) printf("rsn_b200: field_fwd_kernel: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
 
   if (warp == 1) {
     if (lane == 0) {
@@ -359,6 +380,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         mbar_init(&bars.enc_full[i], ARRIVALS);
         mbar_init(&bars.enc_empty[i], 1);
         mbar_init(&bars.acc_full[i], 1);
+        mbar_init(&bars.bias_full[i], 1);
       }
       for (int i = 0; i < 4; ++i) mbar_init(&bars.act_ready[i], ARRIVALS);
       mbar_init(&bars.ide_ready, ARRIVALS);
@@ -483,6 +505,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         if (ksteps == 4) mma(6, 1u);
         acc = true;
       };
+      // Bias of wide layer j (10 per tile) -> slot j & 1, requested as soon as the epilogue of layer j - 2 has published
+      // its last group (the issuer sees that as the last act_ready wait of layer j - 1).
+      auto request_bias = [&](int j) {
+        if (!SBIAS || j >= n_my_tiles * WIDE_LAYERS) return;
+        const int jl = j % WIDE_LAYERS;
+        const int off = jl < 8 ? BIAS_BASE + jl * 256 : (jl == 8 ? BIAS_BOTT : BIAS_MID);
+        const uint32_t bytes = jl == 9 ? 512u : 1024u;
+        mbar_expect_tx(&bars.bias_full[j & 1], bytes);
+        bulk_g2s(smem + SMEM_BIAS + (j & 1) * 1024, p.bias + off, bytes, &bars.bias_full[j & 1]);
+      };
+      request_bias(0);
+      request_bias(1);
       for (int it = 0; it < n_my_tiles; ++it) {
         const int eb = it & 1;
         const uint32_t enc_a = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
@@ -506,6 +540,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           if (l > 0) {
             for (int g = 0; g < 4; ++g) {
               wait_act(g);
+              if (g == 3) request_bias(it * WIDE_LAYERS + l + 1);
               const uint32_t w = ring_wait();
               issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tm, acc);
               ring_release();
@@ -520,6 +555,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           acc = false;
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
+            if (g == 3) request_bias(it * WIDE_LAYERS + 9);
             const uint32_t w = ring_wait();
             issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tm, acc);
             ring_release();
@@ -540,6 +576,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           for (int c = 0; c < 2; ++c) {
             wait_act(2 * c);
             wait_act(2 * c + 1);
+            if (c == 1) request_bias(it * WIDE_LAYERS + 10);
             const uint32_t w = ring_wait();
             issue_kb(s_act + (2 * c) * BLOCK_BYTES, w, 4, ID128, tm, acc);
             issue_kb(s_act + (2 * c + 1) * BLOCK_BYTES, w + 128 * 128 / BDIV, 4, ID128, tm, acc);
@@ -560,6 +597,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           acc = false;
           wait_act(0);
           wait_act(1);
+          request_bias(it * WIDE_LAYERS + 11);
           const uint32_t w = ring_wait();
           issue_kb(s_act, w, 4, ID16, tm, acc);
           issue_kb(s_act + BLOCK_BYTES, w + N_HEAD * 128 / BDIV, 4, ID16, tm, acc);
@@ -577,6 +615,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t af_phase = 0;
     int buf = 0;
+    int jw = 0;   // wide layers converted so far
+    // bias slot of the wide layer about to be converted (waits until its bulk copy has landed)
+    auto bias_slot = [&]() -> uint32_t {
+      if (!SBIAS) return 0u;
+      mbar_wait(&bars.bias_full[jw & 1], (uint32_t)(jw >> 1) & 1u);
+      const uint32_t a = s_bias + (uint32_t)(jw & 1) * 1024u;
+      ++jw;
+      return a;
+    };
     for (int it = 0; it < n_my_tiles; ++it) {
       const int eb = it & 1;
       const int tile = tile_of(it);
@@ -607,6 +654,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       };
       for (int l = 0; l < 8; ++l) {
         wait_acc();
+        const uint32_t sb = bias_slot();
         for (int g = 0; g < 4; ++g) {
           if (l == 0) {
             if (st) warp_store_guard<1>(lane);
@@ -614,12 +662,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
             guard();
           }
           if (st)
-            epilogue_group<true, true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
-                                       s_act + g * BLOCK_BYTES, row, false,
-                                       reinterpret_cast<uint2*>(st + STASH_MASK_OFF) + mask_entry(l, g, row));
+            epilogue_group<true, true, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
+                                              s_act + g * BLOCK_BYTES, row, sb + g * 256,
+                                              reinterpret_cast<uint2*>(st + STASH_MASK_OFF) + mask_entry(l, g, row));
           else
-            epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
-                                 s_act + g * BLOCK_BYTES, row, (p.debug & 1) != 0);
+            epilogue_group<true, false, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
+                                               s_act + g * BLOCK_BYTES, row, sb + g * 256);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_H + 4 * l + g));
         }
         buf ^= 1;
@@ -628,10 +676,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       float diff[3], tint[3];
       {
         wait_acc();
+        const uint32_t sb = bias_slot();
         for (int g = 0; g < 4; ++g) {
           guard();
-          epilogue_group<false>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BOTT + g * 64,
-                                s_act + g * BLOCK_BYTES, row);
+          epilogue_group<false, false, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BOTT + g * 64,
+                                              s_act + g * BLOCK_BYTES, row, sb + g * 256);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_BOTT + g));
         }
         uint32_t hv[16];
@@ -710,13 +759,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       // ---- layer 9: mid hidden (ReLU) -> activation blocks 0,1
       {
         wait_acc();
+        const uint32_t sb = bias_slot();
         for (int g = 0; g < 2; ++g) {
           guard();
           if (st)
-            epilogue_group<true, true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64, s_act + g * BLOCK_BYTES,
-                                       row, false, reinterpret_cast<uint2*>(st + STASH_MASK_OFF) + mask_entry(8, g, row));
+            epilogue_group<true, true, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64,
+                                              s_act + g * BLOCK_BYTES, row, sb + g * 256,
+                                              reinterpret_cast<uint2*>(st + STASH_MASK_OFF) + mask_entry(8, g, row));
           else
-            epilogue_group<true>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64, s_act + g * BLOCK_BYTES, row);
+            epilogue_group<true, false, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64,
+                                               s_act + g * BLOCK_BYTES, row, sb + g * 256);
           publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_MIDH + g));
         }
         buf ^= 1;
@@ -855,7 +907,7 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
   p.aux = aux;
   p.debug = getenv("RSN_FWD_DEBUG") ? atoi(getenv("RSN_FWD_DEBUG")) : 0;
   RSN_ARG(((uintptr_t)stash & 15) == 0, "rsn_field_forward: stash must be 16-byte aligned");
-  const size_t smem = SMEM_TOTAL + 1024;
+  const size_t smem = SMEM_TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
     RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -162,6 +162,329 @@ extern "C" int rsn_probe_umma_mnmajor(const void* u_blocks, const void* v_blocks
   return 0;
 }
 
+// ---- A-from-TMEM probe: D[128, N] = X[128, K] * W[N, K]^T with X written into TMEM by the four epilogue-style warps
+// (tcgen05.st, two bf16 per 32-bit column) and read by tcgen05.mma as its A operand; W from shared memory.
+// `iters` > 0 additionally times `iters` back-to-back MMAs of the same form (cycles -> out_cycles).
+namespace {
+__global__ void __launch_bounds__(160, 1) probe_ts_kernel(const uint8_t* __restrict__ x_blocks,
+                                                          const uint8_t* __restrict__ w_blocks, int N, int KB,
+                                                          float* __restrict__ out, int iters, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_load, bar_mma, bar_a;
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* sx = smem;
+  uint8_t* sw = smem + (size_t)KB * 16384;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_block_bytes = (uint32_t)N * 128u;
+  constexpr uint32_t A_COL = 256;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(&bar_load, 1);
+      mbar_init(&bar_mma, 1);
+      mbar_init(&bar_a, 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == 4 && lane == 0) {
+    mbar_expect_tx(&bar_load, (uint32_t)KB * (16384u + w_block_bytes));
+    for (int kb = 0; kb < KB; ++kb) {
+      bulk_g2s(sx + (size_t)kb * 16384, x_blocks + (size_t)kb * 16384, 16384, &bar_load);
+      bulk_g2s(sw + (size_t)kb * w_block_bytes, w_blocks + (size_t)kb * w_block_bytes, w_block_bytes, &bar_load);
+    }
+  }
+  if (warp < 4) {
+    // X rows -> TMEM: column A_COL + kb*32 + j holds elements (64 kb + 2j, 64 kb + 2j + 1) of this thread's row
+    mbar_wait(&bar_load, 0);
+    const int row = warp * 32 + lane;
+    for (int kb = 0; kb < KB; ++kb) {
+      uint32_t v[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 t = *reinterpret_cast<const uint4*>(sx + (size_t)kb * 16384 + row * 128 + ((c ^ (row & 7)) << 4));
+        v[c * 4 + 0] = t.x, v[c * 4 + 1] = t.y, v[c * 4 + 2] = t.z, v[c * 4 + 3] = t.w;
+      }
+      tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + A_COL + kb * 32, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&bar_a);
+  }
+  if (warp == 4 && lane == 0) {
+    mbar_wait(&bar_load, 0);
+    mbar_wait(&bar_a, 0);
+    tc_fence_after();
+    const uint32_t idesc = instr_desc_bf16(128, N, 0, 0);
+    constexpr uint32_t HI = desc_hi_sw128(1024);
+    for (int kb = 0; kb < KB; ++kb)
+      for (int k = 0; k < 4; ++k)
+        mma_bf16_ts_lo(tmem, tmem + A_COL + kb * 32 + k * 8, desc_lo(smem_u32(sw + (size_t)kb * w_block_bytes), 16) + k * 2,
+                       HI, idesc, (kb | k) != 0);
+    mma_commit(&bar_mma);
+  }
+  if (warp < 4) {
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) out[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (iters > 0 && warp == 4 && lane == 0) {
+    tc_fence_after();
+    const uint32_t idesc = instr_desc_bf16(128, N, 0, 0);
+    constexpr uint32_t HI = desc_hi_sw128(1024);
+    const uint32_t b_lo = desc_lo(smem_u32(sw), 16);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_bf16_ts_lo(tmem, tmem + A_COL + k * 8, b_lo + k * 2, HI, idesc, 1u);
+    }
+    mma_commit(&bar_mma);
+    mbar_wait(&bar_mma, 1);
+    const long long t1 = clock64();
+    out_cycles[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" int rsn_probe_umma_ts(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks, float* out,
+                                 int64_t iters, int64_t* cycles_out, cudaStream_t stream) {
+  RSN_ARG(n_out >= 16 && n_out <= 256 && n_out % 16 == 0, "rsn_probe_umma_ts: n_out in [16,256], multiple of 16");
+  RSN_ARG(k_blocks >= 1 && k_blocks <= 4, "rsn_probe_umma_ts: k_blocks in [1,4]");
+  RSN_ARG(iters >= 0 && iters % 4 == 0 && (iters == 0 || cycles_out), "rsn_probe_umma_ts: bad iters");
+  size_t smem = (size_t)k_blocks * (16384 + n_out * 128) + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_ts_kernel<<<1, 160, smem, stream>>>((const uint8_t*)x_blocks, (const uint8_t*)w_blocks, (int)n_out, (int)k_blocks,
+                                            out, (int)iters, (long long*)cycles_out);
+  RSN_LAUNCH_CHECK("probe_ts_kernel");
+  return 0;
+}
+
+// ---- TMEM read / write throughput as the epilogue warps see it: `n_warps` warps (1..8; warp w touches lane quarter
+// w % 4) each move 64 columns x 32 lanes per iteration.  mode 0: 2 x tcgen05.ld.x32 + wait; 1: 4 x ld.x16 + wait;
+// 2: mode 0 followed by one tcgen05.st.x32 + wait::st; 3: mode 0 with the wait only every 4th iteration.
+// mma_iters > 0: a ninth warp issues that many back-to-back M128 x N256 x K16 MMAs into the other 256 columns meanwhile
+// (cycles_out[8] = its time): what the field kernels' epilogue sees while the next layer's MMAs run.
+namespace {
+__global__ void __launch_bounds__(288, 1) probe_tmem_kernel(int n_warps, int mode, int iters, int mma_iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ uint64_t bar_mma;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 6 * 16384 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(&bar_mma, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_slot, 512);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  if (warp < n_warps) {
+    // the readers sweep columns 0..255; a concurrent MMA stream (mma_iters > 0) accumulates into columns 256..511
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t col = (uint32_t)((i + (warp >> 2) * 2) & 3) * 64u;
+      if (mode == 1) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmem_ld16(tl + col + j * 16, v[j]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc += v[j][0] ^ v[j][15];
+      } else {
+        uint32_t v[2][32];
+        tmem_ld32(tl + col, v[0]);
+        tmem_ld32(tl + col + 32, v[1]);
+        if (mode != 3 || (i & 3) == 3) tmem_ld_wait();
+        acc += v[0][0] ^ v[1][31];
+        if (mode == 2) {
+          tmem_st32(tl + col, v[1]);
+          tmem_st_wait();
+        }
+      }
+    }
+    tmem_ld_wait();
+    const long long t1 = clock64();
+    if (lane == 0) out[warp] = (t1 - t0) + (acc == 0x12345u ? 1 : 0);
+  }
+  if (warp == 8 && lane == 0 && mma_iters > 0) {
+    const uint32_t idesc = instr_desc_bf16(128, 256, 0, 0);
+    const uint32_t a_lo = desc_lo(smem_u32(smem), 16), b_lo = desc_lo(smem_u32(smem) + 2 * 16384, 16);
+    const long long t0 = clock64();
+    for (int i = 0; i < mma_iters; i += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_bf16_ss_lo(tmem + 256, a_lo + k * 2, b_lo + k * 2, desc_hi_sw128(1024), idesc, 1u);
+    }
+    mma_commit(&bar_mma);
+    mbar_wait(&bar_mma, 0);
+    out[8] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" int rsn_probe_tmem_rate(int64_t n_warps, int64_t mode, int64_t iters, int64_t mma_iters, int64_t* cycles_out,
+                                   cudaStream_t stream) {
+  RSN_ARG(n_warps >= 1 && n_warps <= 8 && mode >= 0 && mode <= 3 && iters > 0 && cycles_out, "rsn_probe_tmem_rate: bad arguments");
+  RSN_ARG(mma_iters >= 0 && mma_iters % 4 == 0, "rsn_probe_tmem_rate: mma_iters must be a multiple of 4");
+  const size_t smem = 6 * 16384 + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_tmem_kernel<<<1, 288, smem, stream>>>((int)n_warps, (int)mode, (int)iters, (int)mma_iters, (long long*)cycles_out);
+  RSN_LAUNCH_CHECK("probe_tmem_kernel");
+  return 0;
+}
+
+// ---- cost of the field kernels' epilogue step by step: four warps, each iteration converts one 64-column group of
+// its 32 rows.  `steps` bits: 1 = bias add + ReLU + bf16 pack, 2 = 8 x st.shared.v4 into a swizzled block,
+// 4 = fence.proxy.async, 8 = tcgen05.fence::before_thread_sync + mbarrier.arrive by every thread, 16 = bias from
+// constant memory (else a register constant), 32 = tcgen05.st of the packed row + wait::st, 64 = one arrive per warp
+// instead of per thread.  mma_iters > 0: concurrent SS MMA stream as in probe_tmem_kernel.
+namespace {
+__constant__ float4 c_probe_bias[64];
+__global__ void __launch_bounds__(288, 1) probe_epi_kernel(int steps, int iters, int mma_iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ uint64_t bar_mma, bar_grp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 10 * 16384 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(&bar_mma, 1);
+      mbar_init(&bar_grp, (steps & 64) ? 4 : 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_slot, 512);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  if (warp < 4) {
+    const int row = warp * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t s_act = smem_u32(smem) + 6 * 16384;
+    uint32_t sink = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int g = it & 3;
+      uint32_t v[2][32];
+      tmem_ld32(tl + g * 64, v[0]);
+      tmem_ld32(tl + g * 64 + 32, v[1]);
+      float4 b[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        b[i] = (steps & 16) ? c_probe_bias[g * 16 + i] : make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+      tmem_ld_wait();
+      uint32_t a[32];
+      const uint32_t row_saddr = s_act + (uint32_t)g * 16384u + (uint32_t)row * 128u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 bb = b[h * 8 + c * 2 + q];
+            float x0 = __uint_as_float(v[h][c * 8 + q * 4 + 0]), x1 = __uint_as_float(v[h][c * 8 + q * 4 + 1]);
+            float x2 = __uint_as_float(v[h][c * 8 + q * 4 + 2]), x3 = __uint_as_float(v[h][c * 8 + q * 4 + 3]);
+            if (steps & 1) {
+              x0 += bb.x, x1 += bb.y, x2 += bb.z, x3 += bb.w;
+              asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[q * 2 + 0]) : "f"(x1), "f"(x0));
+              asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[q * 2 + 1]) : "f"(x3), "f"(x2));
+            } else {
+              pk[q * 2 + 0] = __float_as_uint(x0) ^ __float_as_uint(x1);
+              pk[q * 2 + 1] = __float_as_uint(x2) ^ __float_as_uint(x3);
+            }
+          }
+          const int chunk = h * 4 + c;
+          if (steps & 2)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4)),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                         : "memory");
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[chunk * 4 + j] = pk[j];
+        }
+      if (steps & 32) {
+        tmem_st32(tl + g * 32, a);
+        tmem_st_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sink ^= a[j];
+      }
+      if (steps & 4) fence_proxy_async();
+      if (steps & 8) {
+        tc_fence_before();
+        if (steps & 64) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_grp);
+        } else {
+          mbar_arrive(&bar_grp);
+        }
+      }
+    }
+    const long long t1 = clock64();
+    if (lane == 0) out[warp] = (t1 - t0) + (sink == 0x12345u ? 1 : 0);
+  }
+  if (warp == 8 && lane == 0 && mma_iters > 0) {
+    const uint32_t idesc = instr_desc_bf16(128, 256, 0, 0);
+    const uint32_t a_lo = desc_lo(smem_u32(smem), 16), b_lo = desc_lo(smem_u32(smem) + 2 * 16384, 16);
+    const long long t0 = clock64();
+    for (int i = 0; i < mma_iters; i += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_bf16_ss_lo(tmem + 256, a_lo + k * 2, b_lo + k * 2, desc_hi_sw128(1024), idesc, 1u);
+    }
+    mma_commit(&bar_mma);
+    mbar_wait(&bar_mma, 0);
+    out[8] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" int rsn_probe_epilogue(int64_t steps, int64_t iters, int64_t mma_iters, int64_t* cycles_out, cudaStream_t stream) {
+  RSN_ARG(steps >= 0 && steps < 128 && iters > 0 && mma_iters >= 0 && mma_iters % 4 == 0 && cycles_out,
+          "rsn_probe_epilogue: bad arguments");
+  const size_t smem = 10 * 16384 + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_epi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_epi_kernel<<<1, 288, smem, stream>>>((int)steps, (int)iters, (int)mma_iters, (long long*)cycles_out);
+  RSN_LAUNCH_CHECK("probe_epi_kernel");
+  return 0;
+}
+
 // ---- tcgen05.mma issue-rate probe: cycles per M128 x N x K16 bf16 MMA for the four operand major-ness
 // combinations (operands: whatever is in shared memory; only the timing matters).  `cheap` selects the issue
 // path: 0 = both 64-bit descriptors rebuilt per MMA, 1 = constant high word + 32-bit add (mma_bf16_ss_lo).

@@ -128,6 +128,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// tmem_ld32 that also "touches" the 32 registers of `hold` (no instruction reads them): every use of hold[] written
+// after this call stays after the load in the schedule, so the load is in flight while those values are consumed.
+__device__ __forceinline__ void tmem_ld32_before(uint32_t taddr, uint32_t (&v)[32], uint32_t (&hold)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+        "+r"(hold[0]), "+r"(hold[1]), "+r"(hold[2]), "+r"(hold[3]), "+r"(hold[4]), "+r"(hold[5]), "+r"(hold[6]), "+r"(hold[7]), "+r"(hold[8]), "+r"(hold[9]), "+r"(hold[10]), "+r"(hold[11]), "+r"(hold[12]), "+r"(hold[13]), "+r"(hold[14]), "+r"(hold[15]), "+r"(hold[16]), "+r"(hold[17]), "+r"(hold[18]), "+r"(hold[19]), "+r"(hold[20]), "+r"(hold[21]), "+r"(hold[22]), "+r"(hold[23]), "+r"(hold[24]), "+r"(hold[25]), "+r"(hold[26]), "+r"(hold[27]), "+r"(hold[28]), "+r"(hold[29]), "+r"(hold[30]), "+r"(hold[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -138,6 +149,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, declared as a read-modify-write of the 32 destination registers of an earlier tmem_ld32: used where
+// a second load is in flight while the first one's values are consumed, so that no use of v can be scheduled (or
+// copied to another register) before the wait.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version bit set.
@@ -195,6 +218,36 @@ __device__ __forceinline__ void mma_bf16_ss_lo(uint32_t tmem_d, uint32_t a_lo, u
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM ("TS" form): rows = the 128 lanes, one 32-bit column = two consecutive K elements (even K in
+// the low half), so one K = 16 step is 8 columns.  A must be K-major; B is a shared-memory descriptor as above.
+__device__ __forceinline__ void mma_bf16_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Thread i of the warp writes 32 consecutive 32-bit columns of lane (base_lane + i); same lane-quarter rule as
+// tmem_ld32.  tmem_st_wait() before the tcgen05.fence / mbarrier hand-over to the MMA issuer.
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

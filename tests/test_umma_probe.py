@@ -49,3 +49,19 @@ def test_cta_pair_tile_gemm(N, KB):
     torch.cuda.synchronize()
     ref = x.float() @ w.float().T
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("N,KB", [(256, 4), (256, 1), (128, 2), (16, 4), (64, 3)])
+def test_a_from_tmem_tile_gemm(N, KB):
+    """tcgen05.mma with the A operand in TMEM (written by tcgen05.st as packed bf16 pairs): the form the fused field
+    kernels use to hand one layer's activations to the next without a shared-memory round trip."""
+    g = torch.Generator().manual_seed(N * 3 + KB)
+    x = torch.randn(128, KB * 64, generator=g).bfloat16()
+    w = torch.randn(N, KB * 64, generator=g).bfloat16()
+    xb, wb = pack_blocks(x).cuda(), pack_blocks(w).cuda()
+    out = torch.full((128, N), float("nan"), device="cuda")
+    cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.call("rsn_probe_umma_ts", xb.data_ptr(), wb.data_ptr(), N, KB, out.data_ptr(), 0, cyc.data_ptr(), _lib.stream())
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().T
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-2)
