@@ -27,6 +27,7 @@
 #include "umma.cuh"
 #include "field_layout.cuh"
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace {
@@ -35,9 +36,9 @@ using namespace umma;
 using namespace rsnf;
 
 constexpr int NUM_STAGES = 3;
-constexpr int SMEM_ACT = 0;                                    // 4 blocks
-constexpr int SMEM_ENC = 4 * BLOCK_BYTES;                      // 2 buffers x 2 blocks
-constexpr int SMEM_W = SMEM_ENC + 4 * BLOCK_BYTES;             // ring
+constexpr int SMEM_ENC = 0;                                    // 2 buffers x 2 blocks
+constexpr int SMEM_ACT = 4 * BLOCK_BYTES;                      // 4 blocks (TS inference: two more ring stages)
+constexpr int SMEM_W = SMEM_ACT + 4 * BLOCK_BYTES;             // ring
 constexpr int SMEM_BARS = SMEM_W + NUM_STAGES * W_STAGE_BYTES;   // 229,376: mbarriers (256 B)
 constexpr int SMEM_BIAS = SMEM_BARS + 256;                       // 2 x 1 KB: fp32 bias of the current / next wide layer
 constexpr int SMEM_TOTAL = SMEM_BIAS + 2 * 1024;                 // 231,680 of the 232,448 a CTA may have
@@ -290,9 +291,20 @@ __device__ __forceinline__ void ide_features(const float d[3], float rho, float 
 // wavefront per load) instead of constant memory (bias_off).  The constant path is an INDEXED load (the layer is a
 // run-time value) of a 10 KB table that cycles once per tile: 32 LDC per group, 0.5 ms of 2.66 at C2 (measured by
 // replacing the bias with a register constant).
-template <bool RELU, bool MASKS = false, bool SBIAS = false>
+// TS: the packed row also goes back into TMEM (columns a_taddr..+31) as the next layer's A operand; SMEM: it is written to
+// the shared-memory block (the A operand of the SS form and / or the staging copy of the activation stash).
+// DEFER (TS + stash): the MMA does not read the shared-memory copy, so the row is handed to the next layer first
+// (tcgen05.st, then `early()` = wait::st + fence + arrive) and only then staged for the stash (`guard()`, 8 x st.shared,
+// masks): the staging is off the layer-critical path.
+struct NoOp {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <bool RELU, bool MASKS = false, bool SBIAS = false, bool TS = false, bool SMEM = true, bool DEFER = false,
+          class Early = NoOp, class Guard = NoOp>
 __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
-                                               uint32_t bias_saddr = 0, uint2* mask_out = nullptr) {
+                                               uint32_t bias_saddr = 0, uint2* mask_out = nullptr, uint32_t a_taddr = 0,
+                                               Early early = Early(), Guard guard = Guard()) {
+  static_assert(!DEFER || (TS && SMEM), "DEFER is the TS + stash form");
   uint32_t mbits[2] = {0u, 0u};
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
@@ -309,6 +321,7 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
   }
   tmem_ld_wait();
   const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
+  uint32_t a[32];   // TS: the 64 bf16 of this row, two per 32-bit TMEM column
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -325,7 +338,11 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
         pk[q * 2 + 1] = RELU ? pack_relu_bf16x2(x2, x3) : pack_bf16x2(x2, x3);
       }
       const int chunk = h * 4 + c;
-      sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      if (SMEM && !DEFER) sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      if (TS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[chunk * 4 + j] = pk[j];
+      }
       if (RELU && MASKS) {
         // ReLU mask bits of the 8 columns just packed: one packed compare (0xFFFF per half > 0) and one LOP3 per
         // word; word i of the 32-column half contributes bits i and 16 + i
@@ -339,6 +356,16 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
       }
     }
   }
+  // TS: over accumulator columns [32 g, 32 g + 32) of the same buffer, which this thread has already read
+  if (TS) tmem_st32(a_taddr, a);
+  if (DEFER) {
+    early();
+    guard();
+#pragma unroll
+    for (int chunk = 0; chunk < 8; ++chunk)
+      sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), a[chunk * 4 + 0], a[chunk * 4 + 1], a[chunk * 4 + 2],
+             a[chunk * 4 + 3]);
+  }
   if (RELU && MASKS) *mask_out = make_uint2(mbits[0], mbits[1]);
 }
 
@@ -350,19 +377,27 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __ex
 // chunk; the leader (r = 0) issues M = 256 MMAs for both.  Per SM and layer this halves the weight bytes written
 // into shared memory and the B-operand bytes read back by the tensor core (384 KB -> 256 KB of shared-memory
 // traffic against 2048 MMA cycles at 128 B/cycle): the single-CTA form is shared-memory-bandwidth bound.
-template <bool PAIR>
+// TS = true (single CTA only): the hidden activations never touch shared memory on the MMA path.  The epilogue writes
+// layer l's bf16 output with tcgen05.st over the first 128 columns of the accumulator it has just read, and layer l+1
+// takes its A operand from there (tcgen05.mma [d], [a], b-desc) while accumulating into the other buffer.  Per layer
+// this removes the A-operand reads (64 of 192 KB) and, outside training, the activation writes (64 KB) from the
+// shared-memory pipe.  The encodings (IPE, IDE) still arrive through shared memory.
+template <bool PAIR, bool TS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdParams p) {
+  static_assert(!(PAIR && TS), "the A-from-TMEM form is single-CTA");
   extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the window starts here
   Barriers& bars = *reinterpret_cast<Barriers*>(smem + SMEM_BARS);
   constexpr bool SBIAS = !PAIR;   // the pair form keeps the constant-memory bias (its issuer serves two CTAs)
-  constexpr int NS = PAIR ? 6 : NUM_STAGES;                       // weight ring: 6 x 16 KB or 3 x 32 KB
+  // weight ring: 3 x 32 KB; CTA pair: 6 x 16 KB; TS without a stash: the activation blocks are free -> 5 x 32 KB
+  const int NS = PAIR ? 6 : ((TS && !p.stash) ? 5 : NUM_STAGES);
+  const int ring_off = (TS && !p.stash) ? SMEM_ACT : SMEM_W;
   constexpr uint32_t STB = PAIR ? W_STAGE_BYTES / 2 : W_STAGE_BYTES;
   constexpr uint32_t ARRIVALS = PAIR ? 8 : TILE;                  // PAIR: one arrival per warp, both CTAs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t s_act = smem_u32(smem + SMEM_ACT);
   const uint32_t s_enc = smem_u32(smem + SMEM_ENC);
-  const uint32_t s_w = smem_u32(smem + SMEM_W);
+  const uint32_t s_w = smem_u32(smem + ring_off);
   const uint32_t s_bias = smem_u32(smem + SMEM_BIAS);
   if ((smem_u32(smem) & 1023u) != 0u) {   // the swizzled operand blocks need 1024-byte alignment
     if (threadIdx.x == 0) printf("rsn_b200: field_fwd_kernel: dynamic shared memory is not 1024-byte aligned\n");
@@ -371,7 +406,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < NS; ++i) {
+      for (int i = 0; i < MAX_STAGES; ++i) {
         mbar_init(&bars.w_full[i], 1);
         mbar_init(&bars.w_empty[i], 1);
         mbar_init(&bars.w_peer[i], 1);
@@ -423,12 +458,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           mbar_wait(&bars.w_empty[stage], phase ^ 1);
           if (!PAIR) {
             mbar_expect_tx(&bars.w_full[stage], bytes);
-            bulk_g2s(smem + SMEM_W + stage * STB, p.wblob + off, bytes, &bars.w_full[stage]);
+            bulk_g2s(smem + ring_off + stage * STB, p.wblob + off, bytes, &bars.w_full[stage]);
           } else {
             mbar_expect_tx(&bars.w_full[stage], bytes / 2);
             const uint32_t half = (uint32_t)fwd_chunk_rows(c) * 64u;     // (rows / 2) * 128 bytes per K-block
             for (int kb = 0; kb < fwd_chunk_nkb(c); ++kb)
-              bulk_g2s(smem + SMEM_W + stage * STB + kb * half, p.wblob + off + kb * 2 * half + rank * half, half,
+              bulk_g2s(smem + ring_off + stage * STB + kb * half, p.wblob + off + kb * 2 * half + rank * half, half,
                        &bars.w_full[stage]);
           }
           off += bytes;
@@ -505,6 +540,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         if (ksteps == 4) mma(6, 1u);
         acc = true;
       };
+      // K-block g of the hidden activations: shared-memory block g (SS) or TMEM columns [32 g, 32 g + 32) of the buffer
+      // the previous layer accumulated into (TS)
+      auto issue_act = [&](int g, uint32_t b_addr, uint32_t idesc, uint32_t tmem_d, uint32_t a_tm, bool& acc) {
+        if (!TS) {
+          issue_kb(s_act + g * BLOCK_BYTES, b_addr, 4, idesc, tmem_d, acc);
+        } else {
+          const uint32_t b_lo = desc_lo(b_addr, 16), a0 = a_tm + (uint32_t)g * 32u;
+          mma_bf16_ts_lo(tmem_d, a0, b_lo, HI, idesc, acc ? 1u : 0u);
+          mma_bf16_ts_lo(tmem_d, a0 + 8, b_lo + 2, HI, idesc, 1u);
+          mma_bf16_ts_lo(tmem_d, a0 + 16, b_lo + 4, HI, idesc, 1u);
+          mma_bf16_ts_lo(tmem_d, a0 + 24, b_lo + 6, HI, idesc, 1u);
+          acc = true;
+        }
+      };
       // Bias of wide layer j (10 per tile) -> slot j & 1, requested as soon as the epilogue of layer j - 2 has published
       // its last group (the issuer sees that as the last act_ready wait of layer j - 1).
       auto request_bias = [&](int j) {
@@ -542,7 +591,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
               wait_act(g);
               if (g == 3) request_bias(it * WIDE_LAYERS + l + 1);
               const uint32_t w = ring_wait();
-              issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tm, acc);
+              issue_act(g, w, ID256, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
               ring_release();
             }
           }
@@ -553,18 +602,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
+          const uint32_t a_tm = tmem + (uint32_t)(buf ^ 1) * 256;
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
             if (g == 3) request_bias(it * WIDE_LAYERS + 9);
             const uint32_t w = ring_wait();
-            issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tm, acc);
+            issue_act(g, w, ID256, tm, a_tm, acc);
             ring_release();
           }
           const uint32_t w = ring_wait();
           bool acc_h = false;
           for (int kb = 0; kb < 4; ++kb)
-            issue_kb(s_act + kb * BLOCK_BYTES, w + kb * (N_HEAD * 128 / BDIV), 4, ID16,
-                     tmem + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, acc_h);
+            issue_act(kb, w + kb * (N_HEAD * 128 / BDIV), ID16, tmem + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, a_tm,
+                      acc_h);
           ring_release();
           commit(&bars.acc_full[buf]);
           buf ^= 1;
@@ -578,8 +628,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
             wait_act(2 * c + 1);
             if (c == 1) request_bias(it * WIDE_LAYERS + 10);
             const uint32_t w = ring_wait();
-            issue_kb(s_act + (2 * c) * BLOCK_BYTES, w, 4, ID128, tm, acc);
-            issue_kb(s_act + (2 * c + 1) * BLOCK_BYTES, w + 128 * 128 / BDIV, 4, ID128, tm, acc);
+            issue_act(2 * c, w, ID128, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
+            issue_act(2 * c + 1, w + 128 * 128 / BDIV, ID128, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
             ring_release();
           }
           wait_in(&bars.ide_ready, (uint32_t)it & 1u);
@@ -599,8 +649,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           wait_act(1);
           request_bias(it * WIDE_LAYERS + 11);
           const uint32_t w = ring_wait();
-          issue_kb(s_act, w, 4, ID16, tm, acc);
-          issue_kb(s_act + BLOCK_BYTES, w + N_HEAD * 128 / BDIV, 4, ID16, tm, acc);
+          issue_act(0, w, ID16, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
+          issue_act(1, w + N_HEAD * 128 / BDIV, ID16, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
           ring_release();
           commit(&bars.acc_full[buf]);
           buf ^= 1;
@@ -641,35 +691,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         if (stash_blk) {
           warp_store_rows(stash_blk, blk_saddr, q, lane);
           if (drain) warp_store_guard<0>(lane);   // another warp role overwrites this block later
-        } else {
+        } else if (!TS || drain) {
           fence_proxy_async();
         }
+        if (TS && !drain) tmem_st_wait();
         tc_fence_before();
         arrive_issuer(bar);
       };
-      // The slice about to be overwritten was handed to the TMA engine 4 bulk groups ago (layer l-1, same g),
-      // except in layer 0, where blocks 0/1 were last stored by the previous tile's mid layer, 2 groups ago.
-      auto guard = [&]() {
-        if (st) warp_store_guard<3>(lane);
+      // Guard depths: the slice about to be overwritten was handed to the TMA engine 4 bulk groups ago (layer l-1, same
+      // g), except in layer 0, where blocks 0/1 were last stored by the previous tile's mid layer, 2 groups ago.
+      // One 64-column group of a wide layer: convert, hand to the issuer (act_ready[g]), stash.  `first` = layer 0 (guard
+      // depth, see above).
+      auto convert = [&](auto relu_c, auto masks_c, int bias_off, uint32_t sb, int g, uint2* mask_ptr, uint8_t* stash_blk,
+                         bool first) {
+        constexpr bool RELU = decltype(relu_c)::value, MASKS = decltype(masks_c)::value;
+        const uint32_t acc_c = tlane + (uint32_t)buf * 256 + g * 64, a_t = tlane + (uint32_t)buf * 256 + g * 32;
+        const uint32_t blk = s_act + g * BLOCK_BYTES;
+        auto guard_g = [&]() {
+          if (st) {
+            if (first) warp_store_guard<1>(lane); else warp_store_guard<3>(lane);
+          }
+        };
+        if (TS && st) {
+          if constexpr (TS) {
+            epilogue_group<RELU, MASKS, SBIAS, true, true, true>(
+                acc_c, bias_off + g * 64, blk, row, sb + g * 256, mask_ptr, a_t,
+                [&]() {
+                  tmem_st_wait();
+                  tc_fence_before();
+                  arrive_issuer(&bars.act_ready[g]);
+                },
+                guard_g);
+            warp_store_rows(stash_blk, blk, q, lane);
+          }
+        } else {
+          guard_g();
+          if (st) epilogue_group<RELU, MASKS, SBIAS, TS, true>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, mask_ptr, a_t);
+          else epilogue_group<RELU, false, SBIAS, TS, !TS>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, nullptr, a_t);
+          publish(&bars.act_ready[g], blk, stash_blk);
+        }
       };
+      using T_ = std::integral_constant<bool, true>;
+      using F_ = std::integral_constant<bool, false>;
+      uint2* const masks = st ? reinterpret_cast<uint2*>(st + STASH_MASK_OFF) : nullptr;
       for (int l = 0; l < 8; ++l) {
         wait_acc();
         const uint32_t sb = bias_slot();
-        for (int g = 0; g < 4; ++g) {
-          if (l == 0) {
-            if (st) warp_store_guard<1>(lane);
-          } else {
-            guard();
-          }
-          if (st)
-            epilogue_group<true, true, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
-                                              s_act + g * BLOCK_BYTES, row, sb + g * 256,
-                                              reinterpret_cast<uint2*>(st + STASH_MASK_OFF) + mask_entry(l, g, row));
-          else
-            epilogue_group<true, false, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BASE + l * 256 + g * 64,
-                                               s_act + g * BLOCK_BYTES, row, sb + g * 256);
-          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_H + 4 * l + g));
-        }
+        for (int g = 0; g < 4; ++g)
+          convert(T_{}, T_{}, BIAS_BASE + l * 256, sb, g, masks + mask_entry(l, g, row), sblk(STASH_H + 4 * l + g), l == 0);
         buf ^= 1;
       }
       // ---- layer 8: bottleneck -> activation blocks (no activation), then heads + IDE
@@ -677,12 +746,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       {
         wait_acc();
         const uint32_t sb = bias_slot();
-        for (int g = 0; g < 4; ++g) {
-          guard();
-          epilogue_group<false, false, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_BOTT + g * 64,
-                                              s_act + g * BLOCK_BYTES, row, sb + g * 256);
-          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_BOTT + g));
-        }
+        for (int g = 0; g < 4; ++g) convert(F_{}, F_{}, BIAS_BOTT, sb, g, nullptr, sblk(STASH_BOTT + g), false);
         uint32_t hv[16];
         tmem_ld16(tlane + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, hv);
         float hb[16];
@@ -760,17 +824,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       {
         wait_acc();
         const uint32_t sb = bias_slot();
-        for (int g = 0; g < 2; ++g) {
-          guard();
-          if (st)
-            epilogue_group<true, true, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64,
-                                              s_act + g * BLOCK_BYTES, row, sb + g * 256,
-                                              reinterpret_cast<uint2*>(st + STASH_MASK_OFF) + mask_entry(8, g, row));
-          else
-            epilogue_group<true, false, SBIAS>(tlane + (uint32_t)buf * 256 + g * 64, BIAS_MID + g * 64,
-                                               s_act + g * BLOCK_BYTES, row, sb + g * 256);
-          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, sblk(STASH_MIDH + g));
-        }
+        for (int g = 0; g < 2; ++g)
+          convert(T_{}, T_{}, BIAS_MID, sb, g, masks + mask_entry(8, g, row), sblk(STASH_MIDH + g), false);
         buf ^= 1;
       }
       // ---- layer 10: rgb
@@ -910,8 +965,9 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
   const size_t smem = SMEM_TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
-    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   RSN_CUDA(cudaMemcpyToSymbolAsync(c_bias4, bias, N_BIAS * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
@@ -921,7 +977,10 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
   const bool pair = p.n_tiles > 1 && getenv("RSN_FWD_PAIR") && atoi(getenv("RSN_FWD_PAIR")) == 1;
   if (!pair) {
     const int grid = std::min(p.n_tiles, rsn_num_sms());
-    field_fwd_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
+    // A-from-TMEM form by default; RSN_FWD_TS=0 selects the shared-memory (SS) form (same results bit for bit)
+    const bool ts = !(getenv("RSN_FWD_TS") && atoi(getenv("RSN_FWD_TS")) == 0);
+    if (ts) field_fwd_kernel<false, true><<<grid, NUM_THREADS, smem, stream>>>(p);
+    else field_fwd_kernel<false, false><<<grid, NUM_THREADS, smem, stream>>>(p);
   } else {
     const int pairs = std::min((p.n_tiles + 1) / 2, rsn_num_sms() / 2);
     cudaLaunchConfig_t cfg = {};
@@ -936,7 +995,7 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RSN_CUDA(cudaLaunchKernelEx(&cfg, field_fwd_kernel<true>, p));
+    RSN_CUDA(cudaLaunchKernelEx(&cfg, field_fwd_kernel<true, false>, p));
   }
   RSN_LAUNCH_CHECK("field_fwd_kernel");
   return 0;
