@@ -70,7 +70,7 @@ extern "C" int rsn_field_backward_fused(const void* wblob_t, const void* x_stash
   WParams w;
   const int n_w = fill_wgrad_params(w, x_stash, dy_stash, p.n_points, grad_blob, sms - n_chain);
   RSN_CUDA(cudaMemsetAsync(workspace, 0, (size_t)p.n_tiles * sizeof(int), stream));
-  const size_t smem = (size_t)std::max<size_t>(SM_TOTAL, (size_t)W_STAGES * SLAB_BYTES) + 1024;
+  const size_t smem = (size_t)std::max<size_t>(SM_TOTAL, (size_t)RING_BYTES) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     RSN_CUDA(cudaFuncSetAttribute(field_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

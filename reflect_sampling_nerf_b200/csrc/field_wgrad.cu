@@ -46,7 +46,7 @@ extern "C" int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_
   RSN_ARG(((uintptr_t)x_stash & 15) == 0 && ((uintptr_t)dy_stash & 15) == 0, "rsn_field_wgrad: stashes must be 16-byte aligned");
   WParams p;
   const int cta = fill_wgrad_params(p, x_stash, dy_stash, n_points, grad_blob, rsn_num_sms());
-  const size_t smem = (size_t)W_STAGES * SLAB_BYTES + 1024;
+  const size_t smem = (size_t)RING_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     RSN_CUDA(cudaFuncSetAttribute(field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

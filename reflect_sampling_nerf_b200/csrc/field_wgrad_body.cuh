@@ -23,8 +23,8 @@ constexpr int W_THREADS = 192;      // warp 0 producer, warp 1 MMA issuer, warps
 #endif
 constexpr int SLAB_ROWS = RSN_WGRAD_SLAB_ROWS;   // points per pipeline slab (SLAB_ROWS / 16 K-steps)
 constexpr int SLAB_BLOCK_BYTES = SLAB_ROWS * 128;
-constexpr int SLAB_BYTES = 8 * SLAB_BLOCK_BYTES;   // up to 4 dY + 4 X blocks
-constexpr int W_STAGES = 196608 / SLAB_BYTES;    // 192 KB ring
+constexpr int RING_BYTES = 196608;                 // 192 KB ring of (m_blocks + n_blocks) * SLAB_BLOCK_BYTES stages:
+constexpr int MAX_W_STAGES = 8;                    // 3 stages for the 4 + 4 block jobs, up to 8 for the small ones
 constexpr int MAX_JOBS = 16;
 
 struct WJob {
@@ -44,7 +44,7 @@ struct WParams {
 };
 
 struct WBarriers {
-  uint64_t full[W_STAGES], empty[W_STAGES];
+  uint64_t full[MAX_W_STAGES], empty[MAX_W_STAGES];
   uint64_t acc_full;
   uint32_t tmem_slot;
 };
@@ -68,11 +68,14 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
   const int t1 = interleave ? p.n_tiles : (int)(((int64_t)p.n_tiles * (split + 1)) / job.n_ctas);
   const int tstep = interleave ? job.n_ctas : 1;
   const int mb = job.m_blocks, nb = job.n_blocks;
+  // a job with fewer blocks per slab gets more stages: the same bytes in flight for every CTA
+  const int SLAB_BYTES = (mb + nb) * SLAB_BLOCK_BYTES;
+  const int W_STAGES = min(MAX_W_STAGES, RING_BYTES / SLAB_BYTES);
   const int n_slabs = (t1 > t0 ? (t1 - t0 + tstep - 1) / tstep : 0) * (TILE / SLAB_ROWS);
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < W_STAGES; ++i) {
+      for (int i = 0; i < MAX_W_STAGES; ++i) {
         mbar_init(&bars.full[i], 1);
         mbar_init(&bars.empty[i], 1 + 4);   // tcgen05.commit + one arrival per db warp
       }
@@ -262,22 +265,37 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
   p.grad = grad_blob;
   p.n_jobs = kNumJobs;
   p.debug = getenv("RSN_WGRAD_DEBUG") ? atoi(getenv("RSN_WGRAD_DEBUG")) : 0;
-  int units = 0;
+  int units = 0, n_of[kNumJobs], used = 0;
   for (int j = 0; j < kNumJobs; ++j) units += kJobs[j].m_blocks + kJobs[j].n_blocks;
+  // CTAs per job proportional to the job's bytes per tile; the kernel ends with the job whose CTAs carry the most
+  // bytes each, so the CTAs left over by the rounding go, one at a time, to the job with the largest bytes / CTA
+  for (int j = 0; j < kNumJobs; ++j) {
+    const int u = kJobs[j].m_blocks + kJobs[j].n_blocks;
+    n_of[j] = std::min(std::max(1, (u * cta_budget) / units), p.n_tiles);
+    used += n_of[j];
+  }
+  while (used < cta_budget) {
+    int best = -1;
+    double worst = 0.0;
+    for (int j = 0; j < kNumJobs; ++j) {
+      const double load = (double)(kJobs[j].m_blocks + kJobs[j].n_blocks) / n_of[j];
+      if (n_of[j] < p.n_tiles && load > worst) worst = load, best = j;
+    }
+    if (best < 0) break;
+    ++n_of[best];
+    ++used;
+  }
   int64_t off = 0;
   int cta = 0;
   for (int j = 0; j < kNumJobs; ++j) {
-    const int u = kJobs[j].m_blocks + kJobs[j].n_blocks;
-    int n = std::max(1, (u * cta_budget) / units);
-    n = std::min(n, p.n_tiles);
     WJob& w = p.jobs[j];
     w.a_blk = kJobs[j].a_blk, w.m_blocks = kJobs[j].m_blocks, w.b_blk = kJobs[j].b_blk, w.n_blocks = kJobs[j].n_blocks;
     w.out_off = (int)off;
     off += (int64_t)w.m_blocks * 64 * w.n_blocks * 64;
     w.db_off = kJobs[j].has_db ? (int)off : -1;
     if (kJobs[j].has_db) off += w.m_blocks * 64;
-    w.cta_begin = cta, w.n_ctas = n;
-    cta += n;
+    w.cta_begin = cta, w.n_ctas = n_of[j];
+    cta += n_of[j];
   }
   return cta;
 }
