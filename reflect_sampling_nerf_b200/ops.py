@@ -25,7 +25,9 @@ KERNEL_WORK = {
     "field_chain_kernel<normals>": (1019392, 288 + 4 * 128 + 12),
     "field_chain_kernel<backward>": (1179904, 288 + 39 * 128 + 160),
     "field_chain_kernel<backward+area>": (1229056, 288 + 4 * 128 + 39 * 128 + 164),
-    "field_wgrad_kernel": (1230592, 95 * 128),
+    # every stash block once: 41 activation + 39 dY blocks of 128 B per point (the 14 jobs read 95 blocks per tile; the 15
+    # second reads are served by L2 when the jobs stream the same tiles together)
+    "field_wgrad_kernel": (1230592, 80 * 128),
     # fused backward: dgrad + wgrad FLOPs; HBM: masks + dY written once + X read (dY read back from L2)
     "field_bwd_fused_kernel": (1179904 + 1230592, 288 + 39 * 128 + 160 + 56 * 128),
     "field_bwd_fused_kernel+area": (1229056 + 1230592, 288 + 4 * 128 + 39 * 128 + 164 + 56 * 128),

@@ -58,7 +58,7 @@ timeit(lambda: ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sig
        P * 1179904, P * (288 + 39 * 128 + 160), "field_chain<backward>")
 timeit(lambda: ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, True),
        P * 1229056, P * (288 + 4 * 128 + 39 * 128 + 164), "field_chain<backward+area>")
-timeit(lambda: ops.field_wgrad(stash, dy, P, blob), P * 1230592, P * 95 * 128, "field_wgrad")
+timeit(lambda: ops.field_wgrad(stash, dy, P, blob), P * 1230592, P * 80 * 128, "field_wgrad")
 blob2 = torch.zeros(ops.wgrad_layout()[2], device="cuda")
 timeit(lambda: ops.field_backward_fused(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, False, blob2),
        P * (1179904 + 1230592), P * (288 + 39 * 128 + 160 + 56 * 128), "field_bwd_fused (chain+wgrad)")
