@@ -46,6 +46,8 @@ struct BwdParams {
   const float* aux;         // [P,8]    forward aux (mid rgb, raw normal head)
   uint8_t* dy_stash;        // [n_tiles][DY_BLOCKS][16 KB]
   float* g_area;            // [P]      dL/d pixel_area (or sqradius) contribution of each point, or NULL
+  int debug;                // RSN_BWD_DEBUG (timing experiments only; results are wrong): 1 = no dY bulk stores,
+                            // 4 = no wait for the TMA engine before a staged slice is overwritten, 8 = no weight streaming
 };
 
 struct BBarriers {
@@ -72,8 +74,11 @@ __device__ __forceinline__ uint4 lds128b(uint32_t saddr) {
 }
 // Stashed ReLU bit masks (csrc/field_layout.cuh): bit i / 16 + i of word w = columns 32 w + 2 i / + 1 of the group.
 // 0xFFFF in each half of packed word i whose column was > 0 in the forward.
+// (shift bit i to the top of byte 0 and bit 16 + i to the top of byte 2, then one PRMT whose selector nibbles 0x8 / 0xA
+// replicate the sign of byte 0 / byte 2 over two bytes each)
 __device__ __forceinline__ uint32_t relu_mask_word(uint32_t bits, int i) {
-  return ((bits >> i) & 0x00010001u) * 0xffffu;
+  const uint32_t t = (i <= 7) ? (bits << (7 - i)) : (bits >> (i - 7));
+  return __byte_perm(t, 0u, 0xAA88u);
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -240,8 +245,12 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
       uint32_t phase = 0;
       auto push = [&](uint32_t off, uint32_t bytes) {
         mbar_wait(&bars.w_empty[stage], phase ^ 1);
-        mbar_expect_tx(&bars.w_full[stage], bytes);
-        bulk_g2s(smem + SM_W + stage * W_STAGE_BYTES, p.wblob_t + off, bytes, &bars.w_full[stage]);
+        if (p.debug & 8) {
+          mbar_arrive(&bars.w_full[stage]);   // timing experiment: no weight traffic
+        } else {
+          mbar_expect_tx(&bars.w_full[stage], bytes);
+          bulk_g2s(smem + SM_W + stage * W_STAGE_BYTES, p.wblob_t + off, bytes, &bars.w_full[stage]);
+        }
         if (++stage == NUM_WSTAGES) {
           stage = 0;
           phase ^= 1;
@@ -420,7 +429,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
       };
       // publish a freshly written block (rows of this warp): optional coalesced stash store, then the barrier
       auto publish = [&](uint64_t* bar, uint32_t blk_saddr = 0, uint8_t* stash_blk = nullptr) {
-        if (stash_blk) {
+        if (stash_blk && !(p.debug & 1)) {
           warp_store_rows(stash_blk, blk_saddr, q, lane);
         } else {
           fence_proxy_async();
@@ -430,7 +439,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
       };
       // the act slice about to be overwritten was handed to the TMA engine at most 4 bulk groups ago
       auto guard = [&]() {
-        if (KIND == KIND_BACKWARD) warp_store_guard<3>(lane);
+        if (KIND == KIND_BACKWARD && !(p.debug & 4)) warp_store_guard<3>(lane);
       };
       auto mask_wait = [&]() -> uint32_t {
         mbar_wait(&bars.m_full[mstage], mphase);

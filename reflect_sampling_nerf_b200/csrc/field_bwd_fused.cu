@@ -47,6 +47,7 @@ extern "C" int rsn_field_backward_fused(const void* wblob_t, const void* x_stash
   p.wblob_t = (const uint8_t*)wblob_t;
   p.x_stash = (const uint8_t*)x_stash;
   p.kind = KIND_BACKWARD;
+  p.debug = getenv("RSN_BWD_DEBUG") ? atoi(getenv("RSN_BWD_DEBUG")) : 0;
   p.mode = mode;
   p.want_area = g_area != nullptr;
   p.origins = origins;

@@ -78,7 +78,7 @@ struct FwdParams {
   float* feat;              // [P][16]
   uint8_t* stash;           // training: [n_tiles][STASH_BLOCKS][16 KB] activation block images, or NULL
   float* aux;               // training: [P][8] = mid rgb (3), raw normal head (3), 2 spare, or NULL
-  int debug;                // RSN_FWD_DEBUG (timing experiments only): 2 = no trig in the prologue
+  int debug;                // RSN_FWD_DEBUG (timing experiments only): 2 = no trig in the prologue, 4 = no weight streaming
 };
 
 constexpr int MAX_STAGES = 6;
@@ -456,7 +456,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         for (int c = 0; c < N_FWD_CHUNKS; ++c) {
           const uint32_t bytes = fwd_chunk_bytes(c);
           mbar_wait(&bars.w_empty[stage], phase ^ 1);
-          if (!PAIR) {
+          if (!PAIR && (p.debug & 4)) {
+            mbar_arrive(&bars.w_full[stage]);     // timing experiment: no weight traffic at all (results are garbage)
+          } else if (!PAIR) {
             mbar_expect_tx(&bars.w_full[stage], bytes);
             bulk_g2s(smem + ring_off + stage * STB, p.wblob + off, bytes, &bars.w_full[stage]);
           } else {
