@@ -78,7 +78,9 @@ __device__ __forceinline__ uint4 lds128b(uint32_t saddr) {
 // replicate the sign of byte 0 / byte 2 over two bytes each)
 __device__ __forceinline__ uint32_t relu_mask_word(uint32_t bits, int i) {
   const uint32_t t = (i <= 7) ? (bits << (7 - i)) : (bits >> (i - 7));
-  return __byte_perm(t, 0u, 0xAA88u);
+  uint32_t m;   // (inline PTX: the __byte_perm intrinsic only honours the low three bits of each selector nibble)
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(t), "r"(0u), "r"(0xAA88u));
+  return m;
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
