@@ -382,9 +382,15 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __ex
 // takes its A operand from there (tcgen05.mma [d], [a], b-desc) while accumulating into the other buffer.  Per layer
 // this removes the A-operand reads (64 of 192 KB) and, outside training, the activation writes (64 KB) from the
 // shared-memory pipe.  The encodings (IPE, IDE) still arrive through shared memory.
-template <bool PAIR, bool TS>
+// MC = true: 2-CTA clusters that share only the WEIGHT STREAM.  Each CTA is a complete single-CTA pipeline (own tile,
+// own cta_group::1 MMAs, own TMEM); CTA r fetches half r of every weight chunk and multicasts it into both CTAs' ring
+// slots, so the bytes pulled out of L2 per point halve.  The only coupling is the ring: a slot is refilled once both
+// CTAs' MMAs have released it (w_empty counts two multicast commits).
+template <bool PAIR, bool TS, bool MC = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdParams p) {
   static_assert(!(PAIR && TS), "the A-from-TMEM form is single-CTA");
+  static_assert(!(PAIR && MC), "MC pairs CTAs for the weight stream only");
+  constexpr bool CL = PAIR || MC;   // launched as 2-CTA clusters
   extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the window starts here
   Barriers& bars = *reinterpret_cast<Barriers*>(smem + SMEM_BARS);
   constexpr bool SBIAS = !PAIR;   // the pair form keeps the constant-memory bias (its issuer serves two CTAs)
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
   constexpr uint32_t STB = PAIR ? W_STAGE_BYTES / 2 : W_STAGE_BYTES;
   constexpr uint32_t ARRIVALS = PAIR ? 8 : TILE;                  // PAIR: one arrival per warp, both CTAs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t rank = CL ? cluster_ctarank() : 0u;
   const uint32_t s_act = smem_u32(smem + SMEM_ACT);
   const uint32_t s_enc = smem_u32(smem + SMEM_ENC);
   const uint32_t s_w = smem_u32(smem + ring_off);
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     if (lane == 0) {
       for (int i = 0; i < MAX_STAGES; ++i) {
         mbar_init(&bars.w_full[i], 1);
-        mbar_init(&bars.w_empty[i], 1);
+        mbar_init(&bars.w_empty[i], MC ? 2 : 1);
         mbar_init(&bars.w_peer[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -425,15 +431,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     if (PAIR) tmem_alloc_2cta(&bars.tmem_slot, 512); else tmem_alloc(&bars.tmem_slot, 512);
   }
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (CL) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_slot;
   // tiles of this CTA: single CTA: blockIdx.x + it * gridDim.x; pair q of Q: 2 (q + it Q) + rank (the last may be void)
-  const int n_units = PAIR ? (p.n_tiles + 1) / 2 : p.n_tiles;
-  const int unit0 = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
-  const int n_workers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int n_units = CL ? (p.n_tiles + 1) / 2 : p.n_tiles;
+  const int unit0 = CL ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int n_workers = CL ? (int)gridDim.x / 2 : (int)gridDim.x;
   const int n_my_tiles = (n_units > unit0) ? (n_units - unit0 + n_workers - 1) / n_workers : 0;
-  auto tile_of = [&](int it) -> int { return PAIR ? 2 * (unit0 + it * n_workers) + (int)rank : unit0 + it * n_workers; };
+  auto tile_of = [&](int it) -> int { return CL ? 2 * (unit0 + it * n_workers) + (int)rank : unit0 + it * n_workers; };
   // signal a barrier of the MMA issuer (in the leader CTA of a pair)
   auto arrive_issuer = [&](uint64_t* bar) {
     if (!PAIR) {
@@ -458,6 +464,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           mbar_wait(&bars.w_empty[stage], phase ^ 1);
           if (!PAIR && (p.debug & 4)) {
             mbar_arrive(&bars.w_full[stage]);     // timing experiment: no weight traffic at all (results are garbage)
+          } else if (MC) {
+            // my half of the chunk into both CTAs' slots; my barrier expects the whole chunk (the other half arrives
+            // from the peer's multicast -- possibly before this expect_tx, which the transaction count tolerates)
+            mbar_expect_tx(&bars.w_full[stage], bytes);
+            bulk_g2s_multicast(smem + ring_off + stage * STB + rank * (bytes / 2), p.wblob + off + rank * (bytes / 2),
+                               bytes / 2, &bars.w_full[stage], (uint16_t)3);
           } else if (!PAIR) {
             mbar_expect_tx(&bars.w_full[stage], bytes);
             bulk_g2s(smem + ring_off + stage * STB, p.wblob + off, bytes, &bars.w_full[stage]);
@@ -517,7 +529,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         return s_w + (uint32_t)stage * STB;
       };
       auto ring_release = [&]() {
-        commit(&bars.w_empty[stage]);
+        if (MC) mma_commit_multicast2(&bars.w_empty[stage]); else commit(&bars.w_empty[stage]);
         if (++stage == NS) {
           stage = 0;
           wphase ^= 1;
@@ -913,7 +925,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
 
   if (p.stash && lane == 0 && warp >= 2) bulk_wait_all<0>();
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (CL) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     if (PAIR) tmem_dealloc_2cta(tmem, 512); else tmem_dealloc(tmem, 512);
   }
@@ -970,6 +982,7 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
     RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   RSN_CUDA(cudaMemcpyToSymbolAsync(c_bias4, bias, N_BIAS * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
@@ -977,7 +990,8 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
   // one tile in flight per CTA the two cross-CTA hops per layer (commit multicast -> peer epilogue -> remote arrive
   // -> issuer) cost what the halved shared-memory traffic saves: 2.86 ms vs 2.63 ms at C2.
   const bool pair = p.n_tiles > 1 && getenv("RSN_FWD_PAIR") && atoi(getenv("RSN_FWD_PAIR")) == 1;
-  if (!pair) {
+  const bool mc = !pair && p.n_tiles > 1 && getenv("RSN_FWD_MC") && atoi(getenv("RSN_FWD_MC")) == 1;
+  if (!pair && !mc) {
     const int grid = std::min(p.n_tiles, rsn_num_sms());
     // A-from-TMEM form by default; RSN_FWD_TS=0 selects the shared-memory (SS) form (same results bit for bit)
     const bool ts = !(getenv("RSN_FWD_TS") && atoi(getenv("RSN_FWD_TS")) == 0);
@@ -997,7 +1011,8 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RSN_CUDA(cudaLaunchKernelEx(&cfg, field_fwd_kernel<true, false>, p));
+    if (mc) RSN_CUDA(cudaLaunchKernelEx(&cfg, field_fwd_kernel<false, true, true>, p));
+    else RSN_CUDA(cudaLaunchKernelEx(&cfg, field_fwd_kernel<true, false>, p));
   }
   RSN_LAUNCH_CHECK("field_fwd_kernel");
   return 0;

@@ -335,6 +335,27 @@ __device__ __forceinline__ void mma_bf16_ss_lo_2cta(uint32_t tmem_d, uint32_t a_
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Bulk copy global -> the same shared-memory offset in every CTA of the cluster named by cta_mask; each destination
+// CTA's mbarrier at the offset of `bar` receives complete_tx(bytes).
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// cta_group::1 commit that arrives on the mbarrier at this offset in BOTH CTAs of a 2-CTA cluster (each CTA issues its own
+// MMAs; the barrier guards a shared-memory slot that either CTA's multicast copy overwrites)
+__device__ __forceinline__ void mma_commit_multicast2(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once all prior MMAs have completed
 __device__ __forceinline__ void mma_commit_2cta(uint64_t* bar) {
   asm volatile(

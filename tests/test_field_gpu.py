@@ -133,6 +133,27 @@ def test_tmem_operand_form_is_bit_identical(monkeypatch):
     assert torch.equal(t0[3][..., :6], t1[3][..., :6])      # aux: 6 of 8 floats per point are defined
 
 
+def test_multicast_weight_stream_form_is_bit_identical(monkeypatch):
+    """RSN_FWD_MC=1: 2-CTA clusters in which each CTA fetches half of every weight chunk and multicasts it to both
+    (odd tile count => the last cluster has a void tile).  Same arithmetic => identical outputs and stash."""
+    from reflect_sampling_nerf_b200 import _lib
+    field, o, d, pa, bins = _setup(37, 24, 5, "uniform", 8.1e-7)      # 888 points = 7 tiles
+    wblob, bias = [t.cuda() for t in packing.pack_field(field.state_dict())]
+    args = (o.cuda(), d.cuda(), pa.cuda(), bins.cuda())
+    nbytes = _lib.lib().rsn_field_stash_bytes(37 * 24)
+    zeros = lambda: torch.zeros(nbytes, dtype=torch.uint8, device="cuda")  # noqa: E731
+    monkeypatch.delenv("RSN_FWD_MC", raising=False)
+    s0, f0 = ops.field_forward(wblob, bias, *args)
+    t0 = ops.field_forward_train(wblob, bias, 0, *args, stash=zeros())
+    monkeypatch.setenv("RSN_FWD_MC", "1")
+    s1, f1 = ops.field_forward(wblob, bias, *args)
+    t1 = ops.field_forward_train(wblob, bias, 0, *args, stash=zeros())
+    torch.cuda.synchronize()
+    assert torch.equal(s0, s1) and torch.equal(f0, f1)
+    assert torch.equal(t0[0], t1[0]) and torch.equal(t0[1], t1[1]) and torch.equal(t0[2], t1[2])
+    assert torch.equal(t0[3][..., :6], t1[3][..., :6])
+
+
 def test_pack_kernel_matches_host_packing():
     """csrc/pack.cu (one launch) against the tensor-op packers of packing.py: identical bytes."""
     torch.manual_seed(9)
