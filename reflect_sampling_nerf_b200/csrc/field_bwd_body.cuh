@@ -4,6 +4,8 @@
 #include "umma.cuh"
 #include "field_layout.cuh"
 #include <algorithm>
+#include <type_traits>
+#include <stdlib.h>
 
 namespace {
 
@@ -85,15 +87,22 @@ __device__ __forceinline__ uint32_t relu_mask_word(uint32_t bits, int i) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-// 64 accumulator columns of this row -> (optional ReLU mask from the stashed activation block) -> bf16 ->
-// activation block in place, and (optional) the same chunk into the dY stash.
-template <bool MASK>
-__device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_saddr, uint2 mbits, int row) {
+// 64 accumulator columns of this row -> (optional ReLU mask from the stashed bit masks) -> bf16 -> the next step's A
+// operand: SS form: the shared-memory activation block, in place; TS form: TMEM columns a_taddr..+31 (over accumulator
+// columns this thread has already read).  DEFER (TS + dY stash): hand over first (`early()` = wait::st, fence, arrive),
+// then `guard()` and stage the row in shared memory for the bulk store -- off the step-critical path.
+struct NoOpB {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <bool MASK, bool TS = false, bool DEFER = false, class Early = NoOpB, class Guard = NoOpB>
+__device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_saddr, uint2 mbits, int row,
+                                            uint32_t a_taddr = 0, Early early = Early(), Guard guard = Guard()) {
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
   tmem_ld_wait();
   const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
+  uint32_t a[32];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const uint32_t* x = &v[c >> 2][(c & 3) * 8];
@@ -107,7 +116,16 @@ __device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_
       pk.z &= relu_mask_word(bits, i0 + 2);
       pk.w &= relu_mask_word(bits, i0 + 3);
     }
-    sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), pk);
+    if (!TS) sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), pk);
+    else a[c * 4 + 0] = pk.x, a[c * 4 + 1] = pk.y, a[c * 4 + 2] = pk.z, a[c * 4 + 3] = pk.w;
+  }
+  if (TS) tmem_st32(a_taddr, a);
+  if (DEFER) {
+    early();
+    guard();
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), make_uint4(a[c * 4], a[c * 4 + 1], a[c * 4 + 2], a[c * 4 + 3]));
   }
 }
 
@@ -203,7 +221,9 @@ __device__ __forceinline__ void enc_contract(uint32_t tmem_row, uint32_t enc0_sa
 
 // `vbid` / `vgrid`: index of this CTA among the chain CTAs and their number (the fused backward kernel runs wgrad CTAs
 // beside them); `tile_done` (or NULL): per-tile flags this chain sets once a tile's dY blocks are in global memory.
-template <int KIND>
+// TS: the dY operand of every step comes from TMEM (tcgen05.mma [d], [a], b-desc), written there by the previous step's
+// epilogue; the shared-memory activation blocks then only stage the dY stash (BACKWARD) or are unused (NORMALS).
+template <int KIND, bool TS = false>
 __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, const int vgrid, int* tile_done) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -335,6 +355,21 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         }
         acc = true;
       };
+      // K-block g of the current dY: shared-memory block g (SS) or TMEM columns [32 g, 32 g + 32) of the OTHER
+      // accumulator buffer, where the previous step's epilogue left it (TS)
+      auto issue_act = [&](int g, uint32_t b_addr, uint32_t idesc, uint32_t tmem_d, bool& acc) {
+        if (!TS) {
+          issue_kb(s_act + g * BLOCK_BYTES, b_addr, 4, idesc, tmem_d, acc);
+        } else {
+          const uint32_t b_lo = desc_lo(b_addr, 16), a0 = tmem + (uint32_t)(buf ^ 1) * 256 + (uint32_t)g * 32u;
+          mma_bf16_ts_lo(tmem_d, a0, b_lo, HI, idesc, acc ? 1u : 0u);
+          mma_bf16_ts_lo(tmem_d, a0 + 8, b_lo + 2, HI, idesc, 1u);
+          mma_bf16_ts_lo(tmem_d, a0 + 16, b_lo + 4, HI, idesc, 1u);
+          mma_bf16_ts_lo(tmem_d, a0 + 24, b_lo + 6, HI, idesc, 1u);
+          acc = true;
+        }
+      };
+      constexpr uint32_t ENC4_COL = TS ? 128u : 0u;   // layer-4 encoding part: columns of the other buffer (TS: A sits in 0..127)
       for (int it = 0; it < n_my_tiles; ++it) {
         bool acc;
         if (KIND == KIND_BACKWARD) {
@@ -352,7 +387,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           for (int g = 0; g < 2; ++g) {
             wait_act(g);
             w = ring_wait();
-            issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tmem + (uint32_t)buf * 256, acc);
+            issue_act(g, w, ID256, tmem + (uint32_t)buf * 256, acc);
             ring_release();
           }
           mma_commit(&bars.acc_full[buf]);
@@ -362,7 +397,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
             w = ring_wait();
-            issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tmem + (uint32_t)buf * 256, acc);
+            issue_act(g, w, ID256, tmem + (uint32_t)buf * 256, acc);
             ring_release();
           }
           w = ring_wait();
@@ -377,7 +412,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
             const uint32_t w = ring_wait();
-            issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID256, tmem + (uint32_t)buf * 256, acc);
+            issue_act(g, w, ID256, tmem + (uint32_t)buf * 256, acc);
             ring_release();
           }
           if (l == 4 && with_enc) {
@@ -385,7 +420,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
             bool acc_e = false;
             for (int g = 0; g < 4; ++g) {
               const uint32_t w = ring_wait();
-              issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID128, tmem + (uint32_t)(buf ^ 1) * 256, acc_e);
+              issue_act(g, w, ID128, tmem + (uint32_t)(buf ^ 1) * 256 + ENC4_COL, acc_e);
               ring_release();
             }
           }
@@ -403,7 +438,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
             const uint32_t w = ring_wait();
-            issue_kb(s_act + g * BLOCK_BYTES, w, 4, ID128, tmem + (uint32_t)buf * 256, acc);
+            issue_act(g, w, ID128, tmem + (uint32_t)buf * 256, acc);
             ring_release();
           }
           mma_commit(&bars.acc_full[buf]);
@@ -443,6 +478,32 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
       auto guard = [&]() {
         if (KIND == KIND_BACKWARD && !(p.debug & 4)) warp_store_guard<3>(lane);
       };
+      // one 64-column group of a step: convert, hand to the issuer (act_ready[g]), stash (BACKWARD)
+      auto convert = [&](auto mask_c, int g, uint2 mbits, uint8_t* stash_blk, auto guard_fn) {
+        constexpr bool MASK = decltype(mask_c)::value;
+        const uint32_t acc_c = tlane + (uint32_t)buf * 256 + g * 64, a_t = tlane + (uint32_t)buf * 256 + g * 32;
+        const uint32_t blk = s_act + g * BLOCK_BYTES;
+        if constexpr (!TS) {
+          guard_fn();
+          dgrad_group<MASK>(acc_c, blk, mbits, row);
+          publish(&bars.act_ready[g], blk, stash_blk);
+        } else {
+          auto early = [&]() {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.act_ready[g]);
+          };
+          if (KIND == KIND_BACKWARD) {
+            dgrad_group<MASK, true, true>(acc_c, blk, mbits, row, a_t, early, guard_fn);
+            if (!(p.debug & 1)) warp_store_rows(stash_blk, blk, q, lane);
+          } else {
+            dgrad_group<MASK, true, false>(acc_c, blk, mbits, row, a_t);
+            early();
+          }
+        }
+      };
+      using T_ = std::integral_constant<bool, true>;
+      using F_ = std::integral_constant<bool, false>;
       auto mask_wait = [&]() -> uint32_t {
         mbar_wait(&bars.m_full[mstage], mphase);
         return s_m + (uint32_t)mstage * BLOCK_BYTES;
@@ -518,18 +579,12 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         uint2 mk0[4];
         load_masks(8, 2, mk0);
         wait_acc();
-        for (int g = 0; g < 2; ++g) {
-          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, mk0[g], row);
-          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, dblk(DY_MID + g));
-        }
+        for (int g = 0; g < 2; ++g) convert(T_{}, g, mk0[g], dblk(DY_MID + g), []() {});
         buf ^= 1;
         // ---- E1: d bottleneck (no activation) -> dY_bott
         wait_acc();
-        for (int g = 0; g < 4; ++g) {
-          warp_store_guard<1>(lane);   // blocks 0/1 were handed to the TMA engine by E0, 2 groups ago
-          dgrad_group<false>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, make_uint2(0u, 0u), row);
-          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES, dblk(DY_BOTT + g));
-        }
+        for (int g = 0; g < 4; ++g)   // (guard: blocks 0/1 were handed to the TMA engine by E0, 2 groups ago)
+          convert(F_{}, g, make_uint2(0u, 0u), dblk(DY_BOTT + g), [&]() { warp_store_guard<1>(lane); });
         buf ^= 1;
       } else {
         // ---- NORMALS seed: dY_7 = w_density * (h7 > 0)
@@ -537,16 +592,25 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         load_masks(7, 4, mk7);
         for (int g = 0; g < 4; ++g) {
           const uint32_t row_saddr = s_act + g * BLOCK_BYTES + (uint32_t)row * 128u;
+          uint32_t a[32];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.wd_bf16) + g * 8 + c);
             const uint32_t bits = (c >> 2) ? mk7[g].y : mk7[g].x;
             const int i0 = (c & 3) * 4;
-            sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4),
-                    make_uint4(wv.x & relu_mask_word(bits, i0), wv.y & relu_mask_word(bits, i0 + 1),
-                               wv.z & relu_mask_word(bits, i0 + 2), wv.w & relu_mask_word(bits, i0 + 3)));
+            const uint4 m = make_uint4(wv.x & relu_mask_word(bits, i0), wv.y & relu_mask_word(bits, i0 + 1),
+                                       wv.z & relu_mask_word(bits, i0 + 2), wv.w & relu_mask_word(bits, i0 + 3));
+            if (!TS) sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), m);
+            else a[c * 4] = m.x, a[c * 4 + 1] = m.y, a[c * 4 + 2] = m.z, a[c * 4 + 3] = m.w;
           }
-          publish(&bars.act_ready[g]);
+          if (TS) {   // the first step accumulates into `buf`: its A operand goes to the other buffer
+            tmem_st32(tlane + (uint32_t)(buf ^ 1) * 256 + g * 32, a);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.act_ready[g]);
+          } else {
+            publish(&bars.act_ready[g]);
+          }
         }
       }
       // ---- chain: (BACKWARD: E2 = d emb) then layers 7..1; each: acc * (h_{l-1} > 0) -> dY_{l-1}
@@ -567,17 +631,12 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           }
           mbar_wait(&bars.m_full[mstage1], mphase1);
           const uint32_t e1 = s_m + (uint32_t)mstage1 * BLOCK_BYTES;
-          enc_contract<KIND>(tlane + (uint32_t)(buf ^ 1) * 256, e0, e1, row, red);
+          enc_contract<KIND>(tlane + (uint32_t)(buf ^ 1) * 256 + (TS ? 128u : 0u), e0, e1, row, red);
           mask_release();
           mask_release();
         }
-        for (int g = 0; g < 4; ++g) {
-          guard();
-          // output = dY_{l-1}: stash block DY_H + 4 (l-1) + g
-          dgrad_group<true>(tlane + (uint32_t)buf * 256 + g * 64, s_act + g * BLOCK_BYTES, mk[g], row);
-          publish(&bars.act_ready[g], s_act + g * BLOCK_BYTES,
-                  (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr);
-        }
+        for (int g = 0; g < 4; ++g)   // output = dY_{l-1}: stash block DY_H + 4 (l-1) + g
+          convert(T_{}, g, mk[g], (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr, guard);
         buf ^= 1;
       }
       if (with_enc) {
@@ -648,9 +707,9 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-template <int KIND>
+template <int KIND, bool TS>
 __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_constant__ BwdParams p) {
-  chain_body<KIND>(p, (int)blockIdx.x, (int)gridDim.x, nullptr);
+  chain_body<KIND, TS>(p, (int)blockIdx.x, (int)gridDim.x, nullptr);
 }
 
 template <int KIND>
@@ -658,11 +717,15 @@ int launch_chain(const BwdParams& p, cudaStream_t stream) {
   const size_t smem = SM_TOTAL + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    RSN_CUDA(cudaFuncSetAttribute(field_chain_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RSN_CUDA(cudaFuncSetAttribute(field_chain_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RSN_CUDA(cudaFuncSetAttribute(field_chain_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int grid = std::min(p.n_tiles, rsn_num_sms());
-  field_chain_kernel<KIND><<<grid, B_THREADS, smem, stream>>>(p);
+  // dY operand from TMEM by default; RSN_BWD_TS=0 selects the shared-memory (SS) form (same results bit for bit)
+  const bool ts = !(getenv("RSN_BWD_TS") && atoi(getenv("RSN_BWD_TS")) == 0);
+  if (ts) field_chain_kernel<KIND, true><<<grid, B_THREADS, smem, stream>>>(p);
+  else field_chain_kernel<KIND, false><<<grid, B_THREADS, smem, stream>>>(p);
   RSN_LAUNCH_CHECK("field_chain_kernel");
   return 0;
 }

@@ -155,3 +155,31 @@ def test_fused_backward_matches_two_launch_form():
     torch.cuda.synchronize()
     assert torch.equal(dy1, dy2) and torch.equal(a1, a2)
     torch.testing.assert_close(b1, b2, rtol=1e-4, atol=1e-5 * float(b1.abs().max()))     # atomics order differs
+
+
+@pytest.mark.parametrize("want_area", [False, True])
+def test_chain_tmem_operand_form_is_bit_identical(monkeypatch, want_area):
+    """Default chain kernels (dY operand from TMEM, dY stash staged after the hand-over) against the shared-memory
+    operand form (RSN_BWD_TS=0): same arithmetic in the same order => identical normals, dY stash and d pixel_area."""
+    n, s = 37, 24                                                     # 888 points = 7 tiles
+    field, o, d, pa, bins, g = _setup(n, s, 21, "uniform", 8.1e-7)
+    sd = field.state_dict()
+    wblob, bias = [t.cuda() for t in packing.pack_field(sd)]
+    wblob_t, wd = [t.cuda() for t in packing.pack_field_t(sd)]
+    o, d, pa, bins = o.cuda(), d.cuda(), pa.reshape(-1).cuda(), bins.cuda()
+    g_sigma = (torch.randn(n, s, generator=g) * 0.1).cuda()
+    g_feat = (torch.randn(n, s, 16, generator=g) * 0.1).cuda()
+    sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, 0, o, d, pa, bins)
+    nbytes = _lib.lib().rsn_field_dy_stash_bytes(n * s)
+    out = {}
+    for ts in ("1", "0"):
+        monkeypatch.setenv("RSN_BWD_TS", ts)
+        dy = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        normals = ops.field_normals(wblob_t, wd, stash, n, s)
+        g_area = ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, want_area)
+        torch.cuda.synchronize()
+        out[ts] = (normals, dy, g_area)
+    assert torch.equal(out["1"][0], out["0"][0])
+    assert torch.equal(out["1"][1], out["0"][1])
+    if want_area:
+        assert torch.equal(out["1"][2], out["0"][2])
