@@ -15,6 +15,7 @@ using namespace rsnf;
 constexpr int KIND_NORMALS = 0, KIND_BACKWARD = 1;
 constexpr int B_THREADS = 224;
 constexpr int NUM_WSTAGES = 3, NUM_MSTAGES = 2;   // the second ring only carries the two stashed enc blocks
+constexpr int MAX_WSTAGES = 5;                    // NORMALS in the TS form: activation + seed blocks are free -> 5 stages
 constexpr int SM_ACT = 0;                                  // 4 blocks: dY, rewritten in place step by step
 constexpr int SM_SEED = 4 * BLOCK_BYTES;                   // 1 block: d(rgb head) cols 0-15, d(heads) cols 16-31
 constexpr int SM_W = SM_SEED + BLOCK_BYTES;                // weight ring
@@ -53,7 +54,7 @@ struct BwdParams {
 };
 
 struct BBarriers {
-  uint64_t w_full[NUM_WSTAGES], w_empty[NUM_WSTAGES];
+  uint64_t w_full[MAX_WSTAGES], w_empty[MAX_WSTAGES];
   uint64_t m_full[NUM_MSTAGES], m_empty[NUM_MSTAGES];
   uint64_t act_ready[4];
   uint64_t seed_ready;
@@ -231,13 +232,18 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_act = smem_u32(smem + SM_ACT);
   const uint32_t s_seed = smem_u32(smem + SM_SEED);
-  const uint32_t s_w = smem_u32(smem + SM_W);
+  // weight ring: 3 x 32 KB after the activation and seed blocks; the TS form of NORMALS uses neither block: 5 x 32 KB
+  // from the start of the buffer
+  constexpr int NWS = (TS && KIND == KIND_NORMALS) ? MAX_WSTAGES : NUM_WSTAGES;
+  constexpr int RING_OFF = (TS && KIND == KIND_NORMALS) ? SM_ACT : SM_W;
+  static_assert(RING_OFF + NWS * W_STAGE_BYTES <= SM_M, "weight ring overlaps the encoding ring");
+  const uint32_t s_w = smem_u32(smem + RING_OFF);
   const uint32_t s_m = smem_u32(smem + SM_M);
   const bool with_enc = (KIND == KIND_NORMALS) || p.want_area;
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < NUM_WSTAGES; ++i) {
+      for (int i = 0; i < MAX_WSTAGES; ++i) {
         mbar_init(&bars.w_full[i], 1);
         mbar_init(&bars.w_empty[i], 1);
       }
@@ -271,9 +277,9 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           mbar_arrive(&bars.w_full[stage]);   // timing experiment: no weight traffic
         } else {
           mbar_expect_tx(&bars.w_full[stage], bytes);
-          bulk_g2s(smem + SM_W + stage * W_STAGE_BYTES, p.wblob_t + off, bytes, &bars.w_full[stage]);
+          bulk_g2s(smem + RING_OFF + stage * W_STAGE_BYTES, p.wblob_t + off, bytes, &bars.w_full[stage]);
         }
-        if (++stage == NUM_WSTAGES) {
+        if (++stage == NWS) {
           stage = 0;
           phase ^= 1;
         }
@@ -334,7 +340,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
       };
       auto ring_release = [&]() {
         mma_commit(&bars.w_empty[stage]);
-        if (++stage == NUM_WSTAGES) {
+        if (++stage == NWS) {
           stage = 0;
           wphase ^= 1;
         }
