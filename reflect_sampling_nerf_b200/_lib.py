@@ -45,6 +45,7 @@ _SIGNATURES = {
     "rsn_reflect_compose_bwd": ([P, P, P, P, P, I64, P, P, P, P, P, I64, I64, P], c_int),
     "rsn_probe_umma_kmajor": ([P, P, I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_2cta": ([P, P, I64, I64, P, P], c_int),
+    "rsn_field_wgrad_finish": ([P, P, P, P, P], c_int),
     "rsn_probe_epilogue": ([I64, I64, I64, P, P], c_int),
     "rsn_probe_tmem_rate": ([I64, I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_ts": ([P, P, I64, I64, P, I64, P, P], c_int),

@@ -499,7 +499,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
             tc_fence_before();
             mbar_arrive(&bars.act_ready[g]);
           };
-          if (KIND == KIND_BACKWARD) {
+          if (KIND == KIND_BACKWARD && stash_blk) {
             dgrad_group<MASK, true, true>(acc_c, blk, mbits, row, a_t, early, guard_fn);
             if (!(p.debug & 1)) warp_store_rows(stash_blk, blk, q, lane);
           } else {
@@ -589,8 +589,9 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         buf ^= 1;
         // ---- E1: d bottleneck (no activation) -> dY_bott
         wait_acc();
-        for (int g = 0; g < 4; ++g)   // (guard: blocks 0/1 were handed to the TMA engine by E0, 2 groups ago)
-          convert(F_{}, g, make_uint2(0u, 0u), dblk(DY_BOTT + g), [&]() { warp_store_guard<1>(lane); });
+        // (dY_bott is not stashed: the wgrad derives the bottleneck layer's gradients from dY_mid and h7.  SS form: blocks
+        // 0/1 were handed to the TMA engine by E0 and this step commits no bulk groups of its own: drain)
+        for (int g = 0; g < 4; ++g) convert(F_{}, g, make_uint2(0u, 0u), nullptr, [&]() { warp_store_guard<0>(lane); });
         buf ^= 1;
       } else {
         // ---- NORMALS seed: dY_7 = w_density * (h7 > 0)
@@ -642,7 +643,11 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           mask_release();
         }
         for (int g = 0; g < 4; ++g)   // output = dY_{l-1}: stash block DY_H + 4 (l-1) + g
-          convert(T_{}, g, mk[g], (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr, guard);
+          convert(T_{}, g, mk[g], (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr, [&]() {
+            // l == 8 (BACKWARD): the previous commits of this warp are seed, E0 g0, E0 g1 (E1 stores nothing), so block
+            // g < 2 was handed over at most 2 groups ago
+            if (KIND == KIND_BACKWARD && l == 8) warp_store_guard<1>(lane); else guard();
+          });
         buf ^= 1;
       }
       if (with_enc) {

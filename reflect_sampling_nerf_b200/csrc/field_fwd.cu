@@ -78,7 +78,7 @@ struct FwdParams {
   float* feat;              // [P][16]
   uint8_t* stash;           // training: [n_tiles][STASH_BLOCKS][16 KB] activation block images, or NULL
   float* aux;               // training: [P][8] = mid rgb (3), raw normal head (3), 2 spare, or NULL
-  int debug;                // RSN_FWD_DEBUG (timing experiments only): 2 = no trig in the prologue, 4 = no weight streaming
+  int debug;                // RSN_FWD_DEBUG (timing experiments only): 2 = no trig in the prologue, 4 = no weight streaming, 8 = no stash bulk stores (TS form)
 };
 
 constexpr int MAX_STAGES = 6;
@@ -722,11 +722,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         const uint32_t acc_c = tlane + (uint32_t)buf * 256 + g * 64, a_t = tlane + (uint32_t)buf * 256 + g * 32;
         const uint32_t blk = s_act + g * BLOCK_BYTES;
         auto guard_g = [&]() {
-          if (st) {
-            if (first) warp_store_guard<1>(lane); else warp_store_guard<3>(lane);
+          if (st) {   // (a group that is not stashed commits no bulk group: drain instead of counting)
+            if (!stash_blk) warp_store_guard<0>(lane); else if (first) warp_store_guard<1>(lane); else warp_store_guard<3>(lane);
           }
         };
-        if (TS && st) {
+        if (TS && st && stash_blk) {
           if constexpr (TS) {
             epilogue_group<RELU, MASKS, SBIAS, true, true, true>(
                 acc_c, bias_off + g * 64, blk, row, sb + g * 256, mask_ptr, a_t,
@@ -736,11 +736,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
                   arrive_issuer(&bars.act_ready[g]);
                 },
                 guard_g);
-            warp_store_rows(stash_blk, blk, q, lane);
+            if (!(p.debug & 8)) warp_store_rows(stash_blk, blk, q, lane);   // 8: timing experiment without the stash stores
           }
         } else {
-          guard_g();
-          if (st) epilogue_group<RELU, MASKS, SBIAS, TS, true>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, mask_ptr, a_t);
+          if (!TS) guard_g();
+          if (st && stash_blk) epilogue_group<RELU, MASKS, SBIAS, TS, true>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, mask_ptr, a_t);
           else epilogue_group<RELU, false, SBIAS, TS, !TS>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, nullptr, a_t);
           publish(&bars.act_ready[g], blk, stash_blk);
         }
@@ -760,7 +760,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       {
         wait_acc();
         const uint32_t sb = bias_slot();
-        for (int g = 0; g < 4; ++g) convert(F_{}, F_{}, BIAS_BOTT, sb, g, nullptr, sblk(STASH_BOTT + g), false);
+        // (not stashed: the wgrad derives everything that involves the bottleneck from h7, csrc/field_wgrad.cu)
+        for (int g = 0; g < 4; ++g) convert(F_{}, F_{}, BIAS_BOTT, sb, g, nullptr, nullptr, false);
         uint32_t hv[16];
         tmem_ld16(tlane + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, hv);
         float hb[16];

@@ -13,8 +13,15 @@
 // tiles (split-K over points); its accumulators stay in TMEM for the whole range and are flushed once with
 // fp32 atomics.  db comes from the same shared-memory dY slabs, summed by the otherwise idle epilogue warps.
 //
-// HBM-bound: algorithmic bytes = (m_blocks + n_blocks) * 16 KB per tile and job; 95 blocks = 1.52 MB per tile
-// over the 12 jobs (11.9 KB per point) against 2 * 618k * 128 = 158 MFLOP per tile.
+// HBM-bound: algorithmic bytes = (m_blocks + n_blocks) * 16 KB per tile and job; 87 block reads = 1.39 MB per tile
+// over the 13 active jobs (10.9 KB per point) against 2 * 618k * 128 = 158 MFLOP per tile.
+//
+// The bottleneck layer is linear in h7 (bott = h7 Wb^T + bb, no activation) and feeds only the mid layer, so neither the
+// bottleneck activations nor their gradients are stashed: with G = dY_mid^T h7 (job 12) and db_mid,
+//   dW_mid[:, bott part] = dY_mid^T bott     = G Wb^T + db_mid bb^T
+//   dW_bott              = (dY_mid Wmb)^T h7 = Wmb^T G            db_bott = Wmb^T db_mid
+// (rsn_field_wgrad_finish, once per step on the accumulated -- and all-reduced -- blob): 8 of 95 block reads and 8 of 80
+// stash blocks per tile disappear from the wgrad, the training forward and the backward chain.
 #include "field_wgrad_body.cuh"
 
 
@@ -36,6 +43,64 @@ extern "C" int rsn_field_wgrad_layout(int64_t* host_offsets, int64_t* host_shape
   }
   if (total_floats) *total_floats = off;
   return kNumJobs;
+}
+
+namespace {
+constexpr int MID_IN = 290, MID_IDE = 34;   // mlp_mid.layers.0.weight is [128][34 IDE + 256 bottleneck]
+// region 9 (dW_bott [256][256], db_bott [256]) from G (region 12 dW [128][256]) and db_mid: block j, thread k
+__global__ void __launch_bounds__(256) wgrad_finish_bott_kernel(const float* __restrict__ G, const float* __restrict__ db_mid,
+                                                                const float* __restrict__ w_mid, float* __restrict__ dw_bott,
+                                                                float* __restrict__ db_bott) {
+  __shared__ float wcol[128];   // Wmb[:, j]
+  const int j = blockIdx.x, k = threadIdx.x;
+  if (k < 128) wcol[k] = w_mid[k * MID_IN + MID_IDE + j];
+  __syncthreads();
+  float acc = 0.f;
+#pragma unroll 8
+  for (int m = 0; m < 128; ++m) acc = fmaf(wcol[m], G[m * 256 + k], acc);
+  dw_bott[j * 256 + k] = acc;
+  if (k == 0) {
+    float b = 0.f;
+    for (int m = 0; m < 128; ++m) b = fmaf(wcol[m], db_mid[m], b);
+    db_bott[j] = b;
+  }
+}
+// region 12 in place: row m of G -> row m of dW_mid[:, bott part] = G[m, :] Wb^T + db_mid[m] bb: block m, thread j
+__global__ void __launch_bounds__(256) wgrad_finish_mid_kernel(float* __restrict__ G, const float* __restrict__ db_mid,
+                                                               const float* __restrict__ w_bott, const float* __restrict__ b_bott) {
+  __shared__ float4 grow[64];
+  const int m = blockIdx.x, j = threadIdx.x;
+  if (j < 64) grow[j] = reinterpret_cast<const float4*>(G + m * 256)[j];
+  __syncthreads();
+  const float4* w = reinterpret_cast<const float4*>(w_bott + j * 256);
+  float acc = db_mid[m] * b_bott[j];
+#pragma unroll 8
+  for (int k = 0; k < 64; ++k) {
+    const float4 a = grow[k], b = __ldg(w + k);
+    acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+  }
+  __syncthreads();   // every thread has read the row before anyone overwrites it
+  G[m * 256 + j] = acc;
+}
+}  // namespace
+
+// Completes the gradient blob after the last rsn_field_wgrad of a step (and after the all-reduce): fills the bottleneck
+// layer's region and turns G into the bottleneck columns of the mid layer's weight gradient (see the header comment).
+// w_bott [256][256], b_bott [256], w_mid [128][290]: the fp32 parameters (device).
+extern "C" int rsn_field_wgrad_finish(float* grad_blob, const float* w_bott, const float* b_bott, const float* w_mid,
+                                      cudaStream_t stream) {
+  RSN_ARG(grad_blob && w_bott && b_bott && w_mid, "rsn_field_wgrad_finish: null pointer");
+  RSN_ARG(((uintptr_t)grad_blob & 15) == 0 && ((uintptr_t)w_bott & 15) == 0, "rsn_field_wgrad_finish: 16-byte alignment");
+  int64_t offs[2 * MAX_JOBS], total = 0;
+  rsn_field_wgrad_layout(offs, nullptr, &total);
+  float* G = grad_blob + offs[2 * 12];
+  const float* db_mid = grad_blob + offs[2 * 12 + 1];
+  RSN_ARG((offs[2 * 12] & 3) == 0, "rsn_field_wgrad_finish: region 12 is not 16-byte aligned");
+  wgrad_finish_bott_kernel<<<256, 256, 0, stream>>>(G, db_mid, w_mid, grad_blob + offs[2 * 9], grad_blob + offs[2 * 9 + 1]);
+  RSN_LAUNCH_CHECK("wgrad_finish_bott_kernel");
+  wgrad_finish_mid_kernel<<<128, 256, 0, stream>>>(G, db_mid, w_bott, b_bott);
+  RSN_LAUNCH_CHECK("wgrad_finish_mid_kernel");
+  return 0;
 }
 
 extern "C" int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_t n_points, float* grad_blob,

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
 // The 12 jobs of one pass.  Gradient blob regions (fp32): dW [64 m_blocks][64 n_blocks] row-major, then db.
 struct JobSpec {
   int a_blk, m_blocks, b_blk, n_blocks, has_db;
+  int active = 1;   // 0: the region is part of the blob but filled by rsn_field_wgrad_finish, not by the kernel
 };
 const JobSpec kJobs[] = {
     {DY_H + 0, 4, STASH_ENC, 2, 1},             //  0  layer 0            x enc
@@ -246,10 +247,10 @@ const JobSpec kJobs[] = {
     {DY_H + 20, 4, STASH_H + 16, 4, 1},         //  6  layer 5            x h4
     {DY_H + 24, 4, STASH_H + 20, 4, 1},         //  7  layer 6            x h5
     {DY_H + 28, 4, STASH_H + 24, 4, 1},         //  8  layer 7            x h6
-    {DY_BOTT, 4, STASH_H + 28, 4, 1},           //  9  bottleneck         x h7
+    {DY_BOTT, 4, STASH_H + 28, 4, 1, 0},        //  9  bottleneck         x h7: derived from job 12 (rsn_field_wgrad_finish)
     {DY_SEED, 2, STASH_H + 28, 4, 1},           // 10  heads (rows 16-31) x h7   (rows 0-15: unused product)
     {DY_SEED, 2, STASH_MIDH, 2, 0},             // 11  rgb (rows 0-15)    x mid hidden (db from job 10's sums)
-    {DY_MID, 2, STASH_BOTT, 4, 1},              // 12  mid                x bottleneck
+    {DY_MID, 2, STASH_H + 28, 4, 1},            // 12  G = dY_mid^T h7 (the bottleneck is linear in h7: see the finish kernel)
     {DY_MID, 2, STASH_IDE, 1, 0},               // 13  mid (IDE part)     x IDE
 };
 constexpr int kNumJobs = sizeof(kJobs) / sizeof(kJobs[0]);
@@ -266,18 +267,19 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
   p.n_jobs = kNumJobs;
   p.debug = getenv("RSN_WGRAD_DEBUG") ? atoi(getenv("RSN_WGRAD_DEBUG")) : 0;
   int units = 0, n_of[kNumJobs], used = 0;
-  for (int j = 0; j < kNumJobs; ++j) units += kJobs[j].m_blocks + kJobs[j].n_blocks;
+  for (int j = 0; j < kNumJobs; ++j) units += kJobs[j].active * (kJobs[j].m_blocks + kJobs[j].n_blocks);
   // CTAs per job proportional to the job's bytes per tile; the kernel ends with the job whose CTAs carry the most
   // bytes each, so the CTAs left over by the rounding go, one at a time, to the job with the largest bytes / CTA
   for (int j = 0; j < kNumJobs; ++j) {
     const int u = kJobs[j].m_blocks + kJobs[j].n_blocks;
-    n_of[j] = std::min(std::max(1, (u * cta_budget) / units), p.n_tiles);
+    n_of[j] = kJobs[j].active ? std::min(std::max(1, (u * cta_budget) / units), p.n_tiles) : 0;
     used += n_of[j];
   }
   while (used < cta_budget) {
     int best = -1;
     double worst = 0.0;
     for (int j = 0; j < kNumJobs; ++j) {
+      if (!kJobs[j].active) continue;
       const double load = (double)(kJobs[j].m_blocks + kJobs[j].n_blocks) / n_of[j];
       if (n_of[j] < p.n_tiles && load > worst) worst = load, best = j;
     }

@@ -21,16 +21,16 @@ FLOP_PER_POINT = {0: 1230592, 1: 1225472}   # SURVEY.md §8d (forward; primary f
 # algorithmic (FLOPs, HBM bytes) per point of the four field kernels
 KERNEL_WORK = {
     "field_fwd_kernel": (1230592, 68),
-    "field_fwd_kernel[train]": (1230592, 68 + 32 + 41 * 128 + 288),
+    "field_fwd_kernel[train]": (1230592, 68 + 32 + 37 * 128 + 288),      # 41 stash blocks, the 4 bottleneck ones not written
     "field_chain_kernel<normals>": (1019392, 288 + 4 * 128 + 12),
-    "field_chain_kernel<backward>": (1179904, 288 + 39 * 128 + 160),
-    "field_chain_kernel<backward+area>": (1229056, 288 + 4 * 128 + 39 * 128 + 164),
-    # every stash block once: 41 activation + 39 dY blocks of 128 B per point (the 14 jobs read 95 blocks per tile; the 15
-    # second reads are served by L2 when the jobs stream the same tiles together)
-    "field_wgrad_kernel": (1230592, 80 * 128),
+    "field_chain_kernel<backward>": (1179904, 288 + 35 * 128 + 160),         # 39 dY blocks, the 4 of dY_bott not written
+    "field_chain_kernel<backward+area>": (1229056, 288 + 4 * 128 + 35 * 128 + 164),
+    # every stash block that exists once: 37 activation + 35 dY blocks of 128 B per point (the 13 active jobs issue 87 block
+    # reads per tile: 15 operands are read by two jobs)
+    "field_wgrad_kernel": (1230592, 72 * 128),
     # fused backward: dgrad + wgrad FLOPs; HBM: masks + dY written once + X read (dY read back from L2)
-    "field_bwd_fused_kernel": (1179904 + 1230592, 288 + 39 * 128 + 160 + 56 * 128),
-    "field_bwd_fused_kernel+area": (1229056 + 1230592, 288 + 4 * 128 + 39 * 128 + 164 + 56 * 128),
+    "field_bwd_fused_kernel": (1179904 + 1230592, 288 + 35 * 128 + 160 + 52 * 128),
+    "field_bwd_fused_kernel+area": (1229056 + 1230592, 288 + 4 * 128 + 35 * 128 + 164 + 52 * 128),
     # K8 at C = 16 channels, per SAMPLE: sigma 4 + bin 4 + feat 64 in, weight 4 out | + dL/dw 4 in, dL/dsigma 4 + dL/dfeat 64 out
     "composite_fwd_kernel": (0, 76),
     "composite_bwd_kernel": (0, 144),
@@ -335,6 +335,23 @@ def field_wgrad(stash: Tensor, dy_stash: Tensor, n_points: int, grad_blob: Tenso
     """K5 wgrad: accumulates dW / db of every Linear over the pass into grad_blob (fp32, wgrad_layout())."""
     with _Prof("field_wgrad_kernel", n_points):
         _lib.call("rsn_field_wgrad", _lib.ptr(stash), _lib.ptr(dy_stash), n_points, _lib.ptr(grad_blob), _lib.stream())
+
+
+def wgrad_finish(grad_blob: Tensor, w_bott: Tensor, b_bott: Tensor, w_mid: Tensor) -> None:
+    """Once per step, after the last field_wgrad (and the all-reduce): derive the bottleneck layer's gradients and the
+    bottleneck columns of d mlp_mid.layers.0.weight from G = dY_mid^T h7 (include/rsn_b200.h: rsn_field_wgrad_finish).
+    CPU tensors (the gloo test of the flush path) take the same algebra through torch."""
+    if grad_blob.is_cuda:
+        _lib.call("rsn_field_wgrad_finish", _lib.ptr(grad_blob), _lib.ptr(_f32c(w_bott.detach())),
+                  _lib.ptr(_f32c(b_bott.detach())), _lib.ptr(_f32c(w_mid.detach())), _lib.stream())
+        return
+    offs, shapes, _ = wgrad_layout()
+    g = grad_blob[offs[24]: offs[24] + 128 * 256].view(128, 256).clone()
+    db_mid = grad_blob[offs[25]: offs[25] + 128]
+    w_mb = w_mid.detach()[:, 34:]
+    grad_blob[offs[18]: offs[18] + 256 * 256] = (w_mb.T @ g).reshape(-1)
+    grad_blob[offs[19]: offs[19] + 256] = w_mb.T @ db_mid
+    grad_blob[offs[24]: offs[24] + 128 * 256] = (g @ w_bott.detach().T + torch.outer(db_mid, b_bott.detach())).reshape(-1)
 
 
 PACK_ORDER = ([f"mlp_base.layers.{l}.weight" for l in range(8)] + [f"mlp_base.layers.{l}.bias" for l in range(8)]

@@ -31,6 +31,9 @@ def _flush_grads(field) -> None:
         dist.all_reduce(blob, op=dist.ReduceOp.SUM)
         blob.mul_(1.0 / field.dp_world_size)          # DDP averages (pipeline.py:75)
     params = dict(field.named_parameters())
+    # bottleneck layer: its gradients come from G = dY_mid^T h7 (linear in the blob, so after the all-reduce)
+    ops.wgrad_finish(blob, params["field_output_bottleneck.net.weight"], params["field_output_bottleneck.net.bias"],
+                     params["mlp_mid.layers.0.weight"])
     if blob.is_cuda:
         # one kernel: blob -> flat gradient vector; the parameters' .grad are views of it
         offs, total = ops.flat_layout()

@@ -51,14 +51,14 @@ def fwd():
 
 
 timeit(lambda: ops.field_forward(wblob, bias, o, d, pa, bins), P * 1230592, P * 68, "field_fwd (inference)")
-timeit(fwd, P * 1230592, P * (68 + 32 + 41 * 128 + 288), "field_fwd (train, stash)")
+timeit(fwd, P * 1230592, P * (68 + 32 + 37 * 128 + 288), "field_fwd (train, stash)")
 sigma, feat, stash, aux = out["f"]
 timeit(lambda: ops.field_normals(wblob_t, wd, stash, n, s), P * 1019392, P * (288 + 4 * 128 + 12), "field_chain<normals>")
 timeit(lambda: ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, False),
-       P * 1179904, P * (288 + 39 * 128 + 160), "field_chain<backward>")
+       P * 1179904, P * (288 + 35 * 128 + 160), "field_chain<backward>")
 timeit(lambda: ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, True),
-       P * 1229056, P * (288 + 4 * 128 + 39 * 128 + 164), "field_chain<backward+area>")
-timeit(lambda: ops.field_wgrad(stash, dy, P, blob), P * 1230592, P * 80 * 128, "field_wgrad")
+       P * 1229056, P * (288 + 4 * 128 + 35 * 128 + 164), "field_chain<backward+area>")
+timeit(lambda: ops.field_wgrad(stash, dy, P, blob), P * 1230592, P * 72 * 128, "field_wgrad")
 blob2 = torch.zeros(ops.wgrad_layout()[2], device="cuda")
 timeit(lambda: ops.field_backward_fused(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, False, blob2),
-       P * (1179904 + 1230592), P * (288 + 39 * 128 + 160 + 56 * 128), "field_bwd_fused (chain+wgrad)")
+       P * (1179904 + 1230592), P * (288 + 35 * 128 + 160 + 52 * 128), "field_bwd_fused (chain+wgrad)")

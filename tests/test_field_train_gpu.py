@@ -62,6 +62,8 @@ def _run_mine(field, mode, o, d, pa, bins, g_sigma, g_feat, want_area):
     offs, shapes, total = ops.wgrad_layout()
     blob = torch.zeros(total, device="cuda")
     ops.field_wgrad(stash, dy, n * s, blob)
+    ops.wgrad_finish(blob, sd["field_output_bottleneck.net.weight"].cuda(), sd["field_output_bottleneck.net.bias"].cuda(),
+                     sd["mlp_mid.layers.0.weight"].cuda())
     torch.cuda.synchronize()
     return sigma, feat, stash, (wblob_t, wd), packing.unpack_grads(blob, offs, shapes), g_area
 

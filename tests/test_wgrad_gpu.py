@@ -10,8 +10,9 @@ pytestmark = pytest.mark.gpu
 STASH_BLOCKS, DY_BLOCKS = 41, 39
 # (dY first block, m_blocks, X first block, n_blocks, has_db) -- csrc/field_wgrad.cu kJobs
 JOBS = [(7, 4, 0, 2, 1), (11, 4, 2, 4, 1), (15, 4, 6, 4, 1), (19, 4, 10, 4, 1), (23, 4, 0, 2, 0), (23, 4, 14, 4, 1),
-        (27, 4, 18, 4, 1), (31, 4, 22, 4, 1), (35, 4, 26, 4, 1), (3, 4, 30, 4, 1), (0, 2, 30, 4, 1), (0, 2, 39, 2, 0),
-        (1, 2, 34, 4, 1), (1, 2, 38, 1, 0)]
+        (27, 4, 18, 4, 1), (31, 4, 22, 4, 1), (35, 4, 26, 4, 1), None, (0, 2, 30, 4, 1), (0, 2, 39, 2, 0),
+        (1, 2, 30, 4, 1), (1, 2, 38, 1, 0)]
+# job 9 (bottleneck x h7) is not computed by the kernel: rsn_field_wgrad_finish derives it from job 12 = dY_mid^T h7
 
 
 @pytest.mark.parametrize("n_tiles", [1, 3, 40])
@@ -32,8 +33,12 @@ def test_wgrad_matches_matmul(n_tiles):
     torch.cuda.synchronize()
     blob = blob.cpu()
     xf, dyf = x.float(), dy.float()
-    for j, (a, mb, b, nb, has_db) in enumerate(JOBS):
+    for j, job in enumerate(JOBS):
         m, n = shapes[j]
+        if job is None:
+            assert (m, n) == (256, 256) and not blob[offs[2 * j]: offs[2 * j] + m * n + m].any()
+            continue
+        a, mb, b, nb, has_db = job
         assert (m, n) == (mb * 64, nb * 64)
         ref = dyf[:, a * 64:(a + mb) * 64].T @ xf[:, b * 64:(b + nb) * 64]
         got = blob[offs[2 * j]: offs[2 * j] + m * n].view(m, n)
@@ -44,3 +49,28 @@ def test_wgrad_matches_matmul(n_tiles):
             torch.testing.assert_close(gotb, refb, rtol=2e-3, atol=2e-3 * float(refb.abs().max()))
         else:
             assert offs[2 * j + 1] == -1
+
+
+def test_wgrad_finish_derives_the_bottleneck_gradients():
+    """rsn_field_wgrad_finish on a random blob against the algebra it implements (and its host mirror in ops)."""
+    g = torch.Generator().manual_seed(3)
+    offs, shapes, total = ops.wgrad_layout()
+    blob = torch.randn(total, generator=g)
+    w_b, b_b, w_m = torch.randn(256, 256, generator=g), torch.randn(256, generator=g), torch.randn(128, 290, generator=g)
+    G = blob[offs[24]: offs[24] + 128 * 256].view(128, 256).double()
+    dbm = blob[offs[25]: offs[25] + 128].double()
+    ref9 = w_m[:, 34:].double().T @ G
+    ref9b = w_m[:, 34:].double().T @ dbm
+    ref12 = G @ w_b.double().T + torch.outer(dbm, b_b.double())
+    host, dev = blob.clone(), blob.clone().cuda()
+    ops.wgrad_finish(host, w_b, b_b, w_m)
+    ops.wgrad_finish(dev, w_b.cuda(), b_b.cuda(), w_m.cuda())
+    torch.cuda.synchronize()
+    for got in (host, dev.cpu()):
+        torch.testing.assert_close(got[offs[18]: offs[18] + 65536].view(256, 256).double(), ref9, rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(got[offs[19]: offs[19] + 256].double(), ref9b, rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(got[offs[24]: offs[24] + 32768].view(128, 256).double(), ref12, rtol=1e-4, atol=1e-3)
+        untouched = torch.ones(total, dtype=torch.bool)
+        untouched[offs[18]: offs[19] + 256] = False
+        untouched[offs[24]: offs[24] + 32768] = False
+        assert torch.equal(got[untouched], blob[untouched])
