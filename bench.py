@@ -242,10 +242,10 @@ def run_b200(args):
         src = "MEASURED_PEAKS.json (bf16_tflops_sustained: kernels timed inside a long step; hbm_gbs)" if peaks \
             else "B200_PROFILING.md fallback"
         # ncu --set full dram__bytes_read + dram__bytes_write per launch of a C2 primary pass (2.1 M points;
-        # profiles/r01_field_all_v4_ncu.txt)
-        ncu_traffic = {"field_fwd_kernel": 0.0946e9, "field_fwd_kernel[train]": 11.83e9,
-                       "field_chain_kernel<normals>": 1.10e9, "field_chain_kernel<backward>": 11.44e9,
-                       "field_wgrad_kernel": 24.54e9}
+        # profiles/r01_field_all_v5_ncu.txt)
+        ncu_traffic = {"field_fwd_kernel": 0.0988e9, "field_fwd_kernel[train]": 10.74e9,
+                       "field_chain_kernel<normals>": 1.10e9, "field_chain_kernel<backward>": 10.26e9,
+                       "field_wgrad_kernel": 20.72e9}
         by = {}
         for (name, a, b, flop, nbytes) in prof:
             d = by.setdefault(name, [0.0, 0.0, 0.0, 0])
