@@ -185,3 +185,25 @@ def test_chain_tmem_operand_form_is_bit_identical(monkeypatch, want_area):
     assert torch.equal(out["1"][1], out["0"][1])
     if want_area:
         assert torch.equal(out["1"][2], out["0"][2])
+
+
+def test_field_kernels_accept_empty_batches():
+    """Zero rays (e.g. no pixel of a batch takes the reflected branch): every field entry point is a no-op that
+    returns empty tensors and leaves the gradient blob untouched."""
+    sd = R.OracleField().state_dict()
+    wblob, bias = [t.cuda() for t in packing.pack_field(sd)]
+    wblob_t, wd = [t.cuda() for t in packing.pack_field_t(sd)]
+    z3, z1, zb = torch.zeros(0, 3, device="cuda"), torch.zeros(0, device="cuda"), torch.zeros(0, 9, device="cuda")
+    sigma, feat = ops.field_forward(wblob, bias, z3, z3, z1, zb)
+    assert sigma.shape == (0, 8) and feat.shape == (0, 8, 16)
+    sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, 0, z3, z3, z1, zb)
+    assert stash.numel() == 0 and aux.shape == (0, 8, 8)
+    assert ops.field_normals(wblob_t, wd, stash, 0, 8).shape == (0, 8, 3)
+    dy = torch.zeros(0, dtype=torch.uint8, device="cuda")
+    g_area = ops.field_backward(wblob_t, stash, 0, z3, z3, z1, zb, 0, 8, sigma, feat, feat, aux, dy, True)
+    assert g_area.shape == (0, 8)
+    blob = torch.ones(ops.wgrad_layout()[2], device="cuda")
+    ops.field_wgrad(stash, dy, 0, blob)
+    torch.cuda.synchronize()
+    assert bool((blob == 1).all())
+    assert ops.field_inf_color(wblob, bias, z3, torch.zeros(0, 1, device="cuda")).shape == (0, 3)
