@@ -150,3 +150,24 @@ def test_model_contract_without_gpu():
     m.field = None
     with pytest.raises(ValueError):
         m.get_param_groups()
+
+
+def test_wgrad_finish_host_mirror_matches_the_algebra():
+    """ops.wgrad_finish on a CPU blob (the path the gloo flush test takes): dW_bott = Wmb^T G, db_bott = Wmb^T db_mid,
+    dW_mid[:, bott] = G Wb^T + db_mid bb^T with G = job 12's region; everything else untouched."""
+    g = torch.Generator().manual_seed(5)
+    offs, shapes, total = ops.wgrad_layout()
+    assert shapes[9] == (256, 256) and shapes[12] == (128, 256)
+    blob = torch.randn(total, generator=g)
+    w_b, b_b, w_m = torch.randn(256, 256, generator=g), torch.randn(256, generator=g), torch.randn(128, 290, generator=g)
+    G = blob[offs[24]: offs[24] + 32768].view(128, 256).clone()
+    dbm = blob[offs[25]: offs[25] + 128].clone()
+    out = blob.clone()
+    ops.wgrad_finish(out, w_b, b_b, w_m)
+    torch.testing.assert_close(out[offs[18]: offs[18] + 65536].view(256, 256), w_m[:, 34:].T @ G)
+    torch.testing.assert_close(out[offs[19]: offs[19] + 256], w_m[:, 34:].T @ dbm)
+    torch.testing.assert_close(out[offs[24]: offs[24] + 32768].view(128, 256), G @ w_b.T + torch.outer(dbm, b_b))
+    keep = torch.ones(total, dtype=torch.bool)
+    keep[offs[18]: offs[19] + 256] = False
+    keep[offs[24]: offs[24] + 32768] = False
+    assert torch.equal(out[keep], blob[keep])
