@@ -13,11 +13,12 @@
 // tiles (split-K over points); its accumulators stay in TMEM for the whole range and are flushed once with
 // fp32 atomics.  db comes from the same shared-memory dY slabs, summed by the otherwise idle epilogue warps.
 //
-// HBM-bound: algorithmic bytes = (m_blocks + n_blocks) * 16 KB per tile and job; 87 block reads = 1.39 MB per tile
-// over the 13 active jobs (10.9 KB per point) against 2 * 618k * 128 = 158 MFLOP per tile.
+// HBM-bound: algorithmic bytes = (loaded dY blocks + n_blocks) * 16 KB per tile and job; 82 block reads = 1.31 MB per tile
+// over the 12 active jobs (10.25 KB per point) against 2 * 618k * 128 = 158 MFLOP per tile.
 //
 // The bottleneck layer is linear in h7 (bott = h7 Wb^T + bb, no activation) and feeds only the mid layer, so neither the
-// bottleneck activations nor their gradients are stashed: with G = dY_mid^T h7 (job 12) and db_mid,
+// bottleneck activations nor their gradients are stashed: with G = dY_mid^T h7 (rows 64-191 of job 10, which multiplies
+// [seed | dY_mid] with h7 in one pass) and db_mid,
 //   dW_mid[:, bott part] = dY_mid^T bott     = G Wb^T + db_mid bb^T
 //   dW_bott              = (dY_mid Wmb)^T h7 = Wmb^T G            db_bott = Wmb^T db_mid
 // (rsn_field_wgrad_finish, once per step on the accumulated -- and all-reduced -- blob): 8 of 95 block reads and 8 of 80
@@ -65,9 +66,10 @@ __global__ void __launch_bounds__(256) wgrad_finish_bott_kernel(const float* __r
     db_bott[j] = b;
   }
 }
-// region 12 in place: row m of G -> row m of dW_mid[:, bott part] = G[m, :] Wb^T + db_mid[m] bb: block m, thread j
-__global__ void __launch_bounds__(256) wgrad_finish_mid_kernel(float* __restrict__ G, const float* __restrict__ db_mid,
-                                                               const float* __restrict__ w_bott, const float* __restrict__ b_bott) {
+// region 12: row m of dW_mid[:, bott part] = G[m, :] Wb^T + db_mid[m] bb, and db_mid itself: block m, thread j
+__global__ void __launch_bounds__(256) wgrad_finish_mid_kernel(const float* __restrict__ G, const float* __restrict__ db_mid,
+                                                               const float* __restrict__ w_bott, const float* __restrict__ b_bott,
+                                                               float* __restrict__ dw_mid_bott, float* __restrict__ db_mid_out) {
   __shared__ float4 grow[64];
   const int m = blockIdx.x, j = threadIdx.x;
   if (j < 64) grow[j] = reinterpret_cast<const float4*>(G + m * 256)[j];
@@ -79,8 +81,8 @@ __global__ void __launch_bounds__(256) wgrad_finish_mid_kernel(float* __restrict
     const float4 a = grow[k], b = __ldg(w + k);
     acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
   }
-  __syncthreads();   // every thread has read the row before anyone overwrites it
-  G[m * 256 + j] = acc;
+  dw_mid_bott[m * 256 + j] = acc;
+  if (j == 0) db_mid_out[m] = db_mid[m];
 }
 }  // namespace
 
@@ -93,12 +95,13 @@ extern "C" int rsn_field_wgrad_finish(float* grad_blob, const float* w_bott, con
   RSN_ARG(((uintptr_t)grad_blob & 15) == 0 && ((uintptr_t)w_bott & 15) == 0, "rsn_field_wgrad_finish: 16-byte alignment");
   int64_t offs[2 * MAX_JOBS], total = 0;
   rsn_field_wgrad_layout(offs, nullptr, &total);
-  float* G = grad_blob + offs[2 * 12];
-  const float* db_mid = grad_blob + offs[2 * 12 + 1];
-  RSN_ARG((offs[2 * 12] & 3) == 0, "rsn_field_wgrad_finish: region 12 is not 16-byte aligned");
+  const float* G = grad_blob + offs[2 * 10] + 64 * 256;          // rows 64-191 of job 10's [256][256] region
+  const float* db_mid = grad_blob + offs[2 * 10 + 1] + 64;
+  RSN_ARG((offs[2 * 10] & 3) == 0, "rsn_field_wgrad_finish: region 10 is not 16-byte aligned");
   wgrad_finish_bott_kernel<<<256, 256, 0, stream>>>(G, db_mid, w_mid, grad_blob + offs[2 * 9], grad_blob + offs[2 * 9 + 1]);
   RSN_LAUNCH_CHECK("wgrad_finish_bott_kernel");
-  wgrad_finish_mid_kernel<<<128, 256, 0, stream>>>(G, db_mid, w_bott, b_bott);
+  wgrad_finish_mid_kernel<<<128, 256, 0, stream>>>(G, db_mid, w_bott, b_bott, grad_blob + offs[2 * 12],
+                                                   grad_blob + offs[2 * 12 + 1]);
   RSN_LAUNCH_CHECK("wgrad_finish_mid_kernel");
   return 0;
 }

@@ -29,6 +29,7 @@ constexpr int MAX_JOBS = 16;
 
 struct WJob {
   int a_blk, m_blocks;   // first dY block of the job inside a dY tile; 2 (M=128) or 4 (M=256)
+  int a_load;            // dY blocks actually loaded (m_blocks, or 3: the MMA's fourth A block is then the first X block)
   int b_blk, n_blocks;   // first X block inside a stash tile; 1, 2 or 4 (N = 64, 128, 256)
   int out_off, db_off;   // float offsets into the gradient blob: dW [64 m_blocks][64 n_blocks], db or -1
   int cta_begin, n_ctas;
@@ -67,7 +68,10 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
   const int t0 = interleave ? split : (int)(((int64_t)p.n_tiles * split) / job.n_ctas);
   const int t1 = interleave ? p.n_tiles : (int)(((int64_t)p.n_tiles * (split + 1)) / job.n_ctas);
   const int tstep = interleave ? job.n_ctas : 1;
-  const int mb = job.m_blocks, nb = job.n_blocks;
+  // mb = dY blocks loaded per slab; m_out = 64-row blocks of the accumulator (2 or 4).  mb = 3, m_out = 4: the second M=128
+  // MMA reads blocks 2 and "3" = the first X block, which sits right behind the dY blocks in the stage -- its 64 output rows
+  // are a finite by-product nobody reads, and no fourth dY block has to be fetched
+  const int mb = job.a_load, m_out = job.m_blocks, nb = job.n_blocks;
   // a job with fewer blocks per slab gets more stages: the same bytes in flight for every CTA
   const int SLAB_BYTES = (mb + nb) * SLAB_BLOCK_BYTES;
   const int W_STAGES = min(MAX_W_STAGES, RING_BYTES / SLAB_BYTES);
@@ -144,7 +148,7 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
 #pragma unroll
           for (int ks = 0; ks < SLAB_ROWS / 16; ++ks)
             mma_bf16_ss_lo(tmem, a_lo + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
-          if (mb == 4) {
+          if (m_out == 4) {
 #pragma unroll
             for (int ks = 0; ks < SLAB_ROWS / 16; ++ks)
               mma_bf16_ss_lo(tmem + 256, a_lo + (2 * SLAB_BLOCK_BYTES >> 4) + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
@@ -208,7 +212,7 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
       const int q = warp & 3;
       const int row = q * 32 + lane;
       const int N = nb * 64;
-      for (int h = 0; h < ((p.debug & 4) ? 0 : mb / 2); ++h) {
+      for (int h = 0; h < ((p.debug & 4) ? 0 : m_out / 2); ++h) {
         float* out = p.grad + job.out_off + (size_t)(h * 128 + row) * N;
         for (int c0 = 0; c0 < N; c0 += 32) {
           uint32_t v[32];
@@ -236,6 +240,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_
 struct JobSpec {
   int a_blk, m_blocks, b_blk, n_blocks, has_db;
   int active = 1;   // 0: the region is part of the blob but filled by rsn_field_wgrad_finish, not by the kernel
+  int a_load = 0;   // dY blocks to load if fewer than m_blocks (see wgrad_body); 0 = m_blocks
 };
 const JobSpec kJobs[] = {
     {DY_H + 0, 4, STASH_ENC, 2, 1},             //  0  layer 0            x enc
@@ -248,9 +253,9 @@ const JobSpec kJobs[] = {
     {DY_H + 24, 4, STASH_H + 20, 4, 1},         //  7  layer 6            x h5
     {DY_H + 28, 4, STASH_H + 24, 4, 1},         //  8  layer 7            x h6
     {DY_BOTT, 4, STASH_H + 28, 4, 1, 0},        //  9  bottleneck         x h7: derived from job 12 (rsn_field_wgrad_finish)
-    {DY_SEED, 2, STASH_H + 28, 4, 1},           // 10  heads (rows 16-31) x h7   (rows 0-15: unused product)
+    {DY_SEED, 4, STASH_H + 28, 4, 1, 1, 3},     // 10  [seed | dY_mid] x h7: rows 16-31 heads, rows 64-191 G = dY_mid^T h7
     {DY_SEED, 2, STASH_MIDH, 2, 0},             // 11  rgb (rows 0-15)    x mid hidden (db from job 10's sums)
-    {DY_MID, 2, STASH_H + 28, 4, 1},            // 12  G = dY_mid^T h7 (the bottleneck is linear in h7: see the finish kernel)
+    {DY_MID, 2, STASH_BOTT, 4, 1, 0},           // 12  mid x bottleneck: derived from job 10's G (rsn_field_wgrad_finish)
     {DY_MID, 2, STASH_IDE, 1, 0},               // 13  mid (IDE part)     x IDE
 };
 constexpr int kNumJobs = sizeof(kJobs) / sizeof(kJobs[0]);
@@ -267,11 +272,11 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
   p.n_jobs = kNumJobs;
   p.debug = getenv("RSN_WGRAD_DEBUG") ? atoi(getenv("RSN_WGRAD_DEBUG")) : 0;
   int units = 0, n_of[kNumJobs], used = 0;
-  for (int j = 0; j < kNumJobs; ++j) units += kJobs[j].active * (kJobs[j].m_blocks + kJobs[j].n_blocks);
+  for (int j = 0; j < kNumJobs; ++j) units += kJobs[j].active * ((kJobs[j].a_load ? kJobs[j].a_load : kJobs[j].m_blocks) + kJobs[j].n_blocks);
   // CTAs per job proportional to the job's bytes per tile; the kernel ends with the job whose CTAs carry the most
   // bytes each, so the CTAs left over by the rounding go, one at a time, to the job with the largest bytes / CTA
   for (int j = 0; j < kNumJobs; ++j) {
-    const int u = kJobs[j].m_blocks + kJobs[j].n_blocks;
+    const int u = (kJobs[j].a_load ? kJobs[j].a_load : kJobs[j].m_blocks) + kJobs[j].n_blocks;
     n_of[j] = kJobs[j].active ? std::min(std::max(1, (u * cta_budget) / units), p.n_tiles) : 0;
     used += n_of[j];
   }
@@ -280,7 +285,7 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
     double worst = 0.0;
     for (int j = 0; j < kNumJobs; ++j) {
       if (!kJobs[j].active) continue;
-      const double load = (double)(kJobs[j].m_blocks + kJobs[j].n_blocks) / n_of[j];
+      const double load = (double)((kJobs[j].a_load ? kJobs[j].a_load : kJobs[j].m_blocks) + kJobs[j].n_blocks) / n_of[j];
       if (n_of[j] < p.n_tiles && load > worst) worst = load, best = j;
     }
     if (best < 0) break;
@@ -292,6 +297,7 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
   for (int j = 0; j < kNumJobs; ++j) {
     WJob& w = p.jobs[j];
     w.a_blk = kJobs[j].a_blk, w.m_blocks = kJobs[j].m_blocks, w.b_blk = kJobs[j].b_blk, w.n_blocks = kJobs[j].n_blocks;
+    w.a_load = kJobs[j].a_load ? kJobs[j].a_load : kJobs[j].m_blocks;
     w.out_off = (int)off;
     off += (int64_t)w.m_blocks * 64 * w.n_blocks * 64;
     w.db_off = kJobs[j].has_db ? (int)off : -1;

@@ -25,8 +25,8 @@ KERNEL_WORK = {
     "field_chain_kernel<normals>": (1019392, 288 + 4 * 128 + 12),
     "field_chain_kernel<backward>": (1179904, 288 + 35 * 128 + 160),         # 39 dY blocks, the 4 of dY_bott not written
     "field_chain_kernel<backward+area>": (1229056, 288 + 4 * 128 + 35 * 128 + 164),
-    # every stash block that exists once: 37 activation + 35 dY blocks of 128 B per point (the 13 active jobs issue 87 block
-    # reads per tile: 15 operands are read by two jobs)
+    # every stash block that exists once: 37 activation + 35 dY blocks of 128 B per point (the 12 active jobs issue 82 block
+    # reads per tile: 10 operands are read by two jobs)
     "field_wgrad_kernel": (1230592, 72 * 128),
     # fused backward: dgrad + wgrad FLOPs; HBM: masks + dY written once + X read (dY read back from L2)
     "field_bwd_fused_kernel": (1179904 + 1230592, 288 + 35 * 128 + 160 + 52 * 128),
@@ -346,12 +346,13 @@ def wgrad_finish(grad_blob: Tensor, w_bott: Tensor, b_bott: Tensor, w_mid: Tenso
                   _lib.ptr(_f32c(b_bott.detach())), _lib.ptr(_f32c(w_mid.detach())), _lib.stream())
         return
     offs, shapes, _ = wgrad_layout()
-    g = grad_blob[offs[24]: offs[24] + 128 * 256].view(128, 256).clone()
-    db_mid = grad_blob[offs[25]: offs[25] + 128]
+    g = grad_blob[offs[20] + 64 * 256: offs[20] + 192 * 256].view(128, 256)      # rows 64-191 of job 10's region
+    db_mid = grad_blob[offs[21] + 64: offs[21] + 192]
     w_mb = w_mid.detach()[:, 34:]
     grad_blob[offs[18]: offs[18] + 256 * 256] = (w_mb.T @ g).reshape(-1)
     grad_blob[offs[19]: offs[19] + 256] = w_mb.T @ db_mid
     grad_blob[offs[24]: offs[24] + 128 * 256] = (g @ w_bott.detach().T + torch.outer(db_mid, b_bott.detach())).reshape(-1)
+    grad_blob[offs[25]: offs[25] + 128] = db_mid
 
 
 PACK_ORDER = ([f"mlp_base.layers.{l}.weight" for l in range(8)] + [f"mlp_base.layers.{l}.bias" for l in range(8)]

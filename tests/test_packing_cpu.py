@@ -157,11 +157,11 @@ def test_wgrad_finish_host_mirror_matches_the_algebra():
     dW_mid[:, bott] = G Wb^T + db_mid bb^T with G = job 12's region; everything else untouched."""
     g = torch.Generator().manual_seed(5)
     offs, shapes, total = ops.wgrad_layout()
-    assert shapes[9] == (256, 256) and shapes[12] == (128, 256)
+    assert shapes[9] == (256, 256) and shapes[10] == (256, 256) and shapes[12] == (128, 256)
     blob = torch.randn(total, generator=g)
     w_b, b_b, w_m = torch.randn(256, 256, generator=g), torch.randn(256, generator=g), torch.randn(128, 290, generator=g)
-    G = blob[offs[24]: offs[24] + 32768].view(128, 256).clone()
-    dbm = blob[offs[25]: offs[25] + 128].clone()
+    G = blob[offs[20] + 64 * 256: offs[20] + 192 * 256].view(128, 256).clone()       # rows 64-191 of job 10's region
+    dbm = blob[offs[21] + 64: offs[21] + 192].clone()
     out = blob.clone()
     ops.wgrad_finish(out, w_b, b_b, w_m)
     torch.testing.assert_close(out[offs[18]: offs[18] + 65536].view(256, 256), w_m[:, 34:].T @ G)
@@ -169,5 +169,6 @@ def test_wgrad_finish_host_mirror_matches_the_algebra():
     torch.testing.assert_close(out[offs[24]: offs[24] + 32768].view(128, 256), G @ w_b.T + torch.outer(dbm, b_b))
     keep = torch.ones(total, dtype=torch.bool)
     keep[offs[18]: offs[19] + 256] = False
-    keep[offs[24]: offs[24] + 32768] = False
+    keep[offs[24]: offs[25] + 128] = False
+    assert torch.equal(out[offs[25]: offs[25] + 128], dbm)
     assert torch.equal(out[keep], blob[keep])
