@@ -143,8 +143,9 @@ int rsn_field_wgrad_layout(int64_t* host_offsets, int64_t* host_shapes, int64_t*
 
 /* Completes the gradient blob once per step, after the last rsn_field_wgrad (and after the all-reduce): the bottleneck
  * layer is linear in h7 and feeds only the mid layer, so the kernels stash neither its activations nor their gradients;
- * with G = dY_mid^T h7 (job 12) this fills dW/db of field_output_bottleneck (job 9's region) = Wmb^T G, Wmb^T db_mid and
- * turns job 12's region into the bottleneck columns of d mlp_mid.layers.0.weight = G Wb^T + db_mid bb^T.
+ * with G = dY_mid^T h7 (rows 64-191 of job 10's region) this fills dW/db of field_output_bottleneck (job 9's region) =
+ * Wmb^T G, Wmb^T db_mid and job 12's region = the bottleneck columns of d mlp_mid.layers.0.weight = G Wb^T + db_mid bb^T
+ * (and db_mid).
  * w_bott [256][256], b_bott [256], w_mid [128][290]: the fp32 parameters (field.py:54-86), device pointers. */
 int rsn_field_wgrad_finish(float* grad_blob, const float* w_bott, const float* b_bott, const float* w_mid,
                            rsn_stream_t stream);

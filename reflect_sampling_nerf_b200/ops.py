@@ -339,7 +339,8 @@ def field_wgrad(stash: Tensor, dy_stash: Tensor, n_points: int, grad_blob: Tenso
 
 def wgrad_finish(grad_blob: Tensor, w_bott: Tensor, b_bott: Tensor, w_mid: Tensor) -> None:
     """Once per step, after the last field_wgrad (and the all-reduce): derive the bottleneck layer's gradients and the
-    bottleneck columns of d mlp_mid.layers.0.weight from G = dY_mid^T h7 (include/rsn_b200.h: rsn_field_wgrad_finish).
+    bottleneck columns of d mlp_mid.layers.0.weight from G = dY_mid^T h7 = rows 64-191 of wgrad job 10
+    (include/rsn_b200.h: rsn_field_wgrad_finish).
     CPU tensors (the gloo test of the flush path) take the same algebra through torch."""
     if grad_blob.is_cuda:
         _lib.call("rsn_field_wgrad_finish", _lib.ptr(grad_blob), _lib.ptr(_f32c(w_bott.detach())),
