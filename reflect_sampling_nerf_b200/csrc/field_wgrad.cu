@@ -24,6 +24,7 @@
 // (rsn_field_wgrad_finish, once per step on the accumulated -- and all-reduced -- blob): 8 of 95 block reads and 8 of 80
 // stash blocks per tile disappear from the wgrad, the training forward and the backward chain.
 #include "field_wgrad_body.cuh"
+#include <stdio.h>
 
 
 extern "C" int64_t rsn_field_dy_stash_bytes(int64_t n_points) {
@@ -122,5 +123,22 @@ extern "C" int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_
   }
   field_wgrad_kernel<<<cta, W_THREADS, smem, stream>>>(p);
   RSN_LAUNCH_CHECK("field_wgrad_kernel");
+  if (p.debug & 16) {
+    static unsigned long long t[2][160];
+    RSN_CUDA(cudaStreamSynchronize(stream));
+    RSN_CUDA(cudaMemcpyFromSymbol(t, g_wgrad_times, sizeof(t)));
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < cta; ++i) t0 = t[0][i] < t0 ? t[0][i] : t0;
+    for (int j = 0; j < p.n_jobs; ++j) {
+      if (!p.jobs[j].n_ctas) continue;
+      unsigned long long lo = ~0ull, hi = 0;
+      for (int i = p.jobs[j].cta_begin; i < p.jobs[j].cta_begin + p.jobs[j].n_ctas; ++i) {
+        lo = t[1][i] < lo ? t[1][i] : lo;
+        hi = t[1][i] > hi ? t[1][i] : hi;
+      }
+      fprintf(stderr, "wgrad job %2d: %2d CTAs, %d+%d blocks, CTAs end at %.1f .. %.1f us\n", j, p.jobs[j].n_ctas,
+              p.jobs[j].a_load, p.jobs[j].n_blocks, (lo - t0) * 1e-3, (hi - t0) * 1e-3);
+    }
+  }
   return 0;
 }

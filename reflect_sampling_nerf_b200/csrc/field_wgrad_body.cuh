@@ -44,6 +44,9 @@ struct WParams {
   WJob jobs[MAX_JOBS];
 };
 
+// RSN_WGRAD_DEBUG & 16: start / end %globaltimer of every CTA (per-job balance diagnostics)
+__device__ unsigned long long g_wgrad_times[2][160];
+
 struct WBarriers {
   uint64_t full[MAX_W_STAGES], empty[MAX_W_STAGES];
   uint64_t acc_full;
@@ -57,6 +60,11 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ WBarriers bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((p.debug & 16) && threadIdx.x == 0 && vbid < 160) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_wgrad_times[0][vbid] = t;
+  }
 
   int j = 0;
   for (int i = 0; i < p.n_jobs; ++i)
@@ -230,6 +238,11 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  if ((p.debug & 16) && threadIdx.x == 0 && vbid < 160) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_wgrad_times[1][vbid] = t;
+  }
 }
 
 __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_constant__ WParams p) {
@@ -241,22 +254,24 @@ struct JobSpec {
   int a_blk, m_blocks, b_blk, n_blocks, has_db;
   int active = 1;   // 0: the region is part of the blob but filled by rsn_field_wgrad_finish, not by the kernel
   int a_load = 0;   // dY blocks to load if fewer than m_blocks (see wgrad_body); 0 = m_blocks
+  int cost = 1000;  // measured time per loaded block of one CTA, relative to the 4 + 4 block jobs (x 1000): the small-slab jobs
+                    // pay more per byte (RSN_WGRAD_DEBUG=16 prints when each job's CTAs finish)
 };
 const JobSpec kJobs[] = {
-    {DY_H + 0, 4, STASH_ENC, 2, 1},             //  0  layer 0            x enc
+    {DY_H + 0, 4, STASH_ENC, 2, 1, 1, 0, 910},  //  0  layer 0            x enc
     {DY_H + 4, 4, STASH_H + 0, 4, 1},           //  1  layer 1            x h0
     {DY_H + 8, 4, STASH_H + 4, 4, 1},           //  2  layer 2            x h1
     {DY_H + 12, 4, STASH_H + 8, 4, 1},          //  3  layer 3            x h2
-    {DY_H + 16, 4, STASH_ENC, 2, 0},            //  4  layer 4 (enc part) x enc
+    {DY_H + 16, 4, STASH_ENC, 2, 0, 1, 0, 910}, //  4  layer 4 (enc part) x enc
     {DY_H + 16, 4, STASH_H + 12, 4, 1},         //  5  layer 4 (hidden)   x h3
     {DY_H + 20, 4, STASH_H + 16, 4, 1},         //  6  layer 5            x h4
     {DY_H + 24, 4, STASH_H + 20, 4, 1},         //  7  layer 6            x h5
     {DY_H + 28, 4, STASH_H + 24, 4, 1},         //  8  layer 7            x h6
     {DY_BOTT, 4, STASH_H + 28, 4, 1, 0},        //  9  bottleneck         x h7: derived from job 12 (rsn_field_wgrad_finish)
-    {DY_SEED, 4, STASH_H + 28, 4, 1, 1, 3},     // 10  [seed | dY_mid] x h7: rows 16-31 heads, rows 64-191 G = dY_mid^T h7
-    {DY_SEED, 2, STASH_MIDH, 2, 0},             // 11  rgb (rows 0-15)    x mid hidden (db from job 10's sums)
+    {DY_SEED, 4, STASH_H + 28, 4, 1, 1, 3, 1100},  // 10  [seed | dY_mid] x h7: rows 16-31 heads, rows 64-191 G = dY_mid^T h7
+    {DY_SEED, 2, STASH_MIDH, 2, 0, 1, 0, 990},  // 11  rgb (rows 0-15)    x mid hidden (db from job 10's sums)
     {DY_MID, 2, STASH_BOTT, 4, 1, 0},           // 12  mid x bottleneck: derived from job 10's G (rsn_field_wgrad_finish)
-    {DY_MID, 2, STASH_IDE, 1, 0},               // 13  mid (IDE part)     x IDE
+    {DY_MID, 2, STASH_IDE, 1, 0, 1, 0, 1160},   // 13  mid (IDE part)     x IDE
 };
 constexpr int kNumJobs = sizeof(kJobs) / sizeof(kJobs[0]);
 static_assert(kNumJobs <= MAX_JOBS, "job table too small");
@@ -271,13 +286,18 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
   p.grad = grad_blob;
   p.n_jobs = kNumJobs;
   p.debug = getenv("RSN_WGRAD_DEBUG") ? atoi(getenv("RSN_WGRAD_DEBUG")) : 0;
-  int units = 0, n_of[kNumJobs], used = 0;
-  for (int j = 0; j < kNumJobs; ++j) units += kJobs[j].active * ((kJobs[j].a_load ? kJobs[j].a_load : kJobs[j].m_blocks) + kJobs[j].n_blocks);
-  // CTAs per job proportional to the job's bytes per tile; the kernel ends with the job whose CTAs carry the most
-  // bytes each, so the CTAs left over by the rounding go, one at a time, to the job with the largest bytes / CTA
+  int n_of[kNumJobs], used = 0;
+  // CTAs per job proportional to the job's cost per tile = loaded blocks x measured relative time per block; the kernel
+  // ends with the job whose CTAs carry the most, so the CTAs left over by the rounding go, one at a time, to the job with
+  // the largest cost per CTA
+  auto cost_of = [](int j) -> double {
+    const JobSpec& k = kJobs[j];
+    return k.active ? ((k.a_load ? k.a_load : k.m_blocks) + k.n_blocks) * (k.cost * 1e-3) : 0.0;
+  };
+  double total_cost = 0.0;
+  for (int j = 0; j < kNumJobs; ++j) total_cost += cost_of(j);
   for (int j = 0; j < kNumJobs; ++j) {
-    const int u = (kJobs[j].a_load ? kJobs[j].a_load : kJobs[j].m_blocks) + kJobs[j].n_blocks;
-    n_of[j] = kJobs[j].active ? std::min(std::max(1, (u * cta_budget) / units), p.n_tiles) : 0;
+    n_of[j] = kJobs[j].active ? std::min(std::max(1, (int)(cost_of(j) * cta_budget / total_cost)), p.n_tiles) : 0;
     used += n_of[j];
   }
   while (used < cta_budget) {
@@ -285,7 +305,7 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
     double worst = 0.0;
     for (int j = 0; j < kNumJobs; ++j) {
       if (!kJobs[j].active) continue;
-      const double load = (double)((kJobs[j].a_load ? kJobs[j].a_load : kJobs[j].m_blocks) + kJobs[j].n_blocks) / n_of[j];
+      const double load = cost_of(j) / n_of[j];
       if (n_of[j] < p.n_tiles && load > worst) worst = load, best = j;
     }
     if (best < 0) break;
