@@ -343,7 +343,7 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
 #pragma unroll
         for (int j = 0; j < 4; ++j) a[chunk * 4 + j] = pk[j];
       }
-      if (RELU && MASKS) {
+      if (RELU && MASKS && !DEFER) {
         // ReLU mask bits of the 8 columns just packed: one packed compare (0xFFFF per half > 0) and one LOP3 per
         // word; word i of the 32-column half contributes bits i and 16 + i
 #pragma unroll
@@ -360,6 +360,14 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
   if (TS) tmem_st32(a_taddr, a);
   if (DEFER) {
     early();
+    if (RELU && MASKS) {   // the mask bits, from the packed words, after the hand-over: off the layer-critical path
+#pragma unroll
+      for (int w = 0; w < 32; ++w) {
+        __nv_bfloat162 hv;
+        *reinterpret_cast<uint32_t*>(&hv) = a[w];
+        mbits[w >> 4] |= __hgt2_mask(hv, __nv_bfloat162(__float2bfloat16(0.f), __float2bfloat16(0.f))) & (0x00010001u << (w & 15));
+      }
+    }
     guard();
 #pragma unroll
     for (int chunk = 0; chunk < 8; ++chunk)
