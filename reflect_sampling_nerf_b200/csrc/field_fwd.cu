@@ -299,12 +299,14 @@ __device__ __forceinline__ void ide_features(const float d[3], float rho, float 
 struct NoOp {
   __device__ __forceinline__ void operator()() const {}
 };
-template <bool RELU, bool MASKS = false, bool SBIAS = false, bool TS = false, bool SMEM = true, bool DEFER = false,
-          class Early = NoOp, class Guard = NoOp>
-__device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
-                                               uint32_t bias_saddr = 0, uint2* mask_out = nullptr, uint32_t a_taddr = 0,
-                                               Early early = Early(), Guard guard = Guard()) {
+// LAG (with DEFER): stop after the hand-over and leave the packed row in `a`; the caller stages it (stage_row) after the
+// NEXT group's hand-over, so that no staging work sits between two groups of the layer-critical chain.
+template <bool RELU, bool MASKS, bool SBIAS, bool TS, bool SMEM, bool DEFER, bool LAG, class Early, class Guard>
+__device__ __forceinline__ void epilogue_group_core(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
+                                                    uint32_t bias_saddr, uint2* mask_out, uint32_t a_taddr,
+                                                    uint32_t (&a)[32], Early early, Guard guard) {
   static_assert(!DEFER || (TS && SMEM), "DEFER is the TS + stash form");
+  static_assert(!LAG || DEFER, "LAG refines DEFER");
   uint32_t mbits[2] = {0u, 0u};
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
@@ -321,7 +323,6 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
   }
   tmem_ld_wait();
   const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
-  uint32_t a[32];   // TS: the 64 bf16 of this row, two per 32-bit TMEM column
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -360,6 +361,7 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
   if (TS) tmem_st32(a_taddr, a);
   if (DEFER) {
     early();
+    if (LAG) return;
     if (RELU && MASKS) {   // the mask bits, from the packed words, after the hand-over: off the layer-critical path
 #pragma unroll
       for (int w = 0; w < 32; ++w) {
@@ -375,6 +377,33 @@ __device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_o
              a[chunk * 4 + 3]);
   }
   if (RELU && MASKS) *mask_out = make_uint2(mbits[0], mbits[1]);
+}
+template <bool RELU, bool MASKS = false, bool SBIAS = false, bool TS = false, bool SMEM = true, bool DEFER = false,
+          class Early = NoOp, class Guard = NoOp>
+__device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
+                                               uint32_t bias_saddr = 0, uint2* mask_out = nullptr, uint32_t a_taddr = 0,
+                                               Early early = Early(), Guard guard = Guard()) {
+  uint32_t a[32];   // TS: the 64 bf16 of this row, two per 32-bit TMEM column
+  epilogue_group_core<RELU, MASKS, SBIAS, TS, SMEM, DEFER, false>(tmem_row_col, bias_off, blk_saddr, row, bias_saddr, mask_out,
+                                                                  a_taddr, a, early, guard);
+}
+// The staging half of a LAG group: ReLU mask bits from the packed row, the row into its shared-memory block.
+template <bool MASKS>
+__device__ __forceinline__ void stage_row(const uint32_t (&a)[32], uint32_t blk_saddr, int row, uint2* mask_out) {
+  const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
+#pragma unroll
+  for (int chunk = 0; chunk < 8; ++chunk)
+    sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), a[chunk * 4 + 0], a[chunk * 4 + 1], a[chunk * 4 + 2], a[chunk * 4 + 3]);
+  if (MASKS) {
+    uint32_t mbits[2] = {0u, 0u};
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      __nv_bfloat162 hv;
+      *reinterpret_cast<uint32_t*>(&hv) = a[w];
+      mbits[w >> 4] |= __hgt2_mask(hv, __nv_bfloat162(__float2bfloat16(0.f), __float2bfloat16(0.f))) & (0x00010001u << (w & 15));
+    }
+    *mask_out = make_uint2(mbits[0], mbits[1]);
+  }
 }
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __expf(-x)); }
@@ -756,11 +785,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       using T_ = std::integral_constant<bool, true>;
       using F_ = std::integral_constant<bool, false>;
       uint2* const masks = st ? reinterpret_cast<uint2*>(st + STASH_MASK_OFF) : nullptr;
+      // TS + stash: a whole ReLU layer of NG groups with LAGGED staging -- group g is converted and handed to the issuer,
+      // and only then is group g-1 staged (masks, 8 x st.shared, bulk store): nothing but the conversion itself separates
+      // two hand-overs of the layer-critical chain.
+      auto layer_lag = [&](auto ng_c, int bias_off, uint32_t sb, int mask_layer, int stash_blk0, bool first) {
+        constexpr int NG = decltype(ng_c)::value;
+        if constexpr (TS) {
+          uint32_t a2[2][32];
+          auto stage = [&](int g, const uint32_t (&a)[32]) {
+            const uint32_t blk = s_act + g * BLOCK_BYTES;
+            if (first) warp_store_guard<1>(lane); else warp_store_guard<3>(lane);
+            stage_row<true>(a, blk, row, masks + mask_entry(mask_layer, g, row));
+            if (!(p.debug & 8)) warp_store_rows(sblk(stash_blk0 + g), blk, q, lane);
+          };
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            const uint32_t acc_c = tlane + (uint32_t)buf * 256 + g * 64, a_t = tlane + (uint32_t)buf * 256 + g * 32;
+            epilogue_group_core<true, true, SBIAS, true, true, true, true>(
+                acc_c, bias_off + g * 64, s_act + g * BLOCK_BYTES, row, sb + g * 256, nullptr, a_t, a2[g & 1],
+                [&]() {
+                  tmem_st_wait();
+                  tc_fence_before();
+                  arrive_issuer(&bars.act_ready[g]);
+                },
+                NoOp());
+            if (g > 0) stage(g - 1, a2[(g - 1) & 1]);
+          }
+          stage(NG - 1, a2[(NG - 1) & 1]);
+        }
+      };
       for (int l = 0; l < 8; ++l) {
         wait_acc();
         const uint32_t sb = bias_slot();
-        for (int g = 0; g < 4; ++g)
-          convert(T_{}, T_{}, BIAS_BASE + l * 256, sb, g, masks + mask_entry(l, g, row), sblk(STASH_H + 4 * l + g), l == 0);
+        if (TS && st) {
+          layer_lag(std::integral_constant<int, 4>{}, BIAS_BASE + l * 256, sb, l, STASH_H + 4 * l, l == 0);
+        } else {
+          for (int g = 0; g < 4; ++g)
+            convert(T_{}, T_{}, BIAS_BASE + l * 256, sb, g, masks + mask_entry(l, g, row), sblk(STASH_H + 4 * l + g), l == 0);
+        }
         buf ^= 1;
       }
       // ---- layer 8: bottleneck -> activation blocks (no activation), then heads + IDE
@@ -847,8 +909,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       {
         wait_acc();
         const uint32_t sb = bias_slot();
-        for (int g = 0; g < 2; ++g)
-          convert(T_{}, T_{}, BIAS_MID, sb, g, masks + mask_entry(8, g, row), sblk(STASH_MIDH + g), false);
+        if (TS && st) {
+          layer_lag(std::integral_constant<int, 2>{}, BIAS_MID, sb, 8, STASH_MIDH, false);
+        } else {
+          for (int g = 0; g < 2; ++g)
+            convert(T_{}, T_{}, BIAS_MID, sb, g, masks + mask_entry(8, g, row), sblk(STASH_MIDH + g), false);
+        }
         buf ^= 1;
       }
       // ---- layer 10: rgb
