@@ -16,10 +16,14 @@
 // warp 6 streams the forward's stashed activation blocks (ReLU masks, and the encoding values the IPE
 // Jacobian needs) through a 3 x 16 KB ring, warp 1 issues tcgen05.mma into two alternating 256-column TMEM
 // accumulators, warps 2-5 run the per-row epilogues: dX = acc * (h > 0) -> bf16 -> the next step's A
-// operand, in place, published per 64-column group.
+// operand, published per 64-column group -- by default written back into TMEM (tcgen05.st; the next MMA takes its A
+// operand from there), with RSN_BWD_TS=0 in place into the shared-memory activation blocks.  The ReLU masks arrive as the
+// forward's bit masks (8 bytes per row, layer and group, prefetched into registers), only the two stashed encoding blocks
+// go through the second ring.
 //
 // Roofline: bf16 tensor.  Algorithmic FLOPs per point: NORMALS 1,019,392; BACKWARD dgrad 1,179,904 primary,
-// 1,229,056 reflected.  HBM: masks 4.4 KB/pt in, dY 4.9 KB/pt out.
+// 1,229,056 reflected.  HBM: masks 288 B/pt (+ encodings 256 B/pt) in, dY 4.4 KB/pt out (dY of the
+// bottleneck layer is not written: csrc/field_wgrad.cu).
 #include "field_bwd_body.cuh"
 
 

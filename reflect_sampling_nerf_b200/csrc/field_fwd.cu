@@ -11,12 +11,16 @@
 //   call sites                                        reflect_sampling_nerf_model.py:151-175,185-209,290,293-310,319-336
 //
 // One persistent CTA per SM, 10 warps, one 128-point tile in flight per CTA:
-//   warp 0      weight producer: streams the pre-packed bf16 weight blob (L2 resident, 1.27 MB) through a
-//               3 x 32 KB shared-memory ring with cp.async.bulk (TMA engine) + mbarrier complete_tx
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M128, N<=256, K16, bf16 -> fp32 in TMEM)
-//   warps 6-9   epilogue: tcgen05.ld the accumulator row of "their" point, bias + ReLU, bf16, write the
-//               next layer's A operand IN PLACE into the swizzled activation blocks; heads, IDE, outputs
-//   warps 2-5   prologue for the NEXT tile: frustum gaussian, contraction, IPE -> bf16 A operand
+//   warp 0      weight producer: streams the pre-packed bf16 weight blob (L2 resident, 1.27 MB) through a ring of
+//               32 KB shared-memory stages (3; 5 when no stash is written) with cp.async.bulk + mbarrier complete_tx
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M128, N<=256, K16, bf16 -> fp32 in TMEM) and requests each
+//               wide layer's fp32 bias into a two-slot shared-memory buffer two layers ahead
+//   warps 6-9   epilogue: tcgen05.ld the accumulator row of "their" point, bias + ReLU, bf16, and hand the row to the next
+//               layer as its A operand -- by default back into TMEM (tcgen05.st over accumulator columns already read;
+//               the next MMA is tcgen05.mma [d], [a], b-desc), optionally (RSN_FWD_TS=0) in place into the swizzled
+//               shared-memory activation blocks; then, in training, stage the row for the activation stash (bulk store)
+//               and emit the ReLU bit masks; heads, IDE, outputs
+//   warps 2-5   prologue for the NEXT tile: frustum gaussian, contraction, IPE -> bf16 A operand (shared memory)
 // The two 256-column TMEM accumulator buffers alternate by layer, and every layer's epilogue publishes
 // its output per 64-column group (mbarrier act_ready[g]) so that the next layer's K-block g is issued as
 // soon as that group is written: MMA of layer l+1 overlaps the epilogue of layer l.
