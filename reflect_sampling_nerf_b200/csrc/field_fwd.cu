@@ -55,10 +55,10 @@ __constant__ float c_freq[16] = {
     0x1.33f9760000000p+4f,  0x1.428a320000000p+5f,  0x1.51cb4e0000000p+6f,  0x1.61c5140000000p+7f,
     0x1.7280340000000p+8f,  0x1.8405f60000000p+9f,  0x1.965fde0000000p+10f, 0x1.a998080000000p+11f,
     0x1.bdb8d20000000p+12f, 0x1.d2cd4c0000000p+13f, 0x1.e8e1020000000p+14f, 0x1.0000000000000p+16f};
-// Bias vector of the current launch (N_BIAS floats).  Every epilogue thread of a warp reads the same bias element
-// at the same time (its own row, the same column): the uniform-address case the constant cache serves in a few
-// cycles, where the same load from global memory pays an L2 round trip on the layer-critical path (L1 is empty:
-// the kernel takes the whole carve-out as shared memory).  Refilled device-to-device, stream-ordered, by every
+// Bias vector of the current launch (N_BIAS floats) in constant memory: read with compile-time offsets by the heads and
+// the rgb layer (once per tile each), and with run-time offsets by the CTA-pair form.  The wide layers of the default form
+// take their bias from the two-slot shared-memory buffer instead (SMEM_BIAS): an indexed LDC of a 10 KB table that cycles
+// once per tile was the forward's bottleneck.  Refilled device-to-device, stream-ordered, by every
 // rsn_field_forward call, so it carries no state between calls.
 __constant__ float4 c_bias4[N_BIAS / 4];
 const float h_freq[16] = {

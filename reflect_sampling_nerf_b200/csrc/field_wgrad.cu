@@ -21,7 +21,7 @@
 // [seed | dY_mid] with h7 in one pass) and db_mid,
 //   dW_mid[:, bott part] = dY_mid^T bott     = G Wb^T + db_mid bb^T
 //   dW_bott              = (dY_mid Wmb)^T h7 = Wmb^T G            db_bott = Wmb^T db_mid
-// (rsn_field_wgrad_finish, once per step on the accumulated -- and all-reduced -- blob): 8 of 95 block reads and 8 of 80
+// (rsn_field_wgrad_finish, once per step on the accumulated -- and all-reduced -- blob): 8 of the 95 block reads and 8 of the 80
 // stash blocks per tile disappear from the wgrad, the training forward and the backward chain.
 #include "field_wgrad_body.cuh"
 #include <stdio.h>

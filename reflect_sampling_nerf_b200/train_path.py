@@ -128,7 +128,7 @@ class _FieldPass(torch.autograd.Function):
                 g_feat.contiguous(), feat, aux, field._dy_buffer, want_area)
         if os.environ.get("RSN_FUSED_BWD", "0") == "1":
             # chain + wgrad CTAs in one launch (validated, opt-in): the wgrad's load rate is bound by the bytes one SM
-            # can keep in flight (~36 GB/s per SM), so on half of the SMs it takes twice as long -- 8.2 ms fused against
+            # can keep in flight (~45 GB/s per SM), so on half of the SMs it takes twice as long -- 8.2 ms fused against
             # 3.2 + 3.2 ms back to back at C2
             g_area = ops.field_backward_fused(*args, field._grad_blob)
         else:
