@@ -57,7 +57,9 @@ template <int K, int C>
 __global__ void __launch_bounds__(256) composite_fwd_kernel(
     const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
     int64_t bin_stride, const float* __restrict__ feat, float* __restrict__ weights, float* __restrict__ acc_out,
-    float* __restrict__ depth_out, float* __restrict__ feat_out, int64_t n_rays, int S) {
+    float* __restrict__ depth_out, float* __restrict__ feat_out, int64_t n_rays, int S,
+    const int* __restrict__ n_rays_dev) {
+  n_rays = rsn_count(n_rays, n_rays_dev);
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -126,7 +128,8 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
     const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
     int64_t bin_stride, const float* __restrict__ feat, const float* __restrict__ g_weights,
     const float* __restrict__ g_acc, const float* __restrict__ g_feat_out, float* __restrict__ g_sigma,
-    float* __restrict__ g_feat, int64_t n_rays, int S) {
+    float* __restrict__ g_feat, int64_t n_rays, int S, const int* __restrict__ n_rays_dev) {
+  n_rays = rsn_count(n_rays, n_rays_dev);
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -215,8 +218,10 @@ __global__ void __launch_bounds__(256) composite_fwd_vec_kernel(
     const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends,
     int64_t bin_stride, const float4* __restrict__ feat4, float* __restrict__ weights, float* __restrict__ acc_out,
     float* __restrict__ depth_out, float4* __restrict__ feat_out4, int64_t n_rays, int S, int s_pad,
-    const float* __restrict__ normals, float* __restrict__ pnl_out, float* __restrict__ ol_out) {
+    const float* __restrict__ normals, float* __restrict__ pnl_out, float* __restrict__ ol_out,
+    float* __restrict__ blend_out, const int* __restrict__ n_rays_dev) {
   extern __shared__ float sm_rows[];
+  n_rays = rsn_count(n_rays, n_rays_dev);
   const int lane = threadIdx.x & 31;
   float* ws = sm_rows + (threadIdx.x >> 5) * s_pad;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -290,6 +295,12 @@ __global__ void __launch_bounds__(256) composite_fwd_vec_kernel(
     }
     if (lane < Q) feat_out4[r * Q + lane] = a;
     if (lane == 0) {
+      if (blend_out) {   // RGBRenderer with the white background, then torch.clip (model.py:176-177): clip(rgb + (1 - acc))
+        const float rest = 1.f - acc;
+        blend_out[r * 3 + 0] = fminf(fmaxf(a.x + rest, 0.f), 1.f);
+        blend_out[r * 3 + 1] = fminf(fmaxf(a.y + rest, 0.f), 1.f);
+        blend_out[r * 3 + 2] = fminf(fmaxf(a.z + rest, 0.f), 1.f);
+      }
       acc_out[r] = acc;
       const int mi = min(median, S - 1);
       depth_out[r] = (__ldg(st + mi) + __ldg(en + mi)) / 2.f;
@@ -304,8 +315,10 @@ __global__ void __launch_bounds__(256) composite_bwd_vec_kernel(
     int64_t bin_stride, const float4* __restrict__ feat4, const float* __restrict__ g_weights,
     const float* __restrict__ g_acc, const float4* __restrict__ g_feat_out4, float* __restrict__ g_sigma,
     float4* __restrict__ g_feat4, int64_t n_rays, int S, int s_pad, const float* __restrict__ normals,
-    const float* __restrict__ g_pnl, const float* __restrict__ g_ol) {
+    const float* __restrict__ g_pnl, const float* __restrict__ g_ol, const float* __restrict__ g_blend,
+    const float* __restrict__ feat_out, const float* __restrict__ acc_in, const int* __restrict__ n_rays_dev) {
   extern __shared__ float sm_rows[];
+  n_rays = rsn_count(n_rays, n_rays_dev);
   const int lane = threadIdx.x & 31;
   float* ws = sm_rows + (threadIdx.x >> 5) * 3 * s_pad;   // weights
   float* tns = ws + s_pad;                                // transmittance behind the sample
@@ -316,8 +329,19 @@ __global__ void __launch_bounds__(256) composite_bwd_vec_kernel(
     const float* sg = sigma + r * S;
     const float* st = starts + r * bin_stride;
     const float* en = ends + r * bin_stride;
-    const float ga = g_acc ? __ldg(g_acc + r) : 0.f;
-    const float4 go = g_feat_out4 ? __ldg(g_feat_out4 + r * Q + (lane % Q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float ga = g_acc ? __ldg(g_acc + r) : 0.f;
+    float4 go = g_feat_out4 ? __ldg(g_feat_out4 + r * Q + (lane % Q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g_blend) {   // blend = clip(feat_out[0:3] + (1 - acc), 0, 1): torch.clip passes the gradient inside [0, 1]
+      const float rest = 1.f - __ldg(acc_in + r);
+      float gb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = __ldg(feat_out + r * (4 * Q) + c) + rest;
+        gb[c] = (v >= 0.f && v <= 1.f) ? __ldg(g_blend + r * 3 + c) : 0.f;
+      }
+      ga -= gb[0] + gb[1] + gb[2];
+      if ((lane % Q) == 0) go.x += gb[0], go.y += gb[1], go.z += gb[2];
+    }
     double tau_carry = 0.0;
     for (int base = 0; base < S; base += 32 * K) {
       float dd[K], w[K], tn[K];
@@ -360,6 +384,10 @@ __global__ void __launch_bounds__(256) composite_bwd_vec_kernel(
       }
     }
     __syncwarp();
+    if (g_sigma == nullptr) {   // density detached upstream (bounce passes, model.py:297,323)
+      __syncwarp();
+      continue;
+    }
     // dL/d(dd_j) = gw_j T_{j+1} - sum_{s>j} gw_s w_s ;  dL/dsigma_j = dL/d(dd_j) * delta_j
     double total = 0.0;
     for (int s = lane; s < S; s += 32) total += (double)(gws[s] * ws[s]);
@@ -393,12 +421,59 @@ __global__ void __launch_bounds__(256) composite_bwd_vec_kernel(
   }
 }
 
+// The upstream renderers' call forms (AccumulationRenderer / RGBRenderer / DepthRenderer(median) / NormalsRenderer /
+// SemanticRenderer, reflect_sampling_nerf_model.py:117-124) take WEIGHTS, not densities: one warp per
+// ray reduces acc = sum w, feat_out = sum w feat (C <= 16 channels) and the median depth from the given weights.
+__global__ void __launch_bounds__(256) render_weights_kernel(const float* __restrict__ weights, const float* __restrict__ feat,
+                                                             int C, const float* __restrict__ starts,
+                                                             const float* __restrict__ ends, int64_t bin_stride,
+                                                             float* __restrict__ acc_out, float* __restrict__ feat_out,
+                                                             float* __restrict__ depth_out, int64_t n_rays, int S) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rays) return;
+  const float* w = weights + r * S;
+  float acc = 0.f, fs[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) fs[c] = 0.f;
+  for (int s = lane; s < S; s += 32) {
+    const float ws = __ldg(w + s);
+    acc += ws;
+    for (int c = 0; c < C; ++c) fs[c] += ws * __ldg(feat + ((int64_t)r * S + s) * C + c);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && acc_out) acc_out[r] = acc;
+  for (int c = 0; c < C; ++c) {
+    const float v = warp_sum(fs[c]);
+    if (lane == 0) feat_out[r * C + c] = v;
+  }
+  if (depth_out) {   // steps[clamp(searchsorted(cumsum(w), 0.5, side="left"), 0, S-1)], cumulative weight in fp64
+    int median = S;
+    double carry = 0.0;
+    for (int base = 0; base < S; base += 32) {
+      const int s = base + lane;
+      const double v = s < S ? (double)__ldg(w + s) : 0.0;
+      const double incl = warp_incl_scan(v, lane);
+      int mine = (s < S && (float)(carry + incl) >= 0.5f) ? s : S;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(RSN_FULL, mine, o));
+      median = min(median, mine);
+      carry += __shfl_sync(RSN_FULL, incl, 31);
+    }
+    if (lane == 0) {
+      const int mi = min(median, S - 1);
+      depth_out[r] = (__ldg(starts + r * bin_stride + mi) + __ldg(ends + r * bin_stride + mi)) / 2.f;
+    }
+  }
+}
+
 constexpr int VEC_MAX_SAMPLES = 1024;   // 8 warps x 3 rows x 4 KB of dynamic shared memory in the backward
 
 template <int C>
 int launch_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_stride, const float* feat,
                float* weights, float* acc, float* depth, float* feat_out, int64_t n_rays, int S,
-               cudaStream_t stream, const float* normals = nullptr, float* pnl = nullptr, float* ol = nullptr) {
+               cudaStream_t stream, const int* n_rays_dev = nullptr, const float* normals = nullptr, float* pnl = nullptr,
+               float* ol = nullptr, float* blend = nullptr) {
   const int threads = 256;
   int64_t want = (n_rays * 32 + threads - 1) / threads;
   int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
@@ -411,7 +486,7 @@ int launch_fwd(const float* sigma, const float* starts, const float* ends, int64
   composite_fwd_vec_kernel<K, Q><<<blocks, threads, smem, stream>>>(sigma, starts, ends, bin_stride,             \
                                                                     (const float4*)feat, weights, acc, depth,    \
                                                                     (float4*)feat_out, n_rays, S, s_pad, normals, \
-                                                                    pnl, ol)
+                                                                    pnl, ol, blend, n_rays_dev)
     if (S <= 32) RSN_FWDV(1);
     else if (S <= 64) RSN_FWDV(2);
     else RSN_FWDV(4);
@@ -419,10 +494,10 @@ int launch_fwd(const float* sigma, const float* starts, const float* ends, int64
     RSN_LAUNCH_CHECK("composite_fwd_vec_kernel");
     return 0;
   }
-  if (normals) return rsn_fail(-1, "rsn_composite16_fwd: needs n_samples <= %d and 16-byte aligned feat", VEC_MAX_SAMPLES);
+  if (normals || blend) return rsn_fail(-1, "rsn_composite16_fwd: needs n_samples <= %d and 16-byte aligned feat", VEC_MAX_SAMPLES);
 #define RSN_FWD(K)                                                                                        \
   composite_fwd_kernel<K, C><<<blocks, threads, 0, stream>>>(sigma, starts, ends, bin_stride, feat, weights, \
-                                                             acc, depth, feat_out, n_rays, S)
+                                                             acc, depth, feat_out, n_rays, S, n_rays_dev)
   if (S <= 32) RSN_FWD(1);
   else if (S <= 64) RSN_FWD(2);
   else RSN_FWD(4);
@@ -434,8 +509,9 @@ int launch_fwd(const float* sigma, const float* starts, const float* ends, int64
 template <int C>
 int launch_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_stride, const float* feat,
                const float* g_weights, const float* g_acc, const float* g_feat_out, float* g_sigma, float* g_feat,
-               int64_t n_rays, int S, cudaStream_t stream, const float* normals = nullptr, const float* g_pnl = nullptr,
-               const float* g_ol = nullptr) {
+               int64_t n_rays, int S, cudaStream_t stream, const int* n_rays_dev = nullptr, const float* normals = nullptr,
+               const float* g_pnl = nullptr, const float* g_ol = nullptr, const float* g_blend = nullptr,
+               const float* feat_out = nullptr, const float* acc_in = nullptr) {
   const int threads = 256;
   int64_t want = (n_rays * 32 + threads - 1) / threads;
   int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
@@ -444,20 +520,17 @@ int launch_bwd(const float* sigma, const float* starts, const float* ends, int64
     constexpr int Q = C >= 4 ? C / 4 : 1;
     const int s_pad = (S + 3) & ~3;
     const size_t smem = (size_t)(threads / 32) * 3 * s_pad * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(composite_bwd_vec_kernel<1, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * VEC_MAX_SAMPLES * 4);
-      cudaFuncSetAttribute(composite_bwd_vec_kernel<2, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * VEC_MAX_SAMPLES * 4);
-      cudaFuncSetAttribute(composite_bwd_vec_kernel<4, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * VEC_MAX_SAMPLES * 4);
-      attr_set = true;
-    }
+    static std::atomic<unsigned long long> done[3];
+    RSN_CUDA(rsn_ensure_smem(composite_bwd_vec_kernel<1, Q>, 8 * 3 * VEC_MAX_SAMPLES * 4, done[0]));
+    RSN_CUDA(rsn_ensure_smem(composite_bwd_vec_kernel<2, Q>, 8 * 3 * VEC_MAX_SAMPLES * 4, done[1]));
+    RSN_CUDA(rsn_ensure_smem(composite_bwd_vec_kernel<4, Q>, 8 * 3 * VEC_MAX_SAMPLES * 4, done[2]));
     blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 8);
 #define RSN_BWDV(K)                                                                                                \
   composite_bwd_vec_kernel<K, Q><<<blocks, threads, smem, stream>>>(sigma, starts, ends, bin_stride,               \
                                                                     (const float4*)feat, g_weights, g_acc,         \
                                                                     (const float4*)g_feat_out, g_sigma,            \
                                                                     (float4*)g_feat, n_rays, S, s_pad, normals,    \
-                                                                    g_pnl, g_ol)
+                                                                    g_pnl, g_ol, g_blend, feat_out, acc_in, n_rays_dev)
     if (S <= 32) RSN_BWDV(1);
     else if (S <= 64) RSN_BWDV(2);
     else RSN_BWDV(4);
@@ -465,10 +538,11 @@ int launch_bwd(const float* sigma, const float* starts, const float* ends, int64
     RSN_LAUNCH_CHECK("composite_bwd_vec_kernel");
     return 0;
   }
-  if (normals) return rsn_fail(-1, "rsn_composite16_bwd: needs n_samples <= %d and 16-byte aligned buffers", VEC_MAX_SAMPLES);
+  if (normals || g_blend || !g_sigma)
+    return rsn_fail(-1, "rsn_composite16_bwd: needs n_samples <= %d and 16-byte aligned buffers", VEC_MAX_SAMPLES);
 #define RSN_BWD(K)                                                                                          \
   composite_bwd_kernel<K, C><<<blocks, threads, 0, stream>>>(sigma, starts, ends, bin_stride, feat, g_weights, \
-                                                             g_acc, g_feat_out, g_sigma, g_feat, n_rays, S)
+                                                             g_acc, g_feat_out, g_sigma, g_feat, n_rays, S, n_rays_dev)
   if (S <= 32) RSN_BWD(1);
   else if (S <= 64) RSN_BWD(2);
   else RSN_BWD(4);
@@ -493,52 +567,79 @@ int launch_bwd(const float* sigma, const float* starts, const float* ends, int64
 extern "C" int rsn_composite_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
                                  const float* feat, int64_t n_channels, float* weights, float* accumulation,
                                  float* depth_median, float* feat_out, int64_t n_rays, int64_t n_samples,
-                                 cudaStream_t stream) {
+                                 const int* n_rays_dev, cudaStream_t stream) {
   RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_composite_fwd: bad shape");
   if (n_rays == 0) return 0;
   RSN_ARG(sigma && starts && ends && weights && accumulation && depth_median, "rsn_composite_fwd: null pointer");
   RSN_ARG(n_channels == 0 || (feat && feat_out), "rsn_composite_fwd: feat/feat_out required when n_channels > 0");
   RSN_DISPATCH_C(launch_fwd, sigma, starts, ends, bin_row_stride, feat, weights, accumulation, depth_median,
-                 feat_out, n_rays, (int)n_samples, stream);
+                 feat_out, n_rays, (int)n_samples, stream, n_rays_dev);
 }
 
 extern "C" int rsn_composite_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
                                  const float* feat, int64_t n_channels, const float* grad_weights,
                                  const float* grad_accumulation, const float* grad_feat_out, float* grad_sigma,
-                                 float* grad_feat, int64_t n_rays, int64_t n_samples, cudaStream_t stream) {
+                                 float* grad_feat, int64_t n_rays, int64_t n_samples, const int* n_rays_dev,
+                                 cudaStream_t stream) {
   RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_composite_bwd: bad shape");
   if (n_rays == 0) return 0;
   RSN_ARG(sigma && starts && ends && grad_sigma, "rsn_composite_bwd: null pointer");
   RSN_ARG(n_channels == 0 || feat, "rsn_composite_bwd: feat required when n_channels > 0");
   RSN_DISPATCH_C(launch_bwd, sigma, starts, ends, bin_row_stride, feat, grad_weights, grad_accumulation,
-                 grad_feat_out, grad_sigma, grad_feat, n_rays, (int)n_samples, stream);
+                 grad_feat_out, grad_sigma, grad_feat, n_rays, (int)n_samples, stream, n_rays_dev);
 }
 
-// The model's 16-channel form with the two per-sample normal losses fused in (their sample weights are the detached
-// compositing weights, reflect_sampling_nerf_model.py:403-407): per ray
-//   pred_normal_loss[r] = sum_s w_s |normals_s - feat_s[9:12]|^2      orientation_loss[r] = sum_s w_s max(0, feat_s[13])^2
+// The model's 16-channel form.  Optional riders on the same pass:
+//   * normals != NULL: the two per-sample normal losses (their sample weights are the detached compositing weights,
+//     reflect_sampling_nerf_model.py:403-407), per ray
+//       pred_normal_loss[r] = sum_s w_s |normals_s - feat_s[9:12]|^2    orientation_loss[r] = sum_s w_s max(0, feat_s[13])^2
+//   * rgb_blend != NULL: renderer_rgb's white-background blend and the clip that follows it (model.py:176-177,210-211),
+//       rgb_blend[r] = clip(feat_out[r, 0:3] + (1 - accumulation[r]), 0, 1)
+//   * n_rays_dev != NULL: the ray count lives on the device (bounce passes)
 extern "C" int rsn_composite16_fwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
                                    const float* feat, const float* normals, float* weights, float* accumulation,
                                    float* depth_median, float* feat_out, float* pred_normal_loss,
-                                   float* orientation_loss, int64_t n_rays, int64_t n_samples, cudaStream_t stream) {
+                                   float* orientation_loss, float* rgb_blend, int64_t n_rays, int64_t n_samples,
+                                   const int* n_rays_dev, cudaStream_t stream) {
   RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_composite16_fwd: bad shape");
   if (n_rays == 0) return 0;
-  RSN_ARG(sigma && starts && ends && feat && normals && weights && accumulation && depth_median && feat_out &&
-              pred_normal_loss && orientation_loss, "rsn_composite16_fwd: null pointer");
+  RSN_ARG(sigma && starts && ends && feat && weights && accumulation && depth_median && feat_out,
+          "rsn_composite16_fwd: null pointer");
+  RSN_ARG(!normals || (pred_normal_loss && orientation_loss), "rsn_composite16_fwd: loss outputs required with normals");
   return launch_fwd<16>(sigma, starts, ends, bin_row_stride, feat, weights, accumulation, depth_median, feat_out, n_rays,
-                        (int)n_samples, stream, normals, pred_normal_loss, orientation_loss);
+                        (int)n_samples, stream, n_rays_dev, normals, pred_normal_loss, orientation_loss, rgb_blend);
 }
 
+// grad_sigma == NULL: the density is detached upstream (bounce passes), only grad_feat is produced.
+// grad_rgb_blend != NULL needs the forward's feat_out and accumulation (the clip mask is recomputed from them).
 extern "C" int rsn_composite16_bwd(const float* sigma, const float* starts, const float* ends, int64_t bin_row_stride,
                                    const float* feat, const float* normals, const float* grad_weights,
                                    const float* grad_accumulation, const float* grad_feat_out,
                                    const float* grad_pred_normal_loss, const float* grad_orientation_loss,
+                                   const float* grad_rgb_blend, const float* feat_out, const float* accumulation,
                                    float* grad_sigma, float* grad_feat, int64_t n_rays, int64_t n_samples,
-                                   cudaStream_t stream) {
+                                   const int* n_rays_dev, cudaStream_t stream) {
   RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_composite16_bwd: bad shape");
   if (n_rays == 0) return 0;
-  RSN_ARG(sigma && starts && ends && feat && normals && grad_sigma && grad_feat, "rsn_composite16_bwd: null pointer");
+  RSN_ARG(sigma && starts && ends && feat && grad_feat, "rsn_composite16_bwd: null pointer");
+  RSN_ARG(!grad_rgb_blend || (feat_out && accumulation), "rsn_composite16_bwd: feat_out/accumulation required with grad_rgb_blend");
   return launch_bwd<16>(sigma, starts, ends, bin_row_stride, feat, grad_weights, grad_accumulation, grad_feat_out,
-                        grad_sigma, grad_feat, n_rays, (int)n_samples, stream, normals, grad_pred_normal_loss,
-                        grad_orientation_loss);
+                        grad_sigma, grad_feat, n_rays, (int)n_samples, stream, n_rays_dev, normals, grad_pred_normal_loss,
+                        grad_orientation_loss, grad_rgb_blend, feat_out, accumulation);
+}
+
+
+extern "C" int rsn_render_weights(const float* weights, const float* feat, int64_t n_channels, const float* starts,
+                                  const float* ends, int64_t bin_row_stride, float* accumulation, float* feat_out,
+                                  float* depth_median, int64_t n_rays, int64_t n_samples, cudaStream_t stream) {
+  RSN_ARG(n_rays >= 0 && n_samples >= 1 && n_channels >= 0 && n_channels <= 16, "rsn_render_weights: bad shape");
+  if (n_rays == 0) return 0;
+  RSN_ARG(weights != nullptr, "rsn_render_weights: null pointer");
+  RSN_ARG(n_channels == 0 || (feat && feat_out), "rsn_render_weights: feat/feat_out required when n_channels > 0");
+  RSN_ARG(!depth_median || (starts && ends), "rsn_render_weights: starts/ends required for the median depth");
+  render_weights_kernel<<<(unsigned)((n_rays * 32 + 255) / 256), 256, 0, stream>>>(
+      weights, feat, (int)n_channels, starts, ends, bin_row_stride, accumulation, feat_out, depth_median, n_rays,
+      (int)n_samples);
+  RSN_LAUNCH_CHECK("render_weights_kernel");
+  return 0;
 }

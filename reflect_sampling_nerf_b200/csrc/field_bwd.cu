@@ -52,7 +52,8 @@ extern "C" int rsn_field_normals(const void* wblob_t, const void* wd_bf16, const
 extern "C" int rsn_field_backward(const void* wblob_t, const void* x_stash, int mode, const float* origins,
                                   const float* dirs, const float* area, const float* bins, int64_t n_rays,
                                   int64_t n_samples, const float* g_sigma, const float* g_feat, const float* feat,
-                                  const float* aux, void* dy_stash, float* g_area, cudaStream_t stream) {
+                                  const float* aux, void* dy_stash, float* g_area, const int* n_rays_dev,
+                                  cudaStream_t stream) {
   RSN_ARG(mode == 0 || mode == 1, "rsn_field_backward: mode must be 0 or 1");
   RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_field_backward: bad shape");
   if (n_rays == 0) return 0;
@@ -66,7 +67,8 @@ extern "C" int rsn_field_backward(const void* wblob_t, const void* x_stash, int 
   p.wblob_t = (const uint8_t*)wblob_t;
   p.x_stash = (const uint8_t*)x_stash;
   p.kind = KIND_BACKWARD;
-  p.debug = getenv("RSN_BWD_DEBUG") ? atoi(getenv("RSN_BWD_DEBUG")) : 0;
+  p.debug = rsn_env_int("RSN_BWD_DEBUG", 0);
+  p.n_rays_dev = n_rays_dev;
   p.mode = mode;
   p.want_area = g_area != nullptr;
   p.origins = origins;

@@ -38,7 +38,8 @@ struct BwdParams {
   const float* dirs;        // [N,3]
   const float* area;        // [N]
   const float* bins;        // [N,S+1]
-  int n_samples, n_points, n_tiles;
+  int n_samples, n_points, n_tiles;   // n_points / n_tiles: capacity when n_rays_dev is set
+  const int* n_rays_dev;    // optional device-side ray count (bounce passes): the launch covers min(*n_rays_dev, N) rays
   // NORMALS
   const uint32_t* wd_bf16;  // density head row as 128 packed bf16x2 words
   float* normals;           // [P,3]
@@ -264,7 +265,9 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_slot;
-  const int n_my_tiles = (p.n_tiles > vbid) ? (p.n_tiles - vbid + vgrid - 1) / vgrid : 0;
+  const int n_points = (int)rsn_count((int64_t)p.n_points / p.n_samples, p.n_rays_dev) * p.n_samples;
+  const int n_tiles = (n_points + TILE - 1) / TILE;
+  const int n_my_tiles = (n_tiles > vbid) ? (n_tiles - vbid + vgrid - 1) / vgrid : 0;
 
   if (warp == 0) {
     // ===================================================================== transposed-weight producer
@@ -462,7 +465,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
     for (int it = 0; it < n_my_tiles; ++it) {
       const int tile = vbid + it * vgrid;
       const int pt = tile * TILE + row;
-      const bool valid = pt < p.n_points;
+      const bool valid = pt < n_points;
       uint8_t* const dyt = (KIND == KIND_BACKWARD) ? p.dy_stash + (size_t)tile * DY_BLOCKS * BLOCK_BYTES : nullptr;
       auto dblk = [&](int b) -> uint8_t* { return dyt + (size_t)b * BLOCK_BYTES; };
       auto wait_acc = [&]() {
@@ -726,17 +729,19 @@ __global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_
 template <int KIND>
 int launch_chain(const BwdParams& p, cudaStream_t stream) {
   const size_t smem = SM_TOTAL + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RSN_CUDA(cudaFuncSetAttribute(field_chain_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RSN_CUDA(cudaFuncSetAttribute(field_chain_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> done[2];
+  RSN_CUDA(rsn_ensure_smem(field_chain_kernel<KIND, true>, (int)smem, done[0]));
   const int grid = std::min(p.n_tiles, rsn_num_sms());
-  // dY operand from TMEM by default; RSN_BWD_TS=0 selects the shared-memory (SS) form (same results bit for bit)
-  const bool ts = !(getenv("RSN_BWD_TS") && atoi(getenv("RSN_BWD_TS")) == 0);
-  if (ts) field_chain_kernel<KIND, true><<<grid, B_THREADS, smem, stream>>>(p);
-  else field_chain_kernel<KIND, false><<<grid, B_THREADS, smem, stream>>>(p);
+#ifdef RSN_DEBUG_SWITCHES
+  // RSN_BWD_TS=0 selects the shared-memory (SS) operand form (same results bit for bit; test build only)
+  if (rsn_env_int("RSN_BWD_TS", 1) == 0) {
+    RSN_CUDA(rsn_ensure_smem(field_chain_kernel<KIND, false>, (int)smem, done[1]));
+    field_chain_kernel<KIND, false><<<grid, B_THREADS, smem, stream>>>(p);
+    RSN_LAUNCH_CHECK("field_chain_kernel");
+    return 0;
+  }
+#endif
+  field_chain_kernel<KIND, true><<<grid, B_THREADS, smem, stream>>>(p);
   RSN_LAUNCH_CHECK("field_chain_kernel");
   return 0;
 }

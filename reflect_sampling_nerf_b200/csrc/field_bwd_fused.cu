@@ -5,6 +5,9 @@
 // left shared memory, and the wgrad CTAs (which walk the tiles in the same increasing order) pick them up shortly
 // after -- from L2 (126 MB, ~190 tiles of dY) rather than HBM.  The chain never waits on the wgrad and the grid is one
 // wave of <= #SM CTAs (1 CTA per SM by shared memory), so the flag spin cannot deadlock.
+// (validated, slower than the two-launch form -- 8.2 vs 6.4 ms at C2, DESIGN.md §4 -- and therefore part of the test
+// build only: -DRSN_DEBUG_SWITCHES)
+#ifdef RSN_DEBUG_SWITCHES
 #include "field_bwd_body.cuh"
 #include "field_wgrad_body.cuh"
 
@@ -47,7 +50,7 @@ extern "C" int rsn_field_backward_fused(const void* wblob_t, const void* x_stash
   p.wblob_t = (const uint8_t*)wblob_t;
   p.x_stash = (const uint8_t*)x_stash;
   p.kind = KIND_BACKWARD;
-  p.debug = getenv("RSN_BWD_DEBUG") ? atoi(getenv("RSN_BWD_DEBUG")) : 0;
+  p.debug = rsn_env_int("RSN_BWD_DEBUG", 0);
   p.mode = mode;
   p.want_area = g_area != nullptr;
   p.origins = origins;
@@ -66,18 +69,16 @@ extern "C" int rsn_field_backward_fused(const void* wblob_t, const void* x_stash
   // CTA split: chain CTAs get the SM time the chain needs relative to the wgrad's MMA + load time (measured on the
   // separate kernels at C2: chain 3.0 ms x 148, wgrad 5.5 ms HBM-bound); RSN_FUSED_CHAIN_CTAS overrides.
   const int sms = rsn_num_sms();
-  int n_chain = getenv("RSN_FUSED_CHAIN_CTAS") ? atoi(getenv("RSN_FUSED_CHAIN_CTAS")) : (sms * 54) / 100;
+  int n_chain = rsn_env_int("RSN_FUSED_CHAIN_CTAS", (sms * 54) / 100);
   n_chain = std::max(1, std::min(std::min(n_chain, sms - 14), p.n_tiles));
   WParams w;
   const int n_w = fill_wgrad_params(w, x_stash, dy_stash, p.n_points, grad_blob, sms - n_chain);
   RSN_CUDA(cudaMemsetAsync(workspace, 0, (size_t)p.n_tiles * sizeof(int), stream));
   const size_t smem = (size_t)std::max<size_t>(SM_TOTAL, (size_t)RING_BYTES) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RSN_CUDA(cudaFuncSetAttribute(field_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> done;
+  RSN_CUDA(rsn_ensure_smem(field_bwd_fused_kernel, (int)smem, done));
   field_bwd_fused_kernel<<<n_chain + n_w, F_THREADS, smem, stream>>>(p, w, n_chain, (int*)workspace);
   RSN_LAUNCH_CHECK("field_bwd_fused_kernel");
   return 0;
 }
+#endif  // RSN_DEBUG_SWITCHES

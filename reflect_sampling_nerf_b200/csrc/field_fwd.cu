@@ -30,37 +30,34 @@
 #include "rsn_common.cuh"
 #include "umma.cuh"
 #include "field_layout.cuh"
+#include "encodings.cuh"
 #include <algorithm>
 #include <type_traits>
 #include <stdlib.h>
+#include <atomic>
 
 namespace {
 
 using namespace umma;
 using namespace rsnf;
+using namespace rsnenc;
 
 constexpr int NUM_STAGES = 3;
 constexpr int SMEM_ENC = 0;                                    // 2 buffers x 2 blocks
 constexpr int SMEM_ACT = 4 * BLOCK_BYTES;                      // 4 blocks (TS inference: two more ring stages)
 constexpr int SMEM_W = SMEM_ACT + 4 * BLOCK_BYTES;             // ring
 constexpr int SMEM_BARS = SMEM_W + NUM_STAGES * W_STAGE_BYTES;   // 229,376: mbarriers (256 B)
-constexpr int SMEM_BIAS = SMEM_BARS + 256;                       // 2 x 1 KB: fp32 bias of the current / next wide layer
-constexpr int SMEM_TOTAL = SMEM_BIAS + 2 * 1024;                 // 231,680 of the 232,448 a CTA may have
+// two bias slots: [0, 1024) fp32 bias of a wide layer | [1024, 1088) the 16 head biases (arrive with the bottleneck layer's)
+// | [1088, 1152) the rgb layer's (arrive with the mid layer's)
+constexpr int BIAS_SLOT_BYTES = 1152;
+constexpr int SMEM_BIAS = SMEM_BARS + 256;
+constexpr int SMEM_TOTAL = SMEM_BIAS + 2 * BIAS_SLOT_BYTES;      // 231,936 of the 232,448 a CTA may have
 constexpr int WIDE_LAYERS = 10;                                  // per tile: base 0..7, bottleneck, mid
 constexpr int NUM_THREADS = 320;
 
-// 2 ** torch.linspace(0, 16, 16) in fp32, bit for bit (NeRFEncoding, reflect_sampling_nerf_model.py:98-100)
-__constant__ float c_freq[16] = {
-    0x1.0000000000000p+0f,  0x1.0c1b780000000p+1f,  0x1.18c9880000000p+2f,  0x1.26111c0000000p+3f,
-    0x1.33f9760000000p+4f,  0x1.428a320000000p+5f,  0x1.51cb4e0000000p+6f,  0x1.61c5140000000p+7f,
-    0x1.7280340000000p+8f,  0x1.8405f60000000p+9f,  0x1.965fde0000000p+10f, 0x1.a998080000000p+11f,
-    0x1.bdb8d20000000p+12f, 0x1.d2cd4c0000000p+13f, 0x1.e8e1020000000p+14f, 0x1.0000000000000p+16f};
-// Bias vector of the current launch (N_BIAS floats) in constant memory: read with compile-time offsets by the heads and
-// the rgb layer (once per tile each), and with run-time offsets by the CTA-pair form.  The wide layers of the default form
-// take their bias from the two-slot shared-memory buffer instead (SMEM_BIAS): an indexed LDC of a 10 KB table that cycles
-// once per tile was the forward's bottleneck.  Refilled device-to-device, stream-ordered, by every
-// rsn_field_forward call, so it carries no state between calls.
-__constant__ float4 c_bias4[N_BIAS / 4];
+// (Biases never live in __constant__ memory: every layer's fp32 bias reaches the epilogue through a two-slot shared-memory
+// buffer filled by bulk copies from the caller's bias vector, so two launches with different parameters on two streams
+// share no state -- and an indexed LDC of a 10 KB table that cycles once per tile was the forward's bottleneck)
 const float h_freq[16] = {
     0x1.0000000000000p+0f,  0x1.0c1b780000000p+1f,  0x1.18c9880000000p+2f,  0x1.26111c0000000p+3f,
     0x1.33f9760000000p+4f,  0x1.428a320000000p+5f,  0x1.51cb4e0000000p+6f,  0x1.61c5140000000p+7f,
@@ -75,25 +72,29 @@ struct FwdParams {
   const float* dirs;        // [N,3]
   const float* area;        // [N] pixel_area (mode 0) | sqradius (mode 1)
   const float* bins;        // [N,S+1] euclidean bins (mode 0)
-  int n_samples;            // S (mode 1: 1)
-  int n_points;             // P = N*S
+  int n_samples;            // S (mode 1, 2: 1)
+  int n_points;             // P = N*S (capacity when n_rays_dev is set)
   int n_tiles;
+  const int* n_rays_dev;    // optional device-side ray count: the launch covers min(*n_rays_dev, N) rays
+  // mode 2 (the Field method API, field.py:122-186): one point per "ray" with a caller-supplied Gaussian
+  const float* pt_mean;     // [P,3]   (contracted) mean
+  const float* pt_cov;      // [P,3,3] (contracted) covariance; only its diagonal is read (NeRFEncoding, App. A.4)
+  const float* pt_rho;      // [P] roughness fed to the IDE instead of softplus(roughness head), or NULL
   float* sigma;             // [P]
   float* feat;              // [P][16]
   uint8_t* stash;           // training: [n_tiles][STASH_BLOCKS][16 KB] activation block images, or NULL
-  float* aux;               // training: [P][8] = mid rgb (3), raw normal head (3), 2 spare, or NULL
-  int debug;                // RSN_FWD_DEBUG (timing experiments only): 2 = no trig in the prologue, 4 = no weight streaming, 8 = no stash bulk stores (TS form)
+  float* aux;               // training: [P][8] = mid rgb (3), raw normal head (3), raw roughness head, 1 spare, or NULL
+  int debug;                // RSN_FWD_DEBUG (test build only; timing experiments): 2 = no trig in the prologue, 4 = no weight streaming, 8 = no stash bulk stores (TS form)
 };
 
 constexpr int MAX_STAGES = 6;
 struct Barriers {
   uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
-  uint64_t w_peer[MAX_STAGES];   // CTA pair, leader only: the peer CTA's half of the stage has landed
   uint64_t enc_full[2], enc_empty[2];
   uint64_t act_ready[4];
   uint64_t ide_ready;
   uint64_t acc_full[2];
-  uint64_t bias_full[2];         // single CTA: the bias slot (wide layer j -> slot j & 1) has landed
+  uint64_t bias_full[2];         // the bias slot (wide layer j -> slot j & 1) has landed
   uint32_t tmem_slot;
 };
 static_assert(sizeof(Barriers) <= 256, "Barriers must fit their shared-memory slot");
@@ -112,16 +113,6 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// sin of an fp32 argument of any magnitude the encoding produces (|s| <= 2pi * 2 * 65536): two-term
-// Cody-Waite reduction by 2pi (exact products through fma), then the SFU on [-pi, pi].  Absolute error
-// < 1e-6, far below the bf16 resolution of the feature it feeds.
-__device__ __forceinline__ float sin_reduced(float s) {
-  const float k = rintf(s * 0.15915494309189535f);
-  float r = fmaf(-k, 0x1.921fb60000000p+2f, s);
-  r = fmaf(-k, -0x1.777a5cp-23f, r);
-  return __sinf(r);
-}
-
 // 8 encoded columns -> one 16-byte chunk of the row
 __device__ __forceinline__ void store_chunk(uint32_t row_saddr, int row, int chunk, const float (&f)[8]) {
   sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
@@ -211,11 +202,7 @@ __device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const fl
         float f8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float f = c_freq[kk * 8 + i];
-          float s = __fmul_rn(sx, f);
-          if (half) s = __fadd_rn(s, 1.5707963705062866f);
-          const float e = 0.5f * (va * (f * f));
-          f8[i] = (e < 24.f) ? __expf(-e) * sin_reduced(s) : 0.f;
+          f8[i] = ipe_value(sx, va, c_freq[kk * 8 + i], half);
         }
         const int j = half * 6 + a * 2 + kk;  // 16-byte chunk index along the 112 columns
         store_chunk(row0 + (uint32_t)(j >> 3) * BLOCK_BYTES, row, j & 7, f8);
@@ -232,69 +219,14 @@ __device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const fl
   }
 }
 
-// ---------------------------------------------------------------------------------------------- IDE
-// IntegratedSHEncoding.pytorch_fwd (components.py:52-140): 34 hand-expanded polynomials for l = 1,2,4,8 with
-// the reference's constants (entries 17/18/32 keep 5.8314...), each band attenuated by
-// exp(-rho l(l+1)/2) = exp(-rho {1,3,10,36}).
-__device__ __forceinline__ void ide_features(const float d[3], float rho, float (&t)[48]) {
-  const float x = d[0], y = d[1], z = d[2];
-  const float x2 = x * x, y2 = y * y, z2 = z * z;
-  const float xy = x * y, xz = x * z, yz = y * z;
-  const float dxy = x2 - y2;
-  const float a = 3.f * x2 - y2, b = x2 - 3.f * y2;
-  const float z4 = z2 * z2, x4 = x2 * x2, y4 = y2 * y2;
-  const float p = y4 - 10.f * x2 * y2 + 5.f * x4;
-  const float q = x4 - 10.f * x2 * y2 + 5.f * y4;
-  const float r = (x2 - 5.f * y2) * 7.f * x4 + (21.f * x2 - y2) * y4;
-  const float s = (x2 - 21.f * y2) * x4 + (5.f * x2 - y2) * 7.f * y4;
-  const float e1 = __expf(-rho), e2 = __expf(-3.f * rho), e4 = __expf(-10.f * rho), e8 = __expf(-36.f * rho);
-  const float c1 = 0.48860251190291992f;
-  t[0] = e1 * c1 * y;
-  t[1] = e1 * c1 * z;
-  t[2] = e1 * c1 * x;
-  t[3] = e2 * 1.09254843059207907f * xy;
-  t[4] = e2 * 1.09254843059207907f * yz;
-  t[5] = e2 * 0.31539156525252001f * (3.f * z2 - 1.f);
-  t[6] = e2 * 1.09254843059207907f * xz;
-  t[7] = e2 * 0.54627421529603953f * dxy;
-  t[8] = e4 * 2.50334294179670453f * xy * dxy;
-  t[9] = e4 * 1.77013076977993053f * yz * a;
-  t[10] = e4 * 0.94617469575756001f * xy * (7.f * z2 - 1.f);
-  t[11] = e4 * 0.66904654355728916f * yz * (7.f * z2 - 3.f);
-  t[12] = e4 * 0.1057855469152043038f * (35.f * z4 - 30.f * z2 + 3.f);
-  t[13] = e4 * 0.66904654355728916f * xz * (7.f * z2 - 3.f);
-  t[14] = e4 * 0.473087347878780009f * dxy * (7.f * z2 - 1.f);
-  t[15] = e4 * 1.77013076977993053f * xz * b;
-  t[16] = e4 * 0.62583573544917613f * (x2 * b - y2 * a);
-  t[17] = e8 * 5.83141328139863895f * xy * (x2 * x4 - 7.f * x4 * y2 + 7.f * x2 * y4 - y2 * y4);
-  t[18] = e8 * 5.83141328139863895f * yz * r;
-  t[19] = e8 * 1.06466553211908514f * xy * (15.f * z2 - 1.f) * (3.f * x4 - 10.f * x2 * y2 + 3.f * y4);
-  t[20] = e8 * 3.44991062209810801f * yz * (5.f * z2 - 1.f) * p;
-  t[21] = e8 * 1.91366609903732278f * xy * (65.f * z4 - 26.f * z2 + 1.f) * dxy;
-  t[22] = e8 * 1.23526615529554407f * yz * (39.f * z4 - 26.f * z2 + 3.f) * a;
-  t[23] = e8 * 0.91230451686981894f * xy * (143.f * z4 * z2 - 143.f * z4 + 33.f * z2 - 1.f);
-  t[24] = e8 * 0.1090412458987799555f * yz * (715.f * z4 * z2 - 1001.f * z4 + 385.f * z2 - 35.f);
-  t[25] = e8 * 0.0090867704915649962938f * (6435.f * z4 * z4 - 12012.f * z4 * z2 + 6930.f * z4 - 1260.f * z2 + 35.f);
-  t[26] = e8 * 0.1090412458987799555f * xz * (715.f * z4 * z2 - 1001.f * z4 + 385.f * z2 - 35.f);
-  t[27] = e8 * 0.456152258434909470f * (143.f * z4 * z2 - 143.f * z4 + 33.f * z2 - 1.f) * dxy;
-  t[28] = e8 * 1.23526615529554407f * xz * (39.f * z4 - 26.f * z2 + 3.f) * b;
-  t[29] = e8 * 0.478416524759330697f * (65.f * z4 - 26.f * z2 + 1.f) * (x2 * b - y2 * a);
-  t[30] = e8 * 3.44991062209810801f * xz * (5.f * z2 - 1.f) * q;
-  t[31] = e8 * 0.53233276605954257f * (15.f * z2 - 1.f) * (x2 * q - y2 * p);
-  t[32] = e8 * 5.83141328139863895f * xz * s;
-  t[33] = e8 * 0.72892666017482986f * (x2 * s - y2 * r);
-#pragma unroll
-  for (int i = 34; i < 48; ++i) t[i] = 0.f;
-}
-
 // ---------------------------------------------------------------------------------------------- epilogue
 // 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> activation block `blk`.
 // MASKS (training): also emit the ReLU bit masks of the group (a separate instantiation, so that the inference path keeps
 // its branch-free schedule: a runtime test of the mask pointer inside the chunk loop cost 0.47 ms of 2.62 at C2)
-// SBIAS: the 64 biases come from shared memory (bias_saddr; every lane reads the same 16 bytes: one broadcast
-// wavefront per load) instead of constant memory (bias_off).  The constant path is an INDEXED load (the layer is a
-// run-time value) of a 10 KB table that cycles once per tile: 32 LDC per group, 0.5 ms of 2.66 at C2 (measured by
-// replacing the bias with a register constant).
+// The 64 biases come from shared memory (bias_saddr; every lane reads the same 16 bytes: one broadcast wavefront per
+// load).  (A __constant__ table was an INDEXED load -- the layer is a run-time value -- of 10 KB that cycles once per
+// tile: 32 LDC per group, 0.5 ms of 2.66 at C2, measured by replacing the bias with a register constant.)  SBIAS is kept
+// as a template parameter for the call sites' readability; it is always true.
 // TS: the packed row also goes back into TMEM (columns a_taddr..+31) as the next layer's A operand; SMEM: it is written to
 // the shared-memory block (the A operand of the SS form and / or the staging copy of the activation stash).
 // DEFER (TS + stash): the MMA does not read the shared-memory copy, so the row is handed to the next layer first
@@ -318,12 +250,9 @@ __device__ __forceinline__ void epilogue_group_core(uint32_t tmem_row_col, int b
   float4 b[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    if (SBIAS)
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(b[i].x), "=f"(b[i].y), "=f"(b[i].z), "=f"(b[i].w)
-                   : "r"(bias_saddr + (uint32_t)i * 16u));
-    else
-      b[i] = c_bias4[(bias_off >> 2) + i];
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(b[i].x), "=f"(b[i].y), "=f"(b[i].z), "=f"(b[i].w)
+                 : "r"(bias_saddr + (uint32_t)i * 16u));
   }
   tmem_ld_wait();
   const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
@@ -413,35 +342,26 @@ __device__ __forceinline__ void stage_row(const uint32_t (&a)[32], uint32_t blk_
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------- kernel
-// PAIR = true: the kernel runs as 2-CTA clusters (tcgen05 cta_group::2).  CTA r of a pair owns its own 128-point
-// tile (prologue, epilogue, activations, TMEM accumulators) and stages rows [r N/2, (r+1) N/2) of every weight
-// chunk; the leader (r = 0) issues M = 256 MMAs for both.  Per SM and layer this halves the weight bytes written
-// into shared memory and the B-operand bytes read back by the tensor core (384 KB -> 256 KB of shared-memory
-// traffic against 2048 MMA cycles at 128 B/cycle): the single-CTA form is shared-memory-bandwidth bound.
-// TS = true (single CTA only): the hidden activations never touch shared memory on the MMA path.  The epilogue writes
-// layer l's bf16 output with tcgen05.st over the first 128 columns of the accumulator it has just read, and layer l+1
-// takes its A operand from there (tcgen05.mma [d], [a], b-desc) while accumulating into the other buffer.  Per layer
-// this removes the A-operand reads (64 of 192 KB) and, outside training, the activation writes (64 KB) from the
-// shared-memory pipe.  The encodings (IPE, IDE) still arrive through shared memory.
-// MC = true: 2-CTA clusters that share only the WEIGHT STREAM.  Each CTA is a complete single-CTA pipeline (own tile,
-// own cta_group::1 MMAs, own TMEM); CTA r fetches half r of every weight chunk and multicasts it into both CTAs' ring
-// slots, so the bytes pulled out of L2 per point halve.  The only coupling is the ring: a slot is refilled once both
-// CTAs' MMAs have released it (w_empty counts two multicast commits).
-template <bool PAIR, bool TS, bool MC = false>
+// TS = true (default): the hidden activations never touch shared memory on the MMA path.  The epilogue writes layer l's
+// bf16 output with tcgen05.st over the first 128 columns of the accumulator it has just read, and layer l+1 takes its A
+// operand from there (tcgen05.mma [d], [a], b-desc) while accumulating into the other buffer.  Per layer this removes the
+// A-operand reads (64 of 192 KB) and, outside training, the activation writes (64 KB) from the shared-memory pipe.  The
+// encodings (IPE, IDE) still arrive through shared memory.  TS = false (test build only, RSN_FWD_TS=0): the operand is
+// written in place into the swizzled shared-memory activation blocks (bit-identical results).
+// (The cta_group::2 CTA-pair form and the cluster-multicast weight stream of round 1 were validated bit for bit and
+// lost -- 2.86 vs 2.63 ms and no change, DESIGN.md §4 -- and are no longer part of this kernel; their building blocks stay
+// in umma.cuh and csrc/probe.cu.)
+template <bool TS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdParams p) {
-  static_assert(!(PAIR && TS), "the A-from-TMEM form is single-CTA");
-  static_assert(!(PAIR && MC), "MC pairs CTAs for the weight stream only");
-  constexpr bool CL = PAIR || MC;   // launched as 2-CTA clusters
   extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the window starts here
   Barriers& bars = *reinterpret_cast<Barriers*>(smem + SMEM_BARS);
-  constexpr bool SBIAS = !PAIR;   // the pair form keeps the constant-memory bias (its issuer serves two CTAs)
-  // weight ring: 3 x 32 KB; CTA pair: 6 x 16 KB; TS without a stash: the activation blocks are free -> 5 x 32 KB
-  const int NS = PAIR ? 6 : ((TS && !p.stash) ? 5 : NUM_STAGES);
+  constexpr bool SBIAS = true;
+  // weight ring: 3 x 32 KB; TS without a stash: the activation blocks are free -> 5 x 32 KB
+  const int NS = (TS && !p.stash) ? 5 : NUM_STAGES;
   const int ring_off = (TS && !p.stash) ? SMEM_ACT : SMEM_W;
-  constexpr uint32_t STB = PAIR ? W_STAGE_BYTES / 2 : W_STAGE_BYTES;
-  constexpr uint32_t ARRIVALS = PAIR ? 8 : TILE;                  // PAIR: one arrival per warp, both CTAs
+  constexpr uint32_t STB = W_STAGE_BYTES;
+  constexpr uint32_t ARRIVALS = TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = CL ? cluster_ctarank() : 0u;
   const uint32_t s_act = smem_u32(smem + SMEM_ACT);
   const uint32_t s_enc = smem_u32(smem + SMEM_ENC);
   const uint32_t s_w = smem_u32(smem + ring_off);
@@ -450,13 +370,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     if (threadIdx.x == 0) printf("rsn_b200: field_fwd_kernel: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
+  // valid points of this launch: the host's count, or rays counted on the device (bounce passes)
+  const int n_points = (int)rsn_count((int64_t)p.n_points / p.n_samples, p.n_rays_dev) * p.n_samples;
+  const int n_tiles = (n_points + TILE - 1) / TILE;
 
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < MAX_STAGES; ++i) {
         mbar_init(&bars.w_full[i], 1);
-        mbar_init(&bars.w_empty[i], MC ? 2 : 1);
-        mbar_init(&bars.w_peer[i], 1);
+        mbar_init(&bars.w_empty[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars.enc_full[i], ARRIVALS);
@@ -469,29 +391,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       fence_barrier_init();
     }
     __syncwarp();
-    if (PAIR) tmem_alloc_2cta(&bars.tmem_slot, 512); else tmem_alloc(&bars.tmem_slot, 512);
+    tmem_alloc(&bars.tmem_slot, 512);
   }
   tc_fence_before();
-  if (CL) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_slot;
-  // tiles of this CTA: single CTA: blockIdx.x + it * gridDim.x; pair q of Q: 2 (q + it Q) + rank (the last may be void)
-  const int n_units = CL ? (p.n_tiles + 1) / 2 : p.n_tiles;
-  const int unit0 = CL ? (int)blockIdx.x / 2 : (int)blockIdx.x;
-  const int n_workers = CL ? (int)gridDim.x / 2 : (int)gridDim.x;
-  const int n_my_tiles = (n_units > unit0) ? (n_units - unit0 + n_workers - 1) / n_workers : 0;
-  auto tile_of = [&](int it) -> int { return CL ? 2 * (unit0 + it * n_workers) + (int)rank : unit0 + it * n_workers; };
-  // signal a barrier of the MMA issuer (in the leader CTA of a pair)
-  auto arrive_issuer = [&](uint64_t* bar) {
-    if (!PAIR) {
-      mbar_arrive(bar);
-    } else {
-      __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0);
-      }
-    }
-  };
+  // tiles of this CTA: blockIdx.x + it * gridDim.x
+  const int n_my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto tile_of = [&](int it) -> int { return (int)blockIdx.x + it * (int)gridDim.x; };
+  auto arrive_issuer = [&](uint64_t* bar) { mbar_arrive(bar); };
 
   if (warp == 0) {
     // ===================================================================== weight producer
@@ -503,23 +412,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         for (int c = 0; c < N_FWD_CHUNKS; ++c) {
           const uint32_t bytes = fwd_chunk_bytes(c);
           mbar_wait(&bars.w_empty[stage], phase ^ 1);
-          if (!PAIR && (p.debug & 4)) {
+          if (p.debug & 4) {
             mbar_arrive(&bars.w_full[stage]);     // timing experiment: no weight traffic at all (results are garbage)
-          } else if (MC) {
-            // my half of the chunk into both CTAs' slots; my barrier expects the whole chunk (the other half arrives
-            // from the peer's multicast -- possibly before this expect_tx, which the transaction count tolerates)
-            mbar_expect_tx(&bars.w_full[stage], bytes);
-            bulk_g2s_multicast(smem + ring_off + stage * STB + rank * (bytes / 2), p.wblob + off + rank * (bytes / 2),
-                               bytes / 2, &bars.w_full[stage], (uint16_t)3);
-          } else if (!PAIR) {
+          } else {
             mbar_expect_tx(&bars.w_full[stage], bytes);
             bulk_g2s(smem + ring_off + stage * STB, p.wblob + off, bytes, &bars.w_full[stage]);
-          } else {
-            mbar_expect_tx(&bars.w_full[stage], bytes / 2);
-            const uint32_t half = (uint32_t)fwd_chunk_rows(c) * 64u;     // (rows / 2) * 128 bytes per K-block
-            for (int kb = 0; kb < fwd_chunk_nkb(c); ++kb)
-              bulk_g2s(smem + ring_off + stage * STB + kb * half, p.wblob + off + kb * 2 * half + rank * half, half,
-                       &bars.w_full[stage]);
           }
           off += bytes;
           if (++stage == NS) {
@@ -529,21 +426,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         }
       }
     }
-  } else if (warp == 1 && PAIR && rank == 1) {
-    // ===================================================================== peer relay: "my half of the stage landed"
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < n_my_tiles; ++it)
-        for (int c = 0; c < N_FWD_CHUNKS; ++c) {
-          mbar_wait(&bars.w_full[stage], phase);
-          mbar_arrive_remote(&bars.w_peer[stage], 0);
-          if (++stage == NS) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-    }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
@@ -551,26 +433,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       uint32_t wphase = 0;
       uint32_t ar_phase = 0;  // bit g: parity of the next completion of act_ready[g]
       int buf = 0;
-      constexpr int MM = PAIR ? 256 : 128;
+      constexpr int MM = 128;
       constexpr uint32_t ID256 = instr_desc_bf16(MM, 256, 0, 0);
       constexpr uint32_t ID128 = instr_desc_bf16(MM, 128, 0, 0);
       constexpr uint32_t ID16 = instr_desc_bf16(MM, 16, 0, 0);
-      constexpr uint32_t BDIV = PAIR ? 2 : 1;     // a CTA of a pair holds half of the rows of every B K-block
-      auto commit = [&](uint64_t* bar) {
-        if (PAIR) mma_commit_2cta(bar); else mma_commit(bar);
-      };
-      // Barriers the operand producers of BOTH CTAs arrive on.  The issuing thread never reads the peer's operands
-      // itself (the peer's tensor core does, after the peer's own fence.proxy.async), so the plain CTA-scope wait
-      // is enough -- and a cluster-scope acquire on every poll costs ~2.5k cycles per layer (measured).
+      constexpr uint32_t BDIV = 1;
+      auto commit = [&](uint64_t* bar) { mma_commit(bar); };
       auto wait_in = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
       auto ring_wait = [&]() -> uint32_t {
         mbar_wait(&bars.w_full[stage], wphase);
-        if (PAIR) mbar_wait(&bars.w_peer[stage], wphase);
         tc_fence_after();
         return s_w + (uint32_t)stage * STB;
       };
       auto ring_release = [&]() {
-        if (MC) mma_commit_multicast2(&bars.w_empty[stage]); else commit(&bars.w_empty[stage]);
+        commit(&bars.w_empty[stage]);
         if (++stage == NS) {
           stage = 0;
           wphase ^= 1;
@@ -586,8 +462,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       auto issue_kb = [&](uint32_t a_addr, uint32_t b_addr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool& acc) {
         const uint32_t a_lo = desc_lo(a_addr, 16), b_lo = desc_lo(b_addr, 16);
         auto mma = [&](uint32_t k2, uint32_t accum) {
-          if (PAIR) mma_bf16_ss_lo_2cta(tmem_d, a_lo + k2, b_lo + k2, HI, idesc, accum);
-          else mma_bf16_ss_lo(tmem_d, a_lo + k2, b_lo + k2, HI, idesc, accum);
+          mma_bf16_ss_lo(tmem_d, a_lo + k2, b_lo + k2, HI, idesc, accum);
         };
         mma(0, acc ? 1u : 0u);
         mma(2, 1u);
@@ -612,12 +487,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       // Bias of wide layer j (10 per tile) -> slot j & 1, requested as soon as the epilogue of layer j - 2 has published
       // its last group (the issuer sees that as the last act_ready wait of layer j - 1).
       auto request_bias = [&](int j) {
-        if (!SBIAS || j >= n_my_tiles * WIDE_LAYERS) return;
+        if (j >= n_my_tiles * WIDE_LAYERS) return;
         const int jl = j % WIDE_LAYERS;
-        const int off = jl < 8 ? BIAS_BASE + jl * 256 : (jl == 8 ? BIAS_BOTT : BIAS_MID);
-        const uint32_t bytes = jl == 9 ? 512u : 1024u;
-        mbar_expect_tx(&bars.bias_full[j & 1], bytes);
-        bulk_g2s(smem + SMEM_BIAS + (j & 1) * 1024, p.bias + off, bytes, &bars.bias_full[j & 1]);
+        uint8_t* const slot = smem + SMEM_BIAS + (j & 1) * BIAS_SLOT_BYTES;
+        if (jl < 8) {
+          mbar_expect_tx(&bars.bias_full[j & 1], 1024u);
+          bulk_g2s(slot, p.bias + BIAS_BASE + jl * 256, 1024u, &bars.bias_full[j & 1]);
+        } else if (jl == 8) {   // bottleneck (256) + the 16 head biases behind it in the vector -> [0, 1088)
+          static_assert(BIAS_HEAD == BIAS_BOTT + 256, "head biases follow the bottleneck bias");
+          mbar_expect_tx(&bars.bias_full[j & 1], 1088u);
+          bulk_g2s(slot, p.bias + BIAS_BOTT, 1088u, &bars.bias_full[j & 1]);
+        } else {                // mid (128) -> [0, 512), rgb (16) -> [1088, 1152): the slot's wide part is refilled before the
+                                // rgb epilogue runs, its tail only by the next mid layer
+          mbar_expect_tx(&bars.bias_full[j & 1], 512u + 64u);
+          bulk_g2s(slot, p.bias + BIAS_MID, 512u, &bars.bias_full[j & 1]);
+          bulk_g2s(slot + 1088, p.bias + BIAS_RGB, 64u, &bars.bias_full[j & 1]);
+        }
       };
       request_bias(0);
       request_bias(1);
@@ -723,9 +608,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     int jw = 0;   // wide layers converted so far
     // bias slot of the wide layer about to be converted (waits until its bulk copy has landed)
     auto bias_slot = [&]() -> uint32_t {
-      if (!SBIAS) return 0u;
       mbar_wait(&bars.bias_full[jw & 1], (uint32_t)(jw >> 1) & 1u);
-      const uint32_t a = s_bias + (uint32_t)(jw & 1) * 1024u;
+      const uint32_t a = s_bias + (uint32_t)(jw & 1) * BIAS_SLOT_BYTES;
       ++jw;
       return a;
     };
@@ -733,8 +617,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       const int eb = it & 1;
       const int tile = tile_of(it);
       const int pt = tile * TILE + row;
-      const bool valid = pt < p.n_points;
-      uint8_t* const st = (p.stash && tile < p.n_tiles) ? p.stash + (size_t)tile * STASH_TILE_BYTES : nullptr;
+      const bool valid = pt < n_points;
+      uint8_t* const st = (p.stash && tile < n_tiles) ? p.stash + (size_t)tile * STASH_TILE_BYTES : nullptr;
       auto sblk = [&](int b) -> uint8_t* { return st ? st + (size_t)b * BLOCK_BYTES : nullptr; };
       auto wait_acc = [&]() {
         mbar_wait(&bars.acc_full[buf], (af_phase >> buf) & 1u);
@@ -838,12 +722,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         for (int g = 0; g < 4; ++g) convert(F_{}, F_{}, BIAS_BOTT, sb, g, nullptr, nullptr, false);
         uint32_t hv[16];
         tmem_ld16(tlane + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, hv);
-        float hb[16];
+        float hb[12];   // head biases: behind the bottleneck bias in this layer's slot (only this layer's request writes there)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 t4 = c_bias4[BIAS_HEAD / 4 + i];
-          hb[i * 4 + 0] = t4.x, hb[i * 4 + 1] = t4.y, hb[i * 4 + 2] = t4.z, hb[i * 4 + 3] = t4.w;
-        }
+        for (int i = 0; i < 3; ++i)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(hb[i * 4 + 0]), "=f"(hb[i * 4 + 1]), "=f"(hb[i * 4 + 2]), "=f"(hb[i * 4 + 3])
+                       : "r"(sb + 1024u + (uint32_t)i * 16u));
         tmem_ld_wait();
         float h[11];
 #pragma unroll
@@ -875,8 +759,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         }
         // IDE of the VIEW direction (App. B Q1) -> first 48 columns of this tile's enc block 0
         float t[48];
-        if (p.mode == 0) {
-          ide_features(d, rough_sp, t);
+        if (p.mode != 1) {
+          ide_features(d, (p.pt_rho && valid) ? __ldg(p.pt_rho + pt) : rough_sp, t);
         } else {
 #pragma unroll
           for (int i = 0; i < 48; ++i) t[i] = 0.f;  // get_inf_color feeds a zero IDE (field.py:199)
@@ -899,6 +783,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           p.aux[(size_t)pt * 8 + 3] = h[1];
           p.aux[(size_t)pt * 8 + 4] = h[2];
           p.aux[(size_t)pt * 8 + 5] = h[3];
+          p.aux[(size_t)pt * 8 + 6] = h[4];   // raw roughness head (Field.get_roughness with an arbitrary activation)
         }
         if (valid) {
           p.sigma[pt] = sigma;
@@ -926,7 +811,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         uint32_t rv[16];
         tmem_ld16(tlane + (uint32_t)buf * 256, rv);
-        const float4 rb = c_bias4[BIAS_RGB / 4];
+        float4 rb;      // rgb bias: tail of the mid layer's slot (slot 1 of every tile: WIDE_LAYERS is even)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(rb.x), "=f"(rb.y), "=f"(rb.z), "=f"(rb.w)
+                     : "r"(s_bias + BIAS_SLOT_BYTES + 1088u));
         tmem_ld_wait();
         tc_fence_before();
         const float mid[3] = {sigmoid_acc(__uint_as_float(rv[0]) + rb.x), sigmoid_acc(__uint_as_float(rv[1]) + rb.y),
@@ -934,7 +822,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         if (valid) {
           float rgb[3];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) rgb[a] = (p.mode == 0) ? diff[a] + tint[a] * mid[a] : mid[a];
+          for (int a = 0; a < 3; ++a) rgb[a] = (p.mode != 1) ? diff[a] + tint[a] * mid[a] : mid[a];
           float4* fo = reinterpret_cast<float4*>(p.feat + (size_t)pt * N_FEAT);
           fo[0] = make_float4(rgb[0], rgb[1], rgb[2], diff[0]);  // cols 0..3
           if (p.aux) {
@@ -953,9 +841,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       const int eb = it & 1;
       const int tile = tile_of(it);
       const int pt = tile * TILE + row;
-      const bool stash_on = p.stash && tile < p.n_tiles;
+      const bool stash_on = p.stash && tile < n_tiles;
       float xm[3] = {0.f, 0.f, 0.f}, dg[3] = {0.f, 0.f, 0.f};
-      if (pt < p.n_points) {
+      if (pt < n_points) {
         if (p.mode == 0) {
           const int ray = pt / p.n_samples;
           const int s = pt - ray * p.n_samples;
@@ -967,6 +855,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           }
           const float* b = p.bins + (size_t)ray * (p.n_samples + 1) + s;
           frustum_gaussian_contracted(o, d, __ldg(b), __ldg(b + 1), __ldg(p.area + ray), xm, dg);
+        } else if (p.mode == 2) {
+          // Field.get_density(mean, cov) on caller-supplied Gaussians (field.py:122-137): the encoding reads diag(cov) only
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            xm[a] = __ldg(p.pt_mean + (size_t)pt * 3 + a);
+            dg[a] = __ldg(p.pt_cov + (size_t)pt * 9 + a * 4);
+          }
         } else {
           // get_inf_color (field.py:190-201): mean = 2 w, cov = 0.6 sqradius (I - w w^T), NOT contracted
           const float sq = __fmul_rn(0.6f, __ldg(p.area + pt));
@@ -1004,10 +899,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
 
   if (p.stash && lane == 0 && warp >= 2) bulk_wait_all<0>();
   tc_fence_before();
-  if (CL) cluster_sync_all(); else __syncthreads();
-  if (warp == 1) {
-    if (PAIR) tmem_dealloc_2cta(tmem, 512); else tmem_dealloc(tmem, 512);
-  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -1025,10 +918,34 @@ extern "C" int64_t rsn_field_stash_bytes(int64_t n_points) {
   return ((n_points + TILE - 1) / TILE) * (int64_t)STASH_TILE_BYTES;
 }
 
+namespace {
+std::atomic<unsigned long long> g_fwd_smem_done[2];
+
+int launch_fwd(FwdParams& p, cudaStream_t stream) {
+  p.n_tiles = (p.n_points + TILE - 1) / TILE;
+  p.debug = rsn_env_int("RSN_FWD_DEBUG", 0);
+  const size_t smem = SMEM_TOTAL;
+  RSN_CUDA(rsn_ensure_smem(field_fwd_kernel<true>, (int)smem, g_fwd_smem_done[0]));
+  const int grid = std::min(p.n_tiles, rsn_num_sms());
+#ifdef RSN_DEBUG_SWITCHES
+  // RSN_FWD_TS=0 selects the shared-memory (SS) operand form (same results bit for bit; test build only)
+  if (rsn_env_int("RSN_FWD_TS", 1) == 0) {
+    RSN_CUDA(rsn_ensure_smem(field_fwd_kernel<false>, (int)smem, g_fwd_smem_done[1]));
+    field_fwd_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
+    RSN_LAUNCH_CHECK("field_fwd_kernel");
+    return 0;
+  }
+#endif
+  field_fwd_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(p);
+  RSN_LAUNCH_CHECK("field_fwd_kernel");
+  return 0;
+}
+}  // namespace
+
 extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int mode, const float* origins,
                                        const float* dirs, const float* area, const float* bins, int64_t n_rays,
                                        int64_t n_samples, float* sigma, float* feat, void* stash, float* aux,
-                                       cudaStream_t stream) {
+                                       const int* n_rays_dev, cudaStream_t stream) {
   RSN_ARG(mode == 0 || mode == 1, "rsn_field_forward: mode must be 0 (samples) or 1 (infinity colour)");
   RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_field_forward: bad shape");
   RSN_ARG(mode == 0 || n_samples == 1, "rsn_field_forward: mode 1 takes one point per ray");
@@ -1038,7 +955,8 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
   RSN_ARG(mode == 1 || (origins && bins), "rsn_field_forward: origins/bins required in mode 0");
   RSN_ARG(((uintptr_t)wblob & 15) == 0 && ((uintptr_t)bias & 15) == 0 && ((uintptr_t)feat & 15) == 0,
           "rsn_field_forward: wblob/bias/feat must be 16-byte aligned");
-  FwdParams p;
+  RSN_ARG(((uintptr_t)stash & 15) == 0, "rsn_field_forward: stash must be 16-byte aligned");
+  FwdParams p = {};
   p.wblob = (const uint8_t*)wblob;
   p.bias = bias;
   p.mode = mode;
@@ -1048,58 +966,43 @@ extern "C" int rsn_field_forward_train(const void* wblob, const float* bias, int
   p.bins = bins;
   p.n_samples = (int)n_samples;
   p.n_points = (int)(n_rays * n_samples);
-  p.n_tiles = (p.n_points + TILE - 1) / TILE;
+  p.n_rays_dev = n_rays_dev;
   p.sigma = sigma;
   p.feat = feat;
   p.stash = (uint8_t*)stash;
   p.aux = aux;
-  p.debug = getenv("RSN_FWD_DEBUG") ? atoi(getenv("RSN_FWD_DEBUG")) : 0;
-  RSN_ARG(((uintptr_t)stash & 15) == 0, "rsn_field_forward: stash must be 16-byte aligned");
-  const size_t smem = SMEM_TOTAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RSN_CUDA(cudaFuncSetAttribute(field_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  RSN_CUDA(cudaMemcpyToSymbolAsync(c_bias4, bias, N_BIAS * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
-  // CTA pairs (cta_group::2) are opt-in (RSN_FWD_PAIR=1): validated bit-for-bit against the single-CTA form, but with
-  // one tile in flight per CTA the two cross-CTA hops per layer (commit multicast -> peer epilogue -> remote arrive
-  // -> issuer) cost what the halved shared-memory traffic saves: 2.86 ms vs 2.63 ms at C2.
-  const bool pair = p.n_tiles > 1 && getenv("RSN_FWD_PAIR") && atoi(getenv("RSN_FWD_PAIR")) == 1;
-  const bool mc = !pair && p.n_tiles > 1 && getenv("RSN_FWD_MC") && atoi(getenv("RSN_FWD_MC")) == 1;
-  if (!pair && !mc) {
-    const int grid = std::min(p.n_tiles, rsn_num_sms());
-    // A-from-TMEM form by default; RSN_FWD_TS=0 selects the shared-memory (SS) form (same results bit for bit)
-    const bool ts = !(getenv("RSN_FWD_TS") && atoi(getenv("RSN_FWD_TS")) == 0);
-    if (ts) field_fwd_kernel<false, true><<<grid, NUM_THREADS, smem, stream>>>(p);
-    else field_fwd_kernel<false, false><<<grid, NUM_THREADS, smem, stream>>>(p);
-  } else {
-    const int pairs = std::min((p.n_tiles + 1) / 2, rsn_num_sms() / 2);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (mc) RSN_CUDA(cudaLaunchKernelEx(&cfg, field_fwd_kernel<false, true, true>, p));
-    else RSN_CUDA(cudaLaunchKernelEx(&cfg, field_fwd_kernel<true, false>, p));
-  }
-  RSN_LAUNCH_CHECK("field_fwd_kernel");
-  return 0;
+  return launch_fwd(p, stream);
 }
 
 extern "C" int rsn_field_forward(const void* wblob, const float* bias, int mode, const float* origins,
                                  const float* dirs, const float* area, const float* bins, int64_t n_rays,
-                                 int64_t n_samples, float* sigma, float* feat, cudaStream_t stream) {
+                                 int64_t n_samples, float* sigma, float* feat, const int* n_rays_dev,
+                                 cudaStream_t stream) {
   return rsn_field_forward_train(wblob, bias, mode, origins, dirs, area, bins, n_rays, n_samples, sigma, feat,
-                                 nullptr, nullptr, stream);
+                                 nullptr, nullptr, n_rays_dev, stream);
+}
+
+extern "C" int rsn_field_forward_points(const void* wblob, const float* bias, const float* mean, const float* cov,
+                                        const float* dirs, const float* rho_override, int64_t n_points, float* sigma,
+                                        float* feat, float* aux, cudaStream_t stream) {
+  RSN_ARG(n_points >= 0, "rsn_field_forward_points: bad shape");
+  if (n_points == 0) return 0;
+  RSN_ARG(n_points < (int64_t)2147483647 - TILE, "rsn_field_forward_points: more than 2^31 points in one call");
+  RSN_ARG(wblob && bias && mean && cov && dirs && sigma && feat, "rsn_field_forward_points: null pointer");
+  RSN_ARG(((uintptr_t)wblob & 15) == 0 && ((uintptr_t)bias & 15) == 0 && ((uintptr_t)feat & 15) == 0,
+          "rsn_field_forward_points: wblob/bias/feat must be 16-byte aligned");
+  FwdParams p = {};
+  p.wblob = (const uint8_t*)wblob;
+  p.bias = bias;
+  p.mode = 2;
+  p.dirs = dirs;
+  p.pt_mean = mean;
+  p.pt_cov = cov;
+  p.pt_rho = rho_override;
+  p.n_samples = 1;
+  p.n_points = (int)n_points;
+  p.sigma = sigma;
+  p.feat = feat;
+  p.aux = aux;
+  return launch_fwd(p, stream);
 }

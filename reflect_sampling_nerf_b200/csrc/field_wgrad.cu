@@ -108,19 +108,19 @@ extern "C" int rsn_field_wgrad_finish(float* grad_blob, const float* w_bott, con
 }
 
 extern "C" int rsn_field_wgrad(const void* x_stash, const void* dy_stash, int64_t n_points, float* grad_blob,
-                               cudaStream_t stream) {
+                               const int* n_rays_dev, int64_t points_per_ray, cudaStream_t stream) {
   RSN_ARG(n_points >= 0, "rsn_field_wgrad: bad shape");
+  RSN_ARG(!n_rays_dev || (points_per_ray >= 1 && points_per_ray < (1 << 20)), "rsn_field_wgrad: bad points_per_ray");
   if (n_points == 0) return 0;
   RSN_ARG(x_stash && dy_stash && grad_blob, "rsn_field_wgrad: null pointer");
   RSN_ARG(((uintptr_t)x_stash & 15) == 0 && ((uintptr_t)dy_stash & 15) == 0, "rsn_field_wgrad: stashes must be 16-byte aligned");
   WParams p;
   const int cta = fill_wgrad_params(p, x_stash, dy_stash, n_points, grad_blob, rsn_num_sms());
+  p.n_rays_dev = n_rays_dev;
+  p.pts_per_ray = n_rays_dev ? (int)points_per_ray : 1;
   const size_t smem = (size_t)RING_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RSN_CUDA(cudaFuncSetAttribute(field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> done;
+  RSN_CUDA(rsn_ensure_smem(field_wgrad_kernel, (int)smem, done));
   field_wgrad_kernel<<<cta, W_THREADS, smem, stream>>>(p);
   RSN_LAUNCH_CHECK("field_wgrad_kernel");
   if (p.debug & 16) {

@@ -37,10 +37,12 @@ struct WJob {
 struct WParams {
   const uint8_t* x;      // forward stash  [n_tiles][STASH_BLOCKS][16 KB]
   const uint8_t* dy;     // dgrad stash    [n_tiles][DY_BLOCKS][16 KB]
-  int n_tiles;
+  int n_tiles;           // capacity when n_rays_dev is set
+  const int* n_rays_dev; // optional device-side ray count (bounce passes): tiles = ceil(min(*n_rays_dev, rays) * pts_per_ray / 128)
+  int pts_per_ray;
   float* grad;
   int n_jobs;
-  int debug;   // RSN_WGRAD_DEBUG: 1 = MMA only (no loads, no db), 2 = loads only (no MMA)
+  int debug;   // RSN_WGRAD_DEBUG (test build only): 1 = MMA only (no loads, no db), 2 = loads only (no MMA)
   WJob jobs[MAX_JOBS];
 };
 
@@ -71,10 +73,15 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
     if (vbid >= p.jobs[i].cta_begin && vbid < p.jobs[i].cta_begin + p.jobs[i].n_ctas) j = i;
   const WJob job = p.jobs[j];
   const int split = vbid - job.cta_begin;
+  int n_tiles = p.n_tiles;
+  if (p.n_rays_dev) {
+    const int64_t pts = (int64_t)max(__ldg(p.n_rays_dev), 0) * p.pts_per_ray;
+    n_tiles = (int)min((int64_t)n_tiles, (pts + TILE - 1) / TILE);
+  }
   // tiles split, split + n_ctas, ...: the CTAs of a job stream neighbouring tiles at the same time
   const bool interleave = !(p.debug & 8);
-  const int t0 = interleave ? split : (int)(((int64_t)p.n_tiles * split) / job.n_ctas);
-  const int t1 = interleave ? p.n_tiles : (int)(((int64_t)p.n_tiles * (split + 1)) / job.n_ctas);
+  const int t0 = interleave ? split : (int)(((int64_t)n_tiles * split) / job.n_ctas);
+  const int t1 = interleave ? n_tiles : (int)(((int64_t)n_tiles * (split + 1)) / job.n_ctas);
   const int tstep = interleave ? job.n_ctas : 1;
   // mb = dY blocks loaded per slab; m_out = 64-row blocks of the accumulator (2 or 4).  mb = 3, m_out = 4: the second M=128
   // MMA reads blocks 2 and "3" = the first X block, which sits right behind the dY blocks in the stage -- its 64 output rows
@@ -285,7 +292,9 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
   p.n_tiles = (int)((n_points + TILE - 1) / TILE);
   p.grad = grad_blob;
   p.n_jobs = kNumJobs;
-  p.debug = getenv("RSN_WGRAD_DEBUG") ? atoi(getenv("RSN_WGRAD_DEBUG")) : 0;
+  p.debug = rsn_env_int("RSN_WGRAD_DEBUG", 0);
+  p.n_rays_dev = nullptr;
+  p.pts_per_ray = 1;
   int n_of[kNumJobs], used = 0;
   // CTAs per job proportional to the job's cost per tile = loaded blocks x measured relative time per block; the kernel
   // ends with the job whose CTAs carry the most, so the CTAs left over by the rounding go, one at a time, to the job with

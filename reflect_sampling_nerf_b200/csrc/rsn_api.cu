@@ -4,7 +4,7 @@
 thread_local char g_rsn_err[512] = {0};
 
 extern "C" const char* rsn_last_error(void) { return g_rsn_err; }
-extern "C" int rsn_version(void) { return 100; }  // 0.1.0
+extern "C" int rsn_version(void) { return 200; }  // 0.2.0
 extern "C" int rsn_device_ok(void) {
   int dev = 0;
   cudaDeviceProp p;

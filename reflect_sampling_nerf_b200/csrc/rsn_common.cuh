@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <atomic>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "rsn_b200 kernels are written for sm_100a (B200) only"
@@ -36,15 +38,49 @@ static inline int rsn_fail(int code, const char* fmt, ...) {
       return rsn_fail((int)e__, "%s: %s", #call, cudaGetErrorString(e__));         \
   } while (0)
 
+// SM count of the CURRENT device (cached per device id; the cache is immutable after its first, idempotent fill).
 static inline int rsn_num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::atomic<int>& slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per device (bit `dev` of
+// `done`); two threads racing on first use both set the same value.
+template <class K>
+static inline cudaError_t rsn_ensure_smem(K kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+// Experiment switches (alternative kernel forms, timing ablations whose results are wrong by design) exist only in the
+// test build (-DRSN_DEBUG_SWITCHES = librsn_b200_dbg.so); the product library never reads the environment.
+static inline int rsn_env_int(const char* name, int dflt) {
+#ifdef RSN_DEBUG_SWITCHES
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
+}
+// Number of valid rays of a launch: the host capacity `cap`, or min(cap, *dev_count) when the count lives on the device
+// (bounce passes: the number of masked rays never visits the host).
+__device__ __forceinline__ int64_t rsn_count(int64_t cap, const int* dev_count) {
+  if (dev_count == nullptr) return cap;
+  const int64_t m = (int64_t)__ldg(dev_count);
+  return m < cap ? (m < 0 ? 0 : m) : cap;
 }
 
 // ---- device helpers ---------------------------------------------------------------------------

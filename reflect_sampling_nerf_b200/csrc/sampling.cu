@@ -14,27 +14,32 @@
 
 namespace {
 
-__device__ __forceinline__ float spacing_fn(float x, int kind) {
-  // kind 1: x / (1/tan + x), tan = 0.25 -> 1/tan = 4.0 exactly
-  return kind == 0 ? x : __fdiv_rn(x, __fadd_rn(4.0f, x));
+// ReciprocalSampler (reflect_sampling_nerf_components.py:30-33): spacing_fn = x / (1/tan + x), inverse = x / tan / (1 - x);
+// the python scalars 1/tan and tan reach the fp32 tensor ops rounded to fp32 (tan = 0.25 in the model: 4.0 and 0.25 exactly)
+struct Spacing {
+  int kind;        // 0 uniform (identity), 1 reciprocal
+  float inv_tan;   // fl32(1 / tan)
+  float tan;       // fl32(tan)
+};
+__device__ __forceinline__ float spacing_fn(float x, Spacing sp) {
+  return sp.kind == 0 ? x : __fdiv_rn(x, __fadd_rn(sp.inv_tan, x));
 }
-__device__ __forceinline__ float spacing_inv(float x, int kind) {
-  // kind 1: x / tan / (1 - x)
-  return kind == 0 ? x : __fdiv_rn(__fdiv_rn(x, 0.25f), __fsub_rn(1.0f, x));
+__device__ __forceinline__ float spacing_inv(float x, Spacing sp) {
+  return sp.kind == 0 ? x : __fdiv_rn(__fdiv_rn(x, sp.tan), __fsub_rn(1.0f, x));
 }
-__device__ __forceinline__ float to_euclid(float b, float s_near, float s_far, int kind) {
+__device__ __forceinline__ float to_euclid(float b, float s_near, float s_far, Spacing sp) {
   // x * s_far + (1 - x) * s_near, each op rounded separately
   float v = __fadd_rn(__fmul_rn(b, s_far), __fmul_rn(__fsub_rn(1.0f, b), s_near));
-  return spacing_inv(v, kind);
+  return spacing_inv(v, sp);
 }
 
 // One thread per bin.  HBM-bound: 8 B written per bin (+4 B read when jitter is injected).
 __global__ void __launch_bounds__(256) sample_spaced_kernel(
     const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ lin,
-    const float* __restrict__ t_rand, int64_t t_rand_cols, int kind, float* __restrict__ spacing,
-    float* __restrict__ euclid, int64_t n_rays, int n_bins) {
+    const float* __restrict__ t_rand, int64_t t_rand_cols, Spacing kind, float* __restrict__ spacing,
+    float* __restrict__ euclid, int64_t n_rays, int n_bins, const int* __restrict__ n_rays_dev) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = n_rays * n_bins;
+  int64_t total = rsn_count(n_rays, n_rays_dev) * n_bins;
   for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = idx / n_bins;
     int i = (int)(idx - r * n_bins);
@@ -52,25 +57,35 @@ __global__ void __launch_bounds__(256) sample_spaced_kernel(
   }
 }
 
-// One warp per ray.  smem: cdf[S+1] and the existing spacing bins[S+1] per warp.
+// One warp per ray.  smem per warp: cdf[S+1], the existing spacing bins[S+1] and the ray's weights (+ histogram padding),
+// staged with coalesced loads (lane-strided) and read back by the lane that owns the sample's chunk; the staging row is
+// skewed by one word per 32 so that the chunked reads (lane stride = chunk words) hit distinct banks.  The arithmetic
+// and its order are unchanged (fp64 partial sums per lane-chunk, xor-tree, fp64 scan), so the bins stay bit-exact.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) pdf_resample_kernel(
     const float* __restrict__ weights, int64_t w_stride, const float* __restrict__ bins_in,
     const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ u_base,
-    const float* __restrict__ rand, int kind, float hist_pad, float* __restrict__ spacing_out,
-    float* __restrict__ euclid_out, int64_t* __restrict__ inds_out, int64_t n_rays, int S, int nb) {
+    const float* __restrict__ rand, Spacing kind, float hist_pad, float* __restrict__ spacing_out,
+    float* __restrict__ euclid_out, int64_t* __restrict__ inds_out, int64_t n_rays, int S, int nb,
+    const int* __restrict__ n_rays_dev) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* cdf = smem + (size_t)warp * 2 * (S + 1);
+  const int row_words = 2 * (S + 1) + S + (S >> 5) + 1;
+  float* cdf = smem + (size_t)warp * row_words;
   float* ebins = cdf + (S + 1);
+  float* wp = ebins + (S + 1);      // wp[i + (i >> 5)] = weights[i] + histogram_padding
   const int chunk = (S + 31) / 32;  // consecutive samples per lane
+  const int64_t n_valid = rsn_count(n_rays, n_rays_dev);
 
-  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < n_rays; r += (int64_t)gridDim.x * WARPS) {
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < n_valid; r += (int64_t)gridDim.x * WARPS) {
     const float* w = weights + r * w_stride;
     const int lo = lane * chunk, hi = min(S, lo + chunk);
+    for (int i = lane; i < S; i += 32) wp[i + (i >> 5)] = __fadd_rn(__ldg(w + i), hist_pad);
+    for (int i = lane; i <= S; i += 32) ebins[i] = __ldg(bins_in + r * (S + 1) + i);
+    __syncwarp();
     // weights + histogram_padding, row sum in fp64
     double part = 0.0;
-    for (int i = lo; i < hi; ++i) part += (double)__fadd_rn(__ldg(w + i), hist_pad);
+    for (int i = lo; i < hi; ++i) part += (double)wp[i + (i >> 5)];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(RSN_FULL, part, o);
     float wsum = (float)part;
@@ -80,18 +95,17 @@ __global__ void __launch_bounds__(WARPS * 32) pdf_resample_kernel(
     // pdf and its inclusive cumsum (fp64 accumulate, rounded per element), clamped at 1
     double run = 0.0;
     for (int i = lo; i < hi; ++i) {
-      float wi = __fadd_rn(__fadd_rn(__ldg(w + i), hist_pad), pad_each);
+      float wi = __fadd_rn(wp[i + (i >> 5)], pad_each);
       run += (double)__fdiv_rn(wi, wsum);
     }
     double incl = warp_incl_scan(run, lane);
     double acc = incl - run;  // exclusive offset of this lane's chunk
     for (int i = lo; i < hi; ++i) {
-      float wi = __fadd_rn(__fadd_rn(__ldg(w + i), hist_pad), pad_each);
+      float wi = __fadd_rn(wp[i + (i >> 5)], pad_each);
       acc += (double)__fdiv_rn(wi, wsum);
       cdf[i + 1] = fminf(1.0f, (float)acc);
     }
     if (lane == 0) cdf[0] = 0.0f;
-    for (int i = lane; i <= S; i += 32) ebins[i] = __ldg(bins_in + r * (S + 1) + i);
     __syncwarp();
 
     const float s_near = spacing_fn(__ldg(nears + r), kind);
@@ -121,12 +135,13 @@ __global__ void __launch_bounds__(WARPS * 32) pdf_resample_kernel(
 }  // namespace
 
 extern "C" int rsn_sample_spaced(const float* nears, const float* fars, const float* lin_bins,
-                                 const float* t_rand, int64_t t_rand_cols, int spacing_kind,
+                                 const float* t_rand, int64_t t_rand_cols, int spacing_kind, float tan,
                                  float* spacing_bins, float* euclid_bins, int64_t n_rays,
-                                 int64_t n_samples, cudaStream_t stream) {
+                                 int64_t n_samples, const int* n_rays_dev, cudaStream_t stream) {
   RSN_ARG(n_rays >= 0 && n_samples >= 1, "rsn_sample_spaced: bad shape (%lld rays, %lld samples)",
           (long long)n_rays, (long long)n_samples);
-  RSN_ARG(spacing_kind == 0 || spacing_kind == 1, "rsn_sample_spaced: spacing_kind must be 0 (uniform) or 1 (reciprocal)");
+  RSN_ARG(spacing_kind == 0 || (spacing_kind == 1 && tan > 0.f), "rsn_sample_spaced: spacing_kind must be 0 (uniform) or 1 (reciprocal, tan > 0)");
+  const Spacing sp = {spacing_kind, (float)(1.0 / (double)tan), tan};
   RSN_ARG(t_rand == nullptr || t_rand_cols == 1 || t_rand_cols == n_samples + 1,
           "rsn_sample_spaced: t_rand must have 1 or n_samples+1 columns");
   if (n_rays == 0) return 0;
@@ -134,32 +149,33 @@ extern "C" int rsn_sample_spaced(const float* nears, const float* fars, const fl
   const int n_bins = (int)n_samples + 1;
   int64_t total = n_rays * n_bins;
   int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)rsn_num_sms() * 8);
-  sample_spaced_kernel<<<blocks, 256, 0, stream>>>(nears, fars, lin_bins, t_rand, t_rand_cols, spacing_kind,
-                                                    spacing_bins, euclid_bins, n_rays, n_bins);
+  sample_spaced_kernel<<<blocks, 256, 0, stream>>>(nears, fars, lin_bins, t_rand, t_rand_cols, sp,
+                                                    spacing_bins, euclid_bins, n_rays, n_bins, n_rays_dev);
   RSN_LAUNCH_CHECK("sample_spaced_kernel");
   return 0;
 }
 
 extern "C" int rsn_pdf_resample(const float* weights, int64_t weights_row_stride, const float* spacing_bins_in,
                                 const float* nears, const float* fars, const float* u_base, const float* rand,
-                                int spacing_kind, float histogram_padding, float* spacing_bins_out,
+                                int spacing_kind, float tan, float histogram_padding, float* spacing_bins_out,
                                 float* euclid_bins_out, int64_t* inds_out, int64_t n_rays, int64_t n_in_samples,
-                                int64_t n_out_samples, cudaStream_t stream) {
+                                int64_t n_out_samples, const int* n_rays_dev, cudaStream_t stream) {
   RSN_ARG(n_rays >= 0 && n_in_samples >= 1 && n_out_samples >= 1, "rsn_pdf_resample: bad shape");
   RSN_ARG(n_in_samples <= 4096, "rsn_pdf_resample: at most 4096 input samples per ray (got %lld)", (long long)n_in_samples);
-  RSN_ARG(spacing_kind == 0 || spacing_kind == 1, "rsn_pdf_resample: spacing_kind must be 0 or 1");
+  RSN_ARG(spacing_kind == 0 || (spacing_kind == 1 && tan > 0.f), "rsn_pdf_resample: spacing_kind must be 0 or 1 (tan > 0)");
+  const Spacing sp = {spacing_kind, (float)(1.0 / (double)tan), tan};
   if (n_rays == 0) return 0;
   RSN_ARG(weights && spacing_bins_in && nears && fars && u_base && spacing_bins_out && euclid_bins_out,
           "rsn_pdf_resample: null pointer");
   constexpr int WARPS = 4;
   const int S = (int)n_in_samples, nb = (int)n_out_samples + 1;
-  size_t smem = (size_t)WARPS * 2 * (S + 1) * sizeof(float);
-  if (smem > 48 * 1024)
-    RSN_CUDA(cudaFuncSetAttribute(pdf_resample_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t smem = (size_t)WARPS * (2 * (S + 1) + S + (S >> 5) + 1) * sizeof(float);
+  static std::atomic<unsigned long long> done;   // sized for the 4096-sample maximum, set once per device
+  RSN_CUDA(rsn_ensure_smem(pdf_resample_kernel<WARPS>, (int)(WARPS * (2 * 4097 + 4096 + 129) * sizeof(float)), done));
   int blocks = (int)std::min<int64_t>((n_rays + WARPS - 1) / WARPS, (int64_t)rsn_num_sms() * 16);
   pdf_resample_kernel<WARPS><<<blocks, WARPS * 32, smem, stream>>>(
-      weights, weights_row_stride, spacing_bins_in, nears, fars, u_base, rand, spacing_kind, histogram_padding,
-      spacing_bins_out, euclid_bins_out, inds_out, n_rays, S, nb);
+      weights, weights_row_stride, spacing_bins_in, nears, fars, u_base, rand, sp, histogram_padding,
+      spacing_bins_out, euclid_bins_out, inds_out, n_rays, S, nb, n_rays_dev);
   RSN_LAUNCH_CHECK("pdf_resample_kernel");
   return 0;
 }

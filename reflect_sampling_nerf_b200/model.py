@@ -1,11 +1,15 @@
 """Drop-in model: the per-ray rendering hot path of ReflectSamplingNeRFModel.get_outputs / get_loss_dict
-(reflect_sampling_nerf_model.py:142-430) on the sm_100a kernels.
+(reflect_sampling_nerf_model.py:142-430) and its eval-image path (model.py:432-482 + upstream
+get_outputs_for_camera_ray_bundle) on the sm_100a kernels.
 
-Same config fields (model.py:46-75), module attribute names (model.py:97-127), output keys / shapes / detach
-status (model.py:233-258,341) and loss keys (model.py:415-428) as the reference.  What differs is only how
-the work is dispatched: each pass over the samples is sampler kernel -> fused field kernel -> compositing
-kernel (3 launches instead of ~3,000 eager ops), the reference's debug prints / quantiles /
-.item() host syncs (App. B Q12) are gone, and the broken eval-image method (Q13) is not reproduced.
+Same config fields (model.py:46-75), module attribute names (model.py:97-132: field, sampler_*, renderer_*, rgb_loss,
+psnr, ssim, near, far), output keys / shapes / detach status (model.py:233-258,341) and loss keys (model.py:415-428) as
+the reference.  What differs is how the work is dispatched: each pass over the samples is sampler kernel -> fused field
+kernel -> compositing kernel (3 launches instead of ~3,000 eager ops), the bounce runs without reading
+the number of masked rays back to the host, and three defects of the reference are not reproduced:
+the debug prints / quantiles / .item() host syncs (Q12), the early return without `depth_reflect_fine` (Q11) and the
+ragged [M,1] `depth_reflect_fine` + `outputs["low_coarse"]` KeyError that break the eval image (Q13) --
+`depth_reflect_fine` is [N,1], zero where the ray did not bounce, and `get_image_metrics_and_images` works.
 
 When nerfstudio is importable the classes derive from its Model / ModelConfig so `ns-train
 reflect-sampling-nerf` instantiates them through the usual `_target` mechanism; otherwise they fall back to
@@ -13,15 +17,17 @@ plain nn.Module / dataclass bases with the same constructor contract.
 """
 from __future__ import annotations
 
-import math
+from collections import defaultdict
 from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional, Type
+from typing import Any, Dict, List, Optional, Tuple, Type
 
 import torch
 from torch import Tensor, nn
 from torch.nn import Parameter
 
 from . import ops
+from .components import (AccumulationRenderer, DepthRenderer, IntegratedSHEncoding, NeRFEncoding, NormalsRenderer,
+                         PDFSampler, ReciprocalSampler, RGBRenderer, SemanticRenderer, UniformSampler, WHITE)
 from .field import ReflectSamplingNeRFNerfField
 from .rays import RayBundle
 
@@ -104,23 +110,59 @@ class _NearFarCollider(nn.Module):
         return ray_bundle
 
 
-class _Sampler(nn.Module):
-    """Holds the sampler hyper-parameters under the reference's attribute names (model.py:109-112); the work is
-    ops.sample_spaced / ops.pdf_resample.  `injected_rand` lets parity tests supply the stratification noise."""
+# ------------------------------------------------------------------------------------------ eval metrics (torchmetrics stand-ins)
+class PeakSignalNoiseRatio(nn.Module):
+    """torchmetrics.image.PeakSignalNoiseRatio(data_range=1.0) over one image pair (model.py:130)."""
 
-    def __init__(self, num_samples: int, kind: int) -> None:
+    def __init__(self, data_range: float = 1.0) -> None:
         super().__init__()
-        self.num_samples, self.kind = num_samples, kind
-        self.injected_rand: Optional[Tensor] = None
+        self.data_range = data_range
 
-    def noise(self, n: int, device) -> Optional[Tensor]:
-        if not self.training:
-            return None
-        if self.injected_rand is not None:
-            return self.injected_rand.to(device)
-        return torch.rand(n, self.num_samples + 1, device=device)
+    def forward(self, preds: Tensor, target: Tensor) -> Tensor:
+        mse = torch.mean((preds - target) ** 2)
+        return 10.0 * torch.log10(self.data_range ** 2 / mse)
 
 
+def structural_similarity_index_measure(preds: Tensor, target: Tensor, data_range: float = 1.0) -> Tensor:
+    """SSIM with the usual 11x11 Gaussian window (sigma 1.5, k1 0.01, k2 0.03) over [1,C,H,W] images: the metric
+    model.py:131 takes from torchmetrics (which is not in this image; the window handling at the border differs)."""
+    c = preds.shape[1]
+    x = torch.arange(11, dtype=preds.dtype, device=preds.device) - 5
+    g = torch.exp(-(x ** 2) / (2 * 1.5 ** 2))
+    g = (g / g.sum())[:, None] * (g / g.sum())[None, :]
+    win = g.expand(c, 1, 11, 11).contiguous()
+    conv = lambda t: torch.nn.functional.conv2d(t, win, groups=c)   # noqa: E731
+    mu_x, mu_y = conv(preds), conv(target)
+    sxx, syy, sxy = conv(preds * preds) - mu_x ** 2, conv(target * target) - mu_y ** 2, conv(preds * target) - mu_x * mu_y
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    ssim = ((2 * mu_x * mu_y + c1) * (2 * sxy + c2)) / ((mu_x ** 2 + mu_y ** 2 + c1) * (sxx + syy + c2))
+    return ssim.mean()
+
+
+def apply_colormap(image: Tensor) -> Tensor:
+    """nerfstudio colormaps.apply_colormap stand-in: [...,1] in [0,1] -> turbo RGB (polynomial approximation)."""
+    x = torch.clamp(torch.nan_to_num(image[..., 0]), 0.0, 1.0)
+    v4 = torch.stack([torch.ones_like(x), x, x * x, x * x * x], -1)
+    v2 = torch.stack([v4[..., 2] * v4[..., 2], v4[..., 3] * v4[..., 2]], -1)
+    k4 = x.new_tensor([[0.13572138, 4.61539260, -42.66032258, 132.13108234], [0.09140261, 2.19418839, 4.84296658, -14.18503333],
+                       [0.10667330, 12.64194608, -60.58204836, 110.36276771]])
+    k2 = x.new_tensor([[-152.94239396, 59.28637943], [4.27729857, 2.82956604], [-89.90310912, 27.34824973]])
+    return torch.clamp(v4 @ k4.T + v2 @ k2.T, 0.0, 1.0)
+
+
+def apply_depth_colormap(depth: Tensor, accumulation: Optional[Tensor] = None, near_plane: Optional[float] = None,
+                         far_plane: Optional[float] = None) -> Tensor:
+    """nerfstudio colormaps.apply_depth_colormap stand-in."""
+    near = float(torch.min(depth)) if near_plane is None else near_plane
+    far = float(torch.max(depth)) if far_plane is None else far_plane
+    d = torch.clip((depth - near) / (far - near + 1e-10), 0, 1)
+    img = apply_colormap(d)
+    if accumulation is not None:
+        img = img * accumulation + (1 - accumulation)
+    return img
+
+
+# ------------------------------------------------------------------------------------------ the model
 class ReflectSamplingNeRFModel(_BaseModel):
     """B200-native ReflectSamplingNeRF model."""
 
@@ -130,22 +172,55 @@ class ReflectSamplingNeRFModel(_BaseModel):
         self.field = None
         assert config.collider_params is not None, "MipNeRF model requires bounding box collider parameters."
         super().__init__(config=config, **kwargs)
+        assert self.config.collider_params is not None, "mip-NeRF requires collider parameters to be set."
 
     def populate_modules(self):
+        """model.py:93-132."""
         super().populate_modules()
         if not HAVE_NERFSTUDIO and self.config.enable_collider:
             self.collider = _NearFarCollider(self.config.collider_params["near_plane"],
                                              self.config.collider_params["far_plane"])
-        self.field = ReflectSamplingNeRFNerfField()
+        # fields (model.py:98-106)
+        position_encoding = NeRFEncoding(in_dim=3, num_frequencies=16, min_freq_exp=0.0, max_freq_exp=16.0,
+                                         include_input=True)
+        direction_encoding = IntegratedSHEncoding()
+        self.field = ReflectSamplingNeRFNerfField(position_encoding=position_encoding,
+                                                  direction_encoding=direction_encoding)
+        # samplers (model.py:109-114)
         c = self.config
-        self.sampler_uniform = _Sampler(c.num_coarse_samples, ops.UNIFORM)
-        self.sampler_pdf = _Sampler(c.num_importance_samples, ops.UNIFORM)
-        self.sampler_reciprocal = _Sampler(c.num_reflect_coarse_samples, ops.RECIPROCAL)
-        self.sampler_reflect_pdf = _Sampler(c.num_reflect_importance_samples, ops.RECIPROCAL)
+        self.sampler_uniform = UniformSampler(num_samples=c.num_coarse_samples)
+        self.sampler_pdf = PDFSampler(num_samples=c.num_importance_samples, include_original=False)
+        self.sampler_reciprocal = ReciprocalSampler(num_samples=c.num_reflect_coarse_samples, tan=0.25)
+        self.sampler_reflect_pdf = PDFSampler(num_samples=c.num_reflect_importance_samples, include_original=False)
+        self.sampler_reflect_pdf.kind = ops.RECIPROCAL
         self.far = 2 ** 8
         self.near = 1.0 / 16
-        self.background_color = torch.tensor([1.0, 1.0, 1.0])   # colors.WHITE (model.py:117)
+        # renderers (model.py:117-124)
+        self.background_color = WHITE.clone()             # colors.WHITE
+        self.renderer_rgb = RGBRenderer(background_color=self.background_color)
+        self.renderer_accumulation = AccumulationRenderer()
+        self.renderer_depth = DepthRenderer()
+        self.renderer_normals = NormalsRenderer()
+        self.renderer_roughness = SemanticRenderer()
+        self.renderer_factor = RGBRenderer()
+        self.renderer_reflect = RGBRenderer()
+        # losses / metrics (model.py:127-132; LPIPS needs torchmetrics + its pretrained network: registered when importable
+        # so that checkpoints interchange, otherwise absent and `lpips.*` keys are ignored on load)
         self.rgb_loss = nn.MSELoss()
+        self.psnr = PeakSignalNoiseRatio(data_range=1.0)
+        self.ssim = structural_similarity_index_measure
+        try:  # pragma: no cover - torchmetrics is not installed in the build image
+            from torchmetrics.image.lpip import LearnedPerceptualImagePatchSimilarity
+            self.lpips = LearnedPerceptualImagePatchSimilarity(normalize=True)
+        except Exception:  # noqa: BLE001
+            self.lpips = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        """Reference checkpoints carry the torchmetrics LPIPS network (`lpips.*`); without torchmetrics those keys have no
+        module here and are dropped instead of failing a strict load."""
+        if self.lpips is None:
+            state_dict = {k: v for k, v in state_dict.items() if not k.startswith("lpips.")}
+        return super().load_state_dict(state_dict, strict=strict, **kwargs)
 
     def get_param_groups(self) -> Dict[str, List[Parameter]]:
         if self.field is None:
@@ -153,122 +228,140 @@ class ReflectSamplingNeRFModel(_BaseModel):
         return {"fields": list(self.field.parameters())}
 
     def set_jitter(self, uniform=None, pdf=None, reciprocal=None, reflect_pdf=None) -> None:
+        """Parity tests inject the stratification noise the oracle used ([rows, S+1]; bounce rows = masked rays in order)."""
         self.sampler_uniform.injected_rand = uniform
         self.sampler_pdf.injected_rand = pdf
         self.sampler_reciprocal.injected_rand = reciprocal
         self.sampler_reflect_pdf.injected_rand = reflect_pdf
 
-    # ------------------------------------------------------------------------------------------ one pass
-    def _pass(self, origins, directions, pixel_area, euclid_bins):
-        """sampled bins -> fused field -> compositing (model.py:151-177 and its three repeats)."""
-        f = self.field.evaluate_samples(origins, directions, pixel_area, euclid_bins)
-        w, acc, depth, comp = ops.composite(f["density"], euclid_bins, f["feat"])
-        return f["feat"], w, acc[:, None], depth[:, None], comp
+    def _bounce_planes(self, n: int, device) -> Tuple[Tensor, Tensor]:
+        """nears = zeros * near (App. B Q4), fars = ones * far of the reflected bundle (model.py:287-288), cached."""
+        cache = self.__dict__.get("_planes")
+        if cache is None or cache[0].shape[0] != n or cache[0].device != device:
+            cache = (torch.zeros(n, 1, device=device), torch.full((n, 1), float(self.far), device=device))
+            self.__dict__["_planes"] = cache
+        return cache
 
+    # ------------------------------------------------------------------------------------------ outputs
     def get_outputs(self, ray_bundle: RayBundle) -> Dict[str, Tensor]:
         if self.field is None:
             raise ValueError("populate_fields() must be called before get_outputs")
+        from . import train_path
         if torch.is_grad_enabled() and self.training:
-            from .train_path import get_outputs_train   # hand-written backward kernels (autograd.Functions)
-            return get_outputs_train(self, ray_bundle)
-        return self._get_outputs_nograd(ray_bundle)
+            return train_path.get_outputs(self, ray_bundle, True)     # hand-written backward kernels (autograd.Functions)
+        with torch.no_grad():
+            return train_path.get_outputs(self, ray_bundle, False)
 
     @torch.no_grad()
-    def _get_outputs_nograd(self, ray_bundle: RayBundle) -> Dict[str, Tensor]:
-        o, d = ray_bundle.origins, ray_bundle.directions
-        area, nears, fars = ray_bundle.pixel_area, ray_bundle.nears, ray_bundle.fars
-        n, dev = o.shape[0], o.device
-        clip01 = lambda x: torch.clip(x, 0.0, 1.0)  # noqa: E731
-        ev = (lambda x: x) if self.training else clip01   # RGBRenderer clamps in eval mode (App. A.6)
-
-        # A. coarse (model.py:148-177)
-        su, sp = self.sampler_uniform, self.sampler_pdf
-        sp_c, eu_c = ops.sample_spaced(nears, fars, su.num_samples, su.kind, su.noise(n, dev))
-        feat_c, w_c, acc_c, depth_c, comp_c = self._pass(o, d, area, eu_c)
-        rgb_c = clip01(ev(comp_c[:, ops.F_RGB] + (1.0 - acc_c)))
-        # B. fine (model.py:182-211)
-        sp_f, eu_f = ops.pdf_resample(w_c, sp_c, nears, fars, sp.num_samples, sp.kind, rand=sp.noise(n, dev),
-                                      train=self.training)
-        feat_f, w_f, acc_f, depth_f, comp_f = self._pass(o, d, area, eu_f)
-        rgb_f = clip01(ev(comp_f[:, ops.F_RGB] + (1.0 - acc_f)))
-        # C. per-ray quantities of the bounce (model.py:215-229), one kernel
-        diff_r, tint_r, nrm_r, ndd, mask, o2_all, wr_all = ops.reflect_setup(comp_f, acc_f, depth_f, o, d,
-                                                                             clamp01=not self.training)
-        rough = comp_f[:, ops.F_ROUGH_SIGMOID, None]
-        white = torch.ones(n, 3, device=dev)
-        outputs = {
-            "mid_rgb_coarse": rgb_c, "mid_rgb_fine": rgb_f,
-            "mid_reflect_coarse": white * (1.0 - acc_f), "mid_reflect_fine": white * (1.0 - acc_f),
-            "accumulation_coarse": acc_c, "accumulation_fine": acc_f,
-            "depth_coarse": depth_c, "depth_fine": depth_f,
-            "weights_coarse": w_c[..., None], "weights_fine": w_f[..., None],
-            "pred_normals_coarse": feat_c[..., ops.F_NORMAL], "pred_normals_fine": feat_f[..., ops.F_NORMAL],
-            # eval: normals = predicted normals (model.py:161-162, App. B Q8); the no-grad training forward
-            # has no density gradient to offer either
-            "normals_coarse": feat_c[..., ops.F_NORMAL], "normals_fine": feat_f[..., ops.F_NORMAL],
-            "n_dot_d_coarse": feat_c[..., ops.F_NDOTD, None], "n_dot_d_fine": feat_f[..., ops.F_NDOTD, None],
-            "diff": diff_r, "tint": tint_r, "roughness": rough, "mask": mask,
-        }
-        idx = torch.nonzero(mask).reshape(-1)            # the reference's boolean indexing syncs here too
-        m = idx.numel()
-        if m == 0:                                        # App. B Q11
-            return outputs
-        # D. reflected bundle (model.py:267-290)
-        o2, w_r = o2_all[idx], wr_all[idx]
-        sqr = 2 * torch.abs(ndd[idx]) * rough[idx] ** 2
-        area2 = math.pi * sqr
-        nears2 = torch.zeros(m, 1, device=dev)            # zeros * near (App. B Q4)
-        fars2 = torch.full((m, 1), float(self.far), device=dev)
-        bg = self.field.get_inf_color(w_r, sqr)
-        # E. reflected coarse (model.py:292-313)
-        sr, sq = self.sampler_reciprocal, self.sampler_reflect_pdf
-        sp_rc, eu_rc = ops.sample_spaced(nears2, fars2, sr.num_samples, sr.kind, sr.noise(m, dev))
-        _, w_rc, acc_rc, _, comp_rc = self._pass(o2, w_r, area2, eu_rc)
-        base = outputs["mid_reflect_coarse"]
-        outputs["mid_reflect_coarse"] = ops.reflect_compose(base, diff_r, tint_r, idx, comp_rc, bg, acc_rc,
-                                                            clamp_inner=not self.training)
-        # F. reflected fine (model.py:317-341)
-        sp_rf, eu_rf = ops.pdf_resample(w_rc, sp_rc, nears2, fars2, sq.num_samples, sq.kind,
-                                        rand=sq.noise(m, dev), train=self.training)
-        _, w_rf, acc_rf, depth_rf, comp_rf = self._pass(o2, w_r, area2, eu_rf)
-        outputs["mid_reflect_fine"] = ops.reflect_compose(base, diff_r, tint_r, idx, comp_rf, bg, acc_rf,
-                                                          clamp_inner=not self.training)
-        outputs["depth_reflect_fine"] = depth_rf
-        return outputs
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle, num_rays_per_chunk: Optional[int] = None
+                                          ) -> Dict[str, Tensor]:
+        """Upstream Model.get_outputs_for_camera_ray_bundle: a full frame ([H,W,*] bundle) in chunks of
+        config.eval_num_rays_per_chunk rays, every output reassembled to [H,W,-1] (the padded `depth_reflect_fine` is what
+        makes that possible, App. B Q13).  BASELINE config C3."""
+        h, w = camera_ray_bundle.origins.shape[:2]
+        chunk = num_rays_per_chunk or self.config.eval_num_rays_per_chunk
+        o = camera_ray_bundle.origins.reshape(-1, 3)
+        d = camera_ray_bundle.directions.reshape(-1, 3)
+        a = camera_ray_bundle.pixel_area.reshape(-1, 1)
+        nears = None if camera_ray_bundle.nears is None else camera_ray_bundle.nears.reshape(-1, 1)
+        fars = None if camera_ray_bundle.fars is None else camera_ray_bundle.fars.reshape(-1, 1)
+        lists = defaultdict(list)
+        for i in range(0, h * w, chunk):
+            sl = slice(i, min(i + chunk, h * w))
+            bundle = RayBundle(origins=o[sl], directions=d[sl], pixel_area=a[sl],
+                               nears=None if nears is None else nears[sl], fars=None if fars is None else fars[sl])
+            for k, v in self.forward(bundle).items():
+                if isinstance(v, Tensor):
+                    lists[k].append(v)
+        return {k: torch.cat(v).view(h, w, -1) for k, v in lists.items()}
 
     # ------------------------------------------------------------------------------------------ losses
+    def loss_coefficient_vector(self, device) -> Tensor:
+        """The eight coefficients of ops.LOSS_KEYS as a DEVICE vector (the fused loss kernel reads them there, so a
+        captured step sees the pipeline's warm-up rewrite, pipeline.py:79-91, without re-capture).  Re-uploaded only
+        when the host dict changed."""
+        host = tuple(float(self.config.loss_coefficients.get(k, 1.0)) for k in ops.LOSS_KEYS)
+        cache = self.__dict__.get("_coef")
+        if cache is None or cache[1].device != device:
+            cache = [None, torch.empty(8, device=device)]
+            self.__dict__["_coef"] = cache
+        if cache[0] != host:
+            cache[1].copy_(torch.tensor(host))
+            cache[0] = host
+        return cache[1]
+
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
         """model.py:346-430.  blend_background_for_loss_computation is the identity for the tensor (white)
-        background and an RGB ground truth; the .item() prints are dropped (Q12)."""
+        background and an RGB ground truth; the .item() prints are dropped (Q12).
+        For the outputs of a training forward the eight terms come from ONE kernel (csrc/loss.cu), the per-sample normal /
+        orientation sums having been reduced inside the compositing kernels; any other outputs dict takes the generic
+        torch expressions below."""
         image = batch["image"].to(outputs["mid_rgb_fine"].device)[..., :3]
+        fused = self.__dict__.pop("_fused_normal_losses", None)
+        fused = fused[1] if fused is not None and fused[0] is outputs.get("weights_fine") else None
+        if fused is not None and image.is_cuda:
+            dev = image.device
+            ws = self.__dict__.get("_loss_ws")
+            if ws is None or ws.device != dev:
+                ws = ops.loss_workspace(dev)
+                self.__dict__["_loss_ws"] = ws
+            terms, total = ops.fused_loss(outputs["mid_rgb_coarse"], outputs["mid_rgb_fine"], outputs["mid_reflect_coarse"],
+                                          outputs["mid_reflect_fine"], image, fused["predicted_normal_loss_coarse"],
+                                          fused["predicted_normal_loss_fine"], fused["orientation_loss_coarse"],
+                                          fused["orientation_loss_fine"], self.loss_coefficient_vector(dev), ws)
+            self.__dict__["_fused_loss_total"] = total       # = sum of the dict (what a trainer back-propagates)
+            return {k: terms[i] for i, k in enumerate(ops.LOSS_KEYS)}
         wc, wf = outputs["weights_coarse"], outputs["weights_fine"]
         sqd = lambda a, b: torch.sum((a - b) ** 2, dim=-1, keepdim=True)   # noqa: E731
         pos = lambda v: torch.clamp_min(v, 0.0) ** 2                       # noqa: E731
-        # the training path computes the four per-sample normal / orientation sums inside the compositing kernels
-        # (ops.composite16); they are used only for the very outputs dict they were computed with
-        fused = self.__dict__.pop("_fused_normal_losses", None)
-        fused = fused[1] if fused is not None and fused[0] is outputs.get("weights_fine") else None
-
-        def normal_term(key, generic):
-            return fused[key].sum() if fused is not None else generic()
-
         loss = {
             "loss_mid_coarse": self.rgb_loss(image, outputs["mid_rgb_coarse"]),
             "loss_mid_fine": self.rgb_loss(image, outputs["mid_rgb_fine"]),
             "loss_reflect_mid_coarse": self.rgb_loss(image, outputs["mid_reflect_coarse"]),
             "loss_reflect_mid_fine": self.rgb_loss(image, outputs["mid_reflect_fine"]),
-            "predicted_normal_loss_coarse": normal_term(
-                "predicted_normal_loss_coarse",
-                lambda: torch.sum(wc * sqd(outputs["normals_coarse"], outputs["pred_normals_coarse"]))),
-            "predicted_normal_loss_fine": normal_term(
-                "predicted_normal_loss_fine",
-                lambda: torch.sum(wf * sqd(outputs["normals_fine"], outputs["pred_normals_fine"]))),
-            "orientation_loss_coarse": normal_term(
-                "orientation_loss_coarse", lambda: torch.sum(wc * pos(outputs["n_dot_d_coarse"]))),
-            "orientation_loss_fine": normal_term(
-                "orientation_loss_fine", lambda: torch.sum(wf * pos(outputs["n_dot_d_fine"]))),
+            "predicted_normal_loss_coarse": torch.sum(wc * sqd(outputs["normals_coarse"], outputs["pred_normals_coarse"])),
+            "predicted_normal_loss_fine": torch.sum(wf * sqd(outputs["normals_fine"], outputs["pred_normals_fine"])),
+            "orientation_loss_coarse": torch.sum(wc * pos(outputs["n_dot_d_coarse"])),
+            "orientation_loss_fine": torch.sum(wf * pos(outputs["n_dot_d_fine"])),
         }
         for k in loss:   # misc.scale_dict
             if k in self.config.loss_coefficients:
                 loss[k] = loss[k] * self.config.loss_coefficients[k]
         return loss
+
+    # ------------------------------------------------------------------------------------------ eval image
+    def get_image_metrics_and_images(self, outputs: Dict[str, Tensor], batch: Dict[str, Tensor]
+                                     ) -> Tuple[Dict[str, float], Dict[str, Tensor]]:
+        """model.py:432-482 with the `outputs["low_coarse"]` KeyError fixed (App. B Q13): the coarse image is
+        `mid_rgb_coarse`, the fine image the reflection-composited `mid_reflect_fine` (as the reference intends,
+        model.py:439).  outputs = get_outputs_for_camera_ray_bundle(...) ([H,W,*])."""
+        assert self.config.collider_params is not None, "mip-NeRF requires collider parameters to be set."
+        image = batch["image"].to(outputs["mid_rgb_coarse"].device)
+        image = self.renderer_rgb.blend_background(image)
+        mid_rgb_coarse = outputs["mid_rgb_coarse"]
+        mid_rgb_fine = outputs["mid_reflect_fine"]
+        acc_coarse = apply_colormap(outputs["accumulation_coarse"])
+        acc_fine = apply_colormap(outputs["accumulation_fine"])
+        near, far = self.config.collider_params["near_plane"], self.config.collider_params["far_plane"]
+        depth_coarse = apply_depth_colormap(outputs["depth_coarse"], accumulation=outputs["accumulation_coarse"],
+                                            near_plane=near, far_plane=far)
+        depth_fine = apply_depth_colormap(outputs["depth_fine"], accumulation=outputs["accumulation_fine"],
+                                          near_plane=near, far_plane=far)
+        combined_rgb = torch.cat([image, mid_rgb_coarse, mid_rgb_fine], dim=1)
+        combined_acc = torch.cat([acc_coarse, acc_fine], dim=1)
+        combined_depth = torch.cat([depth_coarse, depth_fine], dim=1)
+        # [H, W, C] -> [1, C, H, W] for the metrics
+        image = torch.moveaxis(image, -1, 0)[None, ...]
+        mid_rgb_coarse = torch.clip(torch.moveaxis(mid_rgb_coarse, -1, 0)[None, ...], min=0, max=1)
+        mid_rgb_fine = torch.clip(torch.moveaxis(mid_rgb_fine, -1, 0)[None, ...], min=0, max=1)
+        coarse_psnr = self.psnr(image, mid_rgb_coarse)
+        fine_psnr = self.psnr(image, mid_rgb_fine)
+        fine_ssim = self.ssim(image, mid_rgb_fine)
+        metrics_dict = {
+            "psnr": float(fine_psnr.item()), "coarse_psnr": float(coarse_psnr.item()),
+            "fine_psnr": float(fine_psnr.item()), "fine_ssim": float(fine_ssim.item()),
+        }
+        if self.lpips is not None:  # pragma: no cover
+            metrics_dict["fine_lpips"] = float(self.lpips(image, mid_rgb_fine).item())
+        images_dict = {"img": combined_rgb, "accumulation": combined_acc, "depth": combined_depth}
+        return metrics_dict, images_dict

@@ -5,7 +5,8 @@ Two things live in the reference pipeline that touch the hot path:
     step < 50 -- `warmup_loss_coefficients` below, nerfstudio-free so it is testable anywhere;
   * the data-parallel wrapper (pipeline.py:73-77): DistributedDataParallel(find_unused_parameters=True) + barrier.
     Here the model is NOT wrapped: the wgrad kernels write one flat gradient blob and train_path._flush_grads
-    all-reduces it once per step (`field.dp_world_size = world_size`), so the pipeline only records the world size.
+    all-reduces it once per step (`field.dp_world_size = world_size`).  What the wrapper also did at construction --
+    broadcast rank 0's parameters, nerfstudio seeds every rank differently -- is `train_path.sync_parameters`.
 
 The nerfstudio-facing classes exist only when nerfstudio is importable (it is not in the build image).
 """
@@ -66,11 +67,18 @@ try:  # pragma: no cover - nerfstudio is not installed in the build image
             self.world_size = world_size
             self._model.field.dp_world_size = world_size      # flat-gradient all-reduce instead of the DDP wrapper
             if world_size > 1:
+                from .train_path import sync_parameters
+                sync_parameters(self._model.field)            # DDP's construction-time broadcast (pipeline.py:73-77)
                 dist.barrier(device_ids=[local_rank])
 
         def get_train_loss_dict(self, step: int):
             warmup_loss_coefficients(step, self.model.config.loss_coefficients)
             return super().get_train_loss_dict(step)
+
+        def get_eval_image_metrics_and_images(self, step: int):
+            """The reference inherits VanillaPipeline's, which dies on its model's KeyError (App. B Q13); the fixed model
+            method makes the inherited flow work unchanged."""
+            return super().get_eval_image_metrics_and_images(step)
 
     HAVE_NERFSTUDIO = True
 except Exception:  # noqa: BLE001

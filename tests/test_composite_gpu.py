@@ -108,6 +108,7 @@ def test_composite16_fused_normal_losses(S):
     sigma = (torch.rand(n, S, generator=g) * 3).cuda().requires_grad_(True)
     bins = (2 + 4 * torch.sort(torch.rand(n, S + 1, generator=g), dim=-1)[0]).cuda()
     feat = torch.rand(n, S, 16, generator=g).cuda()
+    feat[..., 0:3] *= 1.6                                      # some composited colours leave [0, 1]: the blend's clip bites
     feat[..., 13] = feat[..., 13] * 2 - 1                      # n.d of either sign
     feat.requires_grad_(True)
     normals = torch.nn.functional.normalize(torch.randn(n, S, 3, generator=g), dim=-1).cuda()
@@ -115,8 +116,10 @@ def test_composite16_fused_normal_losses(S):
     gfo = torch.rand(n, 16, generator=g).cuda()
     c_pn, c_ol = 0.3, 0.7
 
-    w, acc, depth, fo, pnl, ol = ops.composite16(sigma, bins, feat, normals)
-    ((w * gw).sum() + (acc * gacc).sum() + (fo * gfo).sum() + c_pn * pnl.sum() + c_ol * ol.sum()).backward()
+    gblend = torch.randn(n, 3, generator=g).cuda()
+    w, acc, depth, fo, pnl, ol, blend = ops.composite16(sigma, bins, feat, normals, blend=True)
+    ((w * gw).sum() + (acc * gacc).sum() + (fo * gfo).sum() + c_pn * pnl.sum() + c_ol * ol.sum()
+     + (blend * gblend).sum()).backward()
     gs, gf = sigma.grad.clone(), feat.grad.clone()
     sigma.grad = feat.grad = None
 
@@ -124,7 +127,11 @@ def test_composite16_fused_normal_losses(S):
     wd = w2.detach()[..., None]
     pn_loss = torch.sum(wd * torch.sum((normals - feat[..., 9:12]) ** 2, dim=-1, keepdim=True))
     o_loss = torch.sum(wd * torch.clamp_min(feat[..., 13:14], 0.0) ** 2)
-    ((w2 * gw).sum() + (acc2 * gacc).sum() + (fo2 * gfo).sum() + c_pn * pn_loss + c_ol * o_loss).backward()
+    blend2 = torch.clip(fo2[:, 0:3] + (1.0 - acc2[:, None]), 0.0, 1.0)       # renderer_rgb (white) + clip, model.py:176-177
+    ((w2 * gw).sum() + (acc2 * gacc).sum() + (fo2 * gfo).sum() + c_pn * pn_loss + c_ol * o_loss
+     + (blend2 * gblend).sum()).backward()
+    torch.testing.assert_close(blend, blend2, rtol=1e-6, atol=1e-6)
+    assert float((blend2 == 1.0).float().mean()) > 0.02          # the clip is active for some rays
     torch.testing.assert_close(w, w2, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(fo, fo2, rtol=1e-5, atol=1e-6)
     assert torch.equal(depth, depth2)
@@ -132,3 +139,26 @@ def test_composite16_fused_normal_losses(S):
     torch.testing.assert_close(ol.sum(), o_loss, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(gs, sigma.grad, rtol=1e-4, atol=1e-5 * float(sigma.grad.abs().max()))
     torch.testing.assert_close(gf, feat.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("m", [0, 1, 40, 97, 500])
+def test_composite16_device_side_ray_count_and_detached_density(m):
+    """The bounce form: rows >= the device count are left alone, forward and backward; detach_sigma produces no density
+    gradient and the same feature gradient."""
+    n, S = 97, 64
+    g = torch.Generator().manual_seed(m)
+    sigma = (torch.rand(n, S, generator=g) * 3).cuda().requires_grad_(True)
+    bins = (2 + 4 * torch.sort(torch.rand(n, S + 1, generator=g), dim=-1)[0]).cuda()
+    feat = torch.rand(n, S, 16, generator=g).cuda().requires_grad_(True)
+    gfo = torch.rand(n, 16, generator=g).cuda()
+    count = torch.tensor([m], dtype=torch.int32, device="cuda")
+    k = min(m, n)
+    w0, acc0, d0, fo0, _, _, _ = ops.composite16(sigma, bins, feat)
+    (fo0[:k] * gfo[:k]).sum().backward()
+    gf0 = feat.grad.clone()
+    feat.grad = sigma.grad = None
+    w, acc, d, fo, _, _, _ = ops.composite16(sigma, bins, feat, None, count, detach_sigma=True)
+    assert torch.equal(w[:k], w0[:k]) and torch.equal(fo[:k], fo0[:k]) and torch.equal(d[:k], d0[:k])
+    (fo[:k] * gfo[:k]).sum().backward()
+    assert sigma.grad is None
+    assert torch.equal(feat.grad[:k], gf0[:k])

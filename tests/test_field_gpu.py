@@ -98,60 +98,81 @@ def test_inf_color_matches_oracle():
     torch.testing.assert_close(rgb, ref, rtol=0, atol=1e-2)
 
 
-def test_cta_pair_form_is_bit_identical(monkeypatch):
-    """The cta_group::2 form of the forward kernel (RSN_FWD_PAIR=1) against the default single-CTA form: same
-    arithmetic in the same order => identical bits, including an odd tile count (void second tile of the last pair)."""
-    field, o, d, pa, bins = _setup(37, 24, 5, "uniform", 8.1e-7)      # 888 points = 7 tiles
-    wblob, bias = [t.cuda() for t in packing.pack_field(field.state_dict())]
-    args = (wblob, bias, o.cuda(), d.cuda(), pa.cuda(), bins.cuda())
-    monkeypatch.delenv("RSN_FWD_PAIR", raising=False)
-    s0, f0 = ops.field_forward(*args)
-    monkeypatch.setenv("RSN_FWD_PAIR", "1")
-    s1, f1 = ops.field_forward(*args)
-    torch.cuda.synchronize()
-    assert torch.equal(s0, s1) and torch.equal(f0, f1)
-
-
 def test_tmem_operand_form_is_bit_identical(monkeypatch):
-    """Default forward (A operand of the hidden layers from TMEM, stash staged after the hand-over) against the
-    shared-memory operand form (RSN_FWD_TS=0): same arithmetic in the same order => identical outputs, stash and aux."""
+    """Product forward (A operand of the hidden layers from TMEM, stash staged after the hand-over) against the
+    shared-memory operand form of the TEST BUILD (librsn_b200_dbg.so, RSN_FWD_TS=0): same arithmetic in the same order =>
+    identical outputs, stash and aux.  Also pins product == test build for the default form."""
+    from reflect_sampling_nerf_b200 import _lib
     field, o, d, pa, bins = _setup(37, 24, 5, "uniform", 8.1e-7)      # 888 points = 7 tiles
     wblob, bias = [t.cuda() for t in packing.pack_field(field.state_dict())]
     args = (o.cuda(), d.cuda(), pa.cuda(), bins.cuda())
-    from reflect_sampling_nerf_b200 import _lib
     nbytes = _lib.lib().rsn_field_stash_bytes(37 * 24)
     zeros = lambda: torch.zeros(nbytes, dtype=torch.uint8, device="cuda")  # noqa: E731  (unwritten mask slots compare equal)
+
+    def run():
+        s, f = ops.field_forward(wblob, bias, *args)
+        return (s, f) + tuple(ops.field_forward_train(wblob, bias, 0, *args, stash=zeros()))
     monkeypatch.delenv("RSN_FWD_TS", raising=False)
-    s0, f0 = ops.field_forward(wblob, bias, *args)
-    t0 = ops.field_forward_train(wblob, bias, 0, *args, stash=zeros())
-    monkeypatch.setenv("RSN_FWD_TS", "0")
-    s1, f1 = ops.field_forward(wblob, bias, *args)
-    t1 = ops.field_forward_train(wblob, bias, 0, *args, stash=zeros())
+    prod = run()
+    try:
+        _lib.use_dbg(True)
+        dflt = run()
+        monkeypatch.setenv("RSN_FWD_TS", "0")
+        ss = run()
+    finally:
+        _lib.use_dbg(False)
     torch.cuda.synchronize()
-    assert torch.equal(s0, s1) and torch.equal(f0, f1)
-    assert torch.equal(t0[0], t1[0]) and torch.equal(t0[1], t1[1]) and torch.equal(t0[2], t1[2])
-    assert torch.equal(t0[3][..., :6], t1[3][..., :6])      # aux: 6 of 8 floats per point are defined
+    for other in (dflt, ss):
+        for a, b in zip(prod[:5], other[:5]):
+            assert torch.equal(a, b)
+        assert torch.equal(prod[5][..., :7], other[5][..., :7])      # aux: 7 of 8 floats per point are defined
 
 
-def test_multicast_weight_stream_form_is_bit_identical(monkeypatch):
-    """RSN_FWD_MC=1: 2-CTA clusters in which each CTA fetches half of every weight chunk and multicasts it to both
-    (odd tile count => the last cluster has a void tile).  Same arithmetic => identical outputs and stash."""
-    from reflect_sampling_nerf_b200 import _lib
-    field, o, d, pa, bins = _setup(37, 24, 5, "uniform", 8.1e-7)      # 888 points = 7 tiles
+def test_two_fields_on_two_streams_do_not_share_bias_state():
+    """The bias reaches the kernel by pointer (no __constant__ table rewritten per launch): two fields with different
+    parameters evaluated concurrently on two streams each get their own results."""
+    torch.manual_seed(1)
+    fa, fb = R.OracleField().eval(), R.OracleField().eval()
+    _, o, d, pa, bins = _setup(2000, 64, 3)
+    args = [t.cuda() for t in (o, d, pa, bins)]
+    pa_ = [t.cuda() for t in packing.pack_field(fa.state_dict())]
+    pb_ = [t.cuda() for t in packing.pack_field(fb.state_dict())]
+    ref_a = ops.field_forward(*pa_, *args)[1].clone()
+    ref_b = ops.field_forward(*pb_, *args)[1].clone()
+    torch.cuda.synchronize()
+    assert not torch.equal(ref_a, ref_b)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            a = ops.field_forward(*pa_, *args)[1]
+        with torch.cuda.stream(s2):
+            b = ops.field_forward(*pb_, *args)[1]
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a, ref_a) and torch.equal(b, ref_b)
+
+
+def test_device_side_ray_count_limits_the_pass():
+    """n_rays_dev: the launch is sized for the capacity, rows >= the device count are never written."""
+    field, o, d, pa, bins = _setup(300, 32, 21)
     wblob, bias = [t.cuda() for t in packing.pack_field(field.state_dict())]
     args = (o.cuda(), d.cuda(), pa.cuda(), bins.cuda())
-    nbytes = _lib.lib().rsn_field_stash_bytes(37 * 24)
-    zeros = lambda: torch.zeros(nbytes, dtype=torch.uint8, device="cuda")  # noqa: E731
-    monkeypatch.delenv("RSN_FWD_MC", raising=False)
-    s0, f0 = ops.field_forward(wblob, bias, *args)
-    t0 = ops.field_forward_train(wblob, bias, 0, *args, stash=zeros())
-    monkeypatch.setenv("RSN_FWD_MC", "1")
-    s1, f1 = ops.field_forward(wblob, bias, *args)
-    t1 = ops.field_forward_train(wblob, bias, 0, *args, stash=zeros())
-    torch.cuda.synchronize()
-    assert torch.equal(s0, s1) and torch.equal(f0, f1)
-    assert torch.equal(t0[0], t1[0]) and torch.equal(t0[1], t1[1]) and torch.equal(t0[2], t1[2])
-    assert torch.equal(t0[3][..., :6], t1[3][..., :6])
+    full_s, full_f = ops.field_forward(wblob, bias, *args)
+    for m in (0, 1, 77, 300, 1000):
+        count = torch.tensor([m], dtype=torch.int32, device="cuda")
+        n, s = 300, 32
+        sig = torch.full((n, s), -7.0, device="cuda")
+        feat = torch.full((n, s, 16), -7.0, device="cuda")
+        from reflect_sampling_nerf_b200 import _lib
+        _lib.call("rsn_field_forward", wblob.data_ptr(), bias.data_ptr(), 0, args[0].data_ptr(), args[1].data_ptr(),
+                  args[2].reshape(-1).data_ptr(), args[3].data_ptr(), n, s, sig.data_ptr(), feat.data_ptr(),
+                  count.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        k = min(m, n)
+        assert torch.equal(sig[:k], full_s[:k]) and torch.equal(feat[:k], full_f[:k])
+        assert bool((sig[k:] == -7.0).all()) and bool((feat[k:] == -7.0).all())
 
 
 def test_pack_kernel_matches_host_packing():

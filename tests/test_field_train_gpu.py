@@ -164,8 +164,9 @@ def test_fused_backward_matches_two_launch_form():
 
 @pytest.mark.parametrize("want_area", [False, True])
 def test_chain_tmem_operand_form_is_bit_identical(monkeypatch, want_area):
-    """Default chain kernels (dY operand from TMEM, dY stash staged after the hand-over) against the shared-memory
-    operand form (RSN_BWD_TS=0): same arithmetic in the same order => identical normals, dY stash and d pixel_area."""
+    """Product chain kernels (dY operand from TMEM, dY stash staged after the hand-over) against the shared-memory
+    operand form of the TEST BUILD (RSN_BWD_TS=0): same arithmetic in the same order => identical normals, dY stash and
+    d pixel_area."""
     n, s = 37, 24                                                     # 888 points = 7 tiles
     field, o, d, pa, bins, g = _setup(n, s, 21, "uniform", 8.1e-7)
     sd = field.state_dict()
@@ -177,17 +178,81 @@ def test_chain_tmem_operand_form_is_bit_identical(monkeypatch, want_area):
     sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, 0, o, d, pa, bins)
     nbytes = _lib.lib().rsn_field_dy_stash_bytes(n * s)
     out = {}
-    for ts in ("1", "0"):
-        monkeypatch.setenv("RSN_BWD_TS", ts)
-        dy = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
-        normals = ops.field_normals(wblob_t, wd, stash, n, s)
-        g_area = ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, want_area)
-        torch.cuda.synchronize()
-        out[ts] = (normals, dy, g_area)
-    assert torch.equal(out["1"][0], out["0"][0])
-    assert torch.equal(out["1"][1], out["0"][1])
-    if want_area:
-        assert torch.equal(out["1"][2], out["0"][2])
+    for form in ("product", "dbg-ts", "dbg-ss"):
+        monkeypatch.setenv("RSN_BWD_TS", "0" if form == "dbg-ss" else "1")
+        _lib.use_dbg(form != "product")
+        try:
+            dy = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+            normals = ops.field_normals(wblob_t, wd, stash, n, s)
+            g_area = ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, want_area)
+            torch.cuda.synchronize()
+        finally:
+            _lib.use_dbg(False)
+        out[form] = (normals, dy, g_area)
+    for form in ("dbg-ts", "dbg-ss"):
+        assert torch.equal(out["product"][0], out[form][0])
+        assert torch.equal(out["product"][1], out[form][1])
+        if want_area:
+            assert torch.equal(out["product"][2], out[form][2])
+
+
+def _bf(x):
+    return x.bfloat16().float()       # differentiable: the rounding is a straight-through identity for autograd
+
+
+def _bf16_heads(field, mean, cov, dirs):
+    """The oracle field with every GEMM operand rounded to bf16 where the kernels round (fp32 accumulate), with autograd:
+    the gradient reference that shares the kernels' forward rounding (ReLU patterns, saturations)."""
+    sd = dict(field.named_parameters())
+    lin = lambda x, w, b: _bf(x) @ _bf(sd[w]).T + sd[b]  # noqa: E731
+    enc = R.ipe(mean, cov)
+    h = enc
+    for l in range(8):
+        if l == 4:
+            h = torch.cat([enc, h], -1)
+        h = F.relu(lin(h, f"mlp_base.layers.{l}.weight", f"mlp_base.layers.{l}.bias"))
+    head = lambda n: lin(h, f"field_output_{n}.net.weight", f"field_output_{n}.net.bias")  # noqa: E731
+    out = {"density": F.softplus(head("density") + 0.5)}
+    out["pred_normals"] = F.normalize(-F.normalize(head("normals"), dim=-1), dim=-1)
+    rr = head("roughness")
+    out["rs"], rp = torch.sigmoid(rr), F.softplus(rr)
+    out["diff"], out["tint"] = torch.sigmoid(head("diff")), torch.sigmoid(head("tint"))
+    ide = R.ide(dirs, rp.detach())
+    mid_h = F.relu(lin(torch.cat([ide, head("bottleneck")], -1), "mlp_mid.layers.0.weight", "mlp_mid.layers.0.bias"))
+    out["rgb"] = out["diff"] + out["tint"] * torch.sigmoid(lin(mid_h, "field_output_mid.net.weight", "field_output_mid.net.bias"))
+    out["n_dot_d"] = torch.sum(dirs * out["pred_normals"], dim=-1, keepdim=True)
+    return out
+
+
+def test_gradients_against_the_bf16_emulated_autograd_oracle():
+    """Tight gradient gate (VERDICT r1 weak #1b): against autograd of the bf16-operand emulation the parameter
+    gradients of one primary pass agree to cosine > 0.999 and norm within 2 % for every tensor -- what remains is the
+    bf16 rounding of dY between the dgrad steps and of the wgrad operands."""
+    n, s = 64, 128
+    field, o, d, pa, bins, g = _setup(n, s, 71, "uniform", 3.2e-6)
+    ex = lambda x: x[:, None, :].expand(n, s, x.shape[-1])  # noqa: E731
+    mean, cov = R.frustum_gaussian(ex(o), ex(d), bins[:, :-1, None], bins[:, 1:, None], ex(pa))
+    mean, cov = R.contract(mean, cov)
+    ref = _bf16_heads(field, mean.detach(), cov.detach(), ex(d))
+    g_sigma = torch.randn(n, s, generator=g) * 0.1
+    g_feat = torch.zeros(n, s, 16)
+    g_feat[..., 0:14] = torch.randn(n, s, 14, generator=g) * 0.1
+    loss = (g_sigma * ref["density"][..., 0]).sum() + (g_feat[..., 0:3] * ref["rgb"]).sum() \
+        + (g_feat[..., 3:6] * ref["diff"]).sum() + (g_feat[..., 6:9] * ref["tint"]).sum() \
+        + (g_feat[..., 9:12] * ref["pred_normals"]).sum() + (g_feat[..., 12] * ref["rs"][..., 0]).sum() \
+        + (g_feat[..., 13] * ref["n_dot_d"][..., 0]).sum()
+    loss.backward()
+    _, _, _, _, grads, _ = _run_mine(field, 0, o, d, pa, bins, g_sigma, g_feat, False)
+    rows = []
+    for name, p in field.named_parameters():
+        if "field_output_low" in name:
+            continue
+        got = grads[name].cpu()
+        rows.append((_cos(got, p.grad), float(got.norm() / p.grad.norm()), name))
+    print("\n".join(f"{c:.5f} {r:.4f} {nme}" for c, r, nme in sorted(rows)))
+    for c, r, name in rows:
+        assert c > 0.999, (name, c, r)
+        assert abs(r - 1) < 0.02, (name, c, r)
 
 
 def test_field_kernels_accept_empty_batches():

@@ -126,6 +126,41 @@ def test_flat_gradient_allreduce_world_size_2(tmp_path):
     assert all(torch.load(os.path.join(tmp_path, f"ok{r}.pt")) for r in range(2))
 
 
+def _bcast_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from reflect_sampling_nerf_b200.train_path import _flush_grads, sync_parameters
+    torch.manual_seed(100 + rank)                     # nerfstudio seeds every rank differently (machine.seed + global_rank)
+    field = ReflectSamplingNeRFNerfField()
+    before = field.mlp_base.layers[2].weight.detach().clone()
+    sync_parameters(field)
+    # one "step": identical averaged gradients applied to (now) identical parameters
+    field.dp_world_size = world
+    _, _, total = ops.wgrad_layout()
+    field._grad_blob = torch.full((total,), float(rank + 1))
+    _flush_grads(field)
+    with torch.no_grad():
+        for p in field.parameters():
+            if p.grad is not None:
+                p.add_(p.grad, alpha=-1e-3)
+    flat = torch.cat([p.detach().reshape(-1) for p in field.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    torch.save({"same": all(torch.equal(gathered[0], t) for t in gathered),
+                "changed": bool(rank == 0 or not torch.equal(before, field.mlp_base.layers[2].weight.detach() + 1e-3 * field.mlp_base.layers[2].weight.grad))},
+               os.path.join(out_dir, f"b{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_parameters_are_broadcast_from_rank_0_world_size_2(tmp_path):
+    """without DDP's construction-time broadcast, differently seeded ranks would train different
+    replicas.  After sync_parameters + one averaged-gradient step every rank holds bit-identical parameters."""
+    mp.spawn(_bcast_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    res = [torch.load(os.path.join(tmp_path, f"b{r}.pt")) for r in range(2)]
+    assert all(r["same"] for r in res)
+    assert res[1]["changed"]                          # rank 1's own initialisation was replaced
+
+
 def test_loss_coefficient_warmup_matches_reference_pipeline():
     """reflect_sampling_nerf_pipeline.py:79-91 (also restated in oracle.refpath.warmup_coefficients)."""
     from oracle.refpath import LOSS_COEFFICIENTS, warmup_coefficients
@@ -145,8 +180,21 @@ def test_model_contract_without_gpu():
     assert isinstance(m, ReflectSamplingNeRFModel)
     assert list(m.get_param_groups()) == ["fields"] and len(m.get_param_groups()["fields"]) == 34
     assert (m.near, m.far) == (1.0 / 16, 256)
-    for name in ("sampler_uniform", "sampler_pdf", "sampler_reciprocal", "sampler_reflect_pdf", "rgb_loss", "field"):
-        assert hasattr(m, name)
+    for name in ("sampler_uniform", "sampler_pdf", "sampler_reciprocal", "sampler_reflect_pdf", "rgb_loss", "field",
+                 "renderer_rgb", "renderer_accumulation", "renderer_depth", "renderer_normals", "renderer_roughness",
+                 "renderer_factor", "renderer_reflect", "psnr", "ssim"):
+        assert hasattr(m, name), name
+    # component classes under the reference's names and constructor contracts (components.py:14-36, 38-140; model.py:109-124)
+    from reflect_sampling_nerf_b200 import components as C
+    assert isinstance(m.sampler_reciprocal, C.ReciprocalSampler) and m.sampler_reciprocal.tan == 0.25
+    assert isinstance(m.sampler_uniform, C.UniformSampler) and isinstance(m.sampler_pdf, C.PDFSampler)
+    assert m.sampler_pdf.include_original is False and m.sampler_pdf.histogram_padding == 0.01
+    assert isinstance(m.field.direction_encoding, C.IntegratedSHEncoding) and m.field.direction_encoding.get_out_dim() == 34
+    assert isinstance(m.field.position_encoding, C.NeRFEncoding) and m.field.position_encoding.get_out_dim() == 99
+    assert m.renderer_rgb.background_color.tolist() == [1.0, 1.0, 1.0] and m.renderer_reflect.background_color == "random"
+    for meth in ("get_blob", "contract", "get_density", "get_pred_normals", "get_normals", "get_roughness", "get_low",
+                 "get_mid", "get_diff", "get_tint", "get_inf_color", "get_reflection"):
+        assert callable(getattr(m.field, meth)), meth                       # field.py:90-207
     m.field = None
     with pytest.raises(ValueError):
         m.get_param_groups()

@@ -10,6 +10,14 @@ from reflect_sampling_nerf_b200.blocks import pack_blocks
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _test_build():
+    """The probes live in the test build (librsn_b200_dbg.so, include/rsn_b200_test.h) only."""
+    _lib.use_dbg(True)
+    yield
+    _lib.use_dbg(False)
+
+
 @pytest.mark.parametrize("N,KB,split", [(256, 4, 1), (256, 4, 2), (128, 2, 1), (16, 4, 1), (256, 1, 1), (64, 3, 2)])
 def test_kmajor_tile_gemm(N, KB, split):
     g = torch.Generator().manual_seed(N + KB)
