@@ -9,21 +9,24 @@ from helpers import oracle_model, synthetic_rays
 from oracle import upstream as U
 from reflect_sampling_nerf_b200.model import ReflectSamplingNeRFModel, ReflectSamplingNeRFModelConfig
 from reflect_sampling_nerf_b200.rays import RayBundle
+from reflect_sampling_nerf_b200.train_path import TrainStep
 
 pytestmark = pytest.mark.gpu
 SIZES = dict(num_coarse_samples=32, num_importance_samples=32, num_reflect_coarse_samples=16,
              num_reflect_importance_samples=16)
+C2 = dict(num_coarse_samples=128, num_importance_samples=128, num_reflect_coarse_samples=64, num_reflect_importance_samples=64)
+# thresholds quoted in DESIGN.md §2: (min cosine, max |norm ratio - 1|) over the parameter tensors of a whole step
+GATE_COS, GATE_NORM = 0.995, 0.03
+GATE_ROUGHNESS_NORM = 0.10      # field_output_roughness: heavy-tailed sum over rays of the bf16 d pixel_area path
 
 
 def _cos(a, b):
     return float(F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
 
 
-@pytest.mark.parametrize("boost_normal_losses", [False, True])
-def test_train_step_gradients_match_oracle(boost_normal_losses):
-    n = 512
-    ref = oracle_model(SIZES, seed=11).train()
-    mine = ReflectSamplingNeRFModel(ReflectSamplingNeRFModelConfig(**SIZES)).cuda().train()
+def _both_steps(sizes, n, seed, boost_normal_losses=False):
+    ref = oracle_model(sizes, seed=seed).train()
+    mine = ReflectSamplingNeRFModel(ReflectSamplingNeRFModelConfig(**sizes)).cuda().train()
     mine.field.load_state_dict(ref.field.state_dict(), strict=False)
     if boost_normal_losses:      # make the normal / orientation terms dominate so their paths are really tested
         for m in (ref.loss_coefficients, mine.config.loss_coefficients):
@@ -32,10 +35,10 @@ def test_train_step_gradients_match_oracle(boost_normal_losses):
                 m[k] = m[k] * 300.0
     o, d, pa, img = synthetic_rays(n, 23, pixel_area=3.2e-6)
     g = torch.Generator().manual_seed(5)
-    jit = dict(uniform=torch.rand(n, SIZES["num_coarse_samples"] + 1, generator=g),
-               pdf=torch.rand(n, SIZES["num_importance_samples"] + 1, generator=g))
-    jr = torch.rand(n, SIZES["num_reflect_coarse_samples"] + 1, generator=g)
-    jp = torch.rand(n, SIZES["num_reflect_importance_samples"] + 1, generator=g)
+    jit = dict(uniform=torch.rand(n, sizes["num_coarse_samples"] + 1, generator=g),
+               pdf=torch.rand(n, sizes["num_importance_samples"] + 1, generator=g))
+    jr = torch.rand(n, sizes["num_reflect_coarse_samples"] + 1, generator=g)
+    jp = torch.rand(n, sizes["num_reflect_importance_samples"] + 1, generator=g)
     # reflected-pass noise is one row per RAY, handed to each model for its own masked rays
     ref.set_jitter(**jit)
     mref = ref(U.RayBundle(origins=o, directions=d, pixel_area=pa))["mask"]
@@ -52,29 +55,133 @@ def test_train_step_gradients_match_oracle(boost_normal_losses):
     assert (mmine == mref).float().mean() > 0.97
     mine.set_jitter(**jit, reciprocal=jr[mmine], reflect_pdf=jp[mmine])
     out = mine(bundle())
+    loss = mine.get_loss_dict(out, {"image": img.cuda()})
+    sum(loss.values()).backward()
+    torch.cuda.synchronize()
+    return ref, mine, out_ref, out, loss_ref, loss
+
+
+@pytest.mark.parametrize("sizes,n,boost", [(SIZES, 512, False), (SIZES, 512, True), (C2, 192, False)],
+                         ids=["small", "small-normal-losses", "C2"])
+def test_train_step_gradients_match_oracle(sizes, n, boost):
+    ref, mine, out_ref, out, loss_ref, loss = _both_steps(sizes, n, 11, boost)
     assert set(out) == set(out_ref)
     for k, v in out_ref.items():
         if k != "depth_reflect_fine":
             assert out[k].shape == v.shape, k
             assert out[k].requires_grad == v.requires_grad, k        # same detach topology (App. D)
-    loss = mine.get_loss_dict(out, {"image": img.cuda()})
-    sum(loss.values()).backward()
-    torch.cuda.synchronize()
     for k in loss_ref:
         torch.testing.assert_close(loss[k].detach().cpu(), loss_ref[k].detach(), rtol=6e-2, atol=1e-5,
                                    msg=lambda s, k=k: f"{k}: {s}")
-    # density-gradient normals of the training path
-    cosang = (out["normals_fine"].cpu() * out_ref["normals_fine"]).sum(-1)
-    assert float(cosang.median()) > 0.995
+    # density-gradient normals of the training path: median, 5th and 1st percentile of the cosine
+    cosang = (out["normals_fine"].cpu() * out_ref["normals_fine"]).sum(-1).flatten()
+    q = torch.quantile(cosang, torch.tensor([0.01, 0.05, 0.5]))
+    print("normals_fine cosine quantiles 1/5/50 %:", q.tolist())
+    assert float(q[2]) > 0.999 and float(q[1]) > 0.95 and float(q[0]) > 0.5, q.tolist()
     worst = []
-    for (name, p), (_, q) in zip(ref.field.named_parameters(), mine.field.named_parameters()):
+    for (name, p), (_, q_) in zip(ref.field.named_parameters(), mine.field.named_parameters()):
         if "field_output_low" in name:
-            assert q.grad is None and p.grad is None
+            assert q_.grad is None and p.grad is None
             continue
-        rg, mg = p.grad, q.grad.cpu()
+        rg, mg = p.grad, q_.grad.cpu()
         c, ratio = _cos(mg, rg), float(mg.norm() / rg.norm())
         worst.append((c, ratio, name))
     print("\n".join(f"{c:.4f} {r:.3f} {nme}" for c, r, nme in sorted(worst)))
     for c, ratio, name in worst:
-        assert c > 0.97, (name, c, ratio)
-        assert abs(ratio - 1) < 0.1, (name, c, ratio)
+        assert c > GATE_COS, (name, c, ratio)
+        tol = GATE_ROUGHNESS_NORM if "field_output_roughness" in name else GATE_NORM
+        assert abs(ratio - 1) < tol, (name, c, ratio)
+
+
+def test_train_step_is_sync_free_and_graph_replay_matches_eager():
+    """(a) A whole optimizer step (forward, losses, backward, fused RAdam, re-pack) never synchronises with the host;
+    (b) the CUDA-graph replay of the step computes what the eager step computes."""
+    n = 512
+    torch.manual_seed(0)
+    def make():
+        torch.manual_seed(0)
+        m = ReflectSamplingNeRFModel(ReflectSamplingNeRFModelConfig(**SIZES)).cuda().train()
+        return m
+    o, d, pa, img = [t.cuda() for t in synthetic_rays(n, 31, pixel_area=3.2e-6)]
+    g = torch.Generator().manual_seed(5)
+    jit = dict(uniform=torch.rand(n, 33, generator=g), pdf=torch.rand(n, 33, generator=g),
+               reciprocal=torch.rand(n, 17, generator=g), reflect_pdf=torch.rand(n, 17, generator=g))
+    results = {}
+    for mode in ("eager", "graph"):
+        model = make()
+        model.set_jitter(**{k: v.cuda() for k, v in jit.items()})
+        stepper = TrainStep(model, graph=(mode == "graph"))
+        losses = []
+        for i in range(7):
+            if mode == "eager" and i == 5:
+                torch.cuda.synchronize()
+                torch.cuda.set_sync_debug_mode("error")
+            try:
+                losses.append(stepper.step(RayBundle(origins=o, directions=d, pixel_area=pa), img).clone())
+            finally:
+                torch.cuda.set_sync_debug_mode("default")
+        torch.cuda.synchronize()
+        assert (stepper.graph is not None) == (mode == "graph")
+        results[mode] = (torch.stack(losses).cpu(), model.field.mlp_base.layers[3].weight.detach().cpu().clone())
+    le, lg = results["eager"][0], results["graph"][0]
+    assert bool((le[1:] < le[:-1]).sum() >= 4), le.tolist()          # the loss goes down on a fixed batch
+    torch.testing.assert_close(lg, le, rtol=2e-3, atol=1e-5)         # same step; fp32 atomics order differs run to run
+    torch.testing.assert_close(results["graph"][1], results["eager"][1], rtol=0, atol=2e-4)
+
+
+def test_two_forwards_before_one_backward_use_separate_stashes():
+    """a second training forward must not overwrite the activation stash of a graph that has not
+    run its backward yet -- gradients of the first graph equal those of a single forward/backward."""
+    n = 256
+    torch.manual_seed(0)
+    model = ReflectSamplingNeRFModel(ReflectSamplingNeRFModelConfig(**SIZES)).cuda().train()
+    o, d, pa, img = [t.cuda() for t in synthetic_rays(n, 41, pixel_area=3.2e-6)]
+    o2, d2, pa2, img2 = [t.cuda() for t in synthetic_rays(n, 42, pixel_area=3.2e-6)]
+    g = torch.Generator().manual_seed(1)
+    jit = {k: torch.rand(n, s, generator=g).cuda() for k, s in (("uniform", 33), ("pdf", 33), ("reciprocal", 17), ("reflect_pdf", 17))}
+    model.set_jitter(**jit)
+
+    def grads_of(first_then_second):
+        for p in model.parameters():
+            p.grad = None
+        out1 = model(RayBundle(origins=o, directions=d, pixel_area=pa))
+        loss1 = sum(model.get_loss_dict(out1, {"image": img}).values())
+        if first_then_second:                      # a second forward (another batch) while graph 1 is still alive
+            out2 = model(RayBundle(origins=o2, directions=d2, pixel_area=pa2))
+            loss2 = sum(model.get_loss_dict(out2, {"image": img2}).values())
+        loss1.backward()
+        torch.cuda.synchronize()
+        return [p.grad.clone() for p in model.field.parameters() if p.grad is not None]
+    a = grads_of(False)
+    b = grads_of(True)
+    for x, y in zip(a, b):
+        torch.testing.assert_close(x, y, rtol=1e-3, atol=1e-6 * float(x.abs().max()) + 1e-9)
+    assert sum(s.in_flight for s in model.field._stash_pool) == 5      # graph 2 never ran its backward: its slots stay claimed
+
+
+def test_grad_scaler_path_matches_unscaled_step():
+    """mixed_precision=True as in the reference config (reflect_sampling_nerf_config.py:33): under autocast + GradScaler
+    the hand-written backward carries the power-of-two loss scale through and the un-scaled gradients equal the plain
+    step's."""
+    n = 256
+    torch.manual_seed(0)
+    model = ReflectSamplingNeRFModel(ReflectSamplingNeRFModelConfig(**SIZES)).cuda().train()
+    o, d, pa, img = [t.cuda() for t in synthetic_rays(n, 51, pixel_area=3.2e-6)]
+    g = torch.Generator().manual_seed(1)
+    jit = {k: torch.rand(n, s, generator=g).cuda() for k, s in (("uniform", 33), ("pdf", 33), ("reciprocal", 17), ("reflect_pdf", 17))}
+    model.set_jitter(**jit)
+    opt = torch.optim.RAdam(model.get_param_groups()["fields"], lr=1e-3, eps=1e-15)
+
+    def run(scaled):
+        opt.zero_grad(set_to_none=True)
+        scaler = torch.amp.GradScaler("cuda", enabled=scaled, init_scale=65536.0)
+        with torch.autocast("cuda", enabled=scaled):
+            out = model(RayBundle(origins=o, directions=d, pixel_area=pa))
+            loss = sum(model.get_loss_dict(out, {"image": img}).values())
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.cuda.synchronize()
+        return [p.grad.clone() for p in model.field.parameters() if p.grad is not None]
+    plain, scaled = run(False), run(True)
+    for x, y in zip(plain, scaled):
+        torch.testing.assert_close(x, y, rtol=2e-3, atol=1e-5 * float(x.abs().max()) + 1e-12)
