@@ -382,8 +382,8 @@ def run_b200(args):
         line = {
             "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"C2 {args.workload} step: {n} rays/GPU drawn on the GPU from the procedurally generated "
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.config} {args.workload} step: {n} rays/GPU drawn on the GPU from the procedurally generated "
                                    f"Blender-format shiny-sphere scene ({SCENE['n_views']} views, {SCENE['resolution']}x"
                                    f"{SCENE['resolution']}) x (128 coarse + 128 fine) samples + reflected (64 + 64) per "
                                    f"bouncing ray, random-init field", "rays_per_gpu": n, **CFG,
@@ -419,12 +419,22 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "render"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C5"],
+                    help="BASELINE.json config: C2 = configs[1] train step, 16,384 rays per GPU (weak scaling; with --gpus 8 = "
+                         "configs[3]); C3 = configs[2] render of one 800x800 frame, 640,000 rays sharded over the GPUs; C5 = "
+                         "configs[4] render of 65,536 rays sharded over the GPUs (strong scaling)")
     ap.add_argument("--ref-rays", type=int, default=1024, help="bounded CPU sample (rays per oracle step)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="CUDA-graph the training step (auto: single GPU only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-baseline", action="store_true")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.scaling = "weak"
+    if args.config in ("C3", "C5"):
+        args.workload, args.scaling = "render", "strong"
+        total = 640000 if args.config == "C3" else 65536
+        args.rays = (total + world - 1) // world
     if args.impl == "reference":
         run_reference(args)
     else:

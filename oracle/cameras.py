@@ -15,9 +15,11 @@ for the alpha blend onto white).
 Two forms of the ray arithmetic:
   * `generate_rays_upstream`  the literal tensor expressions (torch.sum over the last axis, linalg.vector_norm);
   * `generate_rays`           the same arithmetic with every fp32 operation written out in a fixed order
-                              (((a b) + (c d)) + (e f), sqrt, divide) -- the BIT-EXACT target of csrc/raygen.cu, since
-                              ATen's reduction order is an implementation detail.  tests/test_oracle_cameras.py measures
-                              how far the two forms are apart on CPU (<= 1 ulp).
+                              (((a b) + (c d)) + (e f), sqrt, divide) and IEEE-rounded -- the BIT-EXACT target of
+                              csrc/raygen.cu.  ATen's reduction order is an implementation detail, and its vectorised CPU
+                              sqrt is not correctly rounded (1 ulp off numpy's / CUDA's sqrtf on ~1 % of inputs, measured
+                              here), so the square roots are taken in float64 and rounded once (= the IEEE fp32 sqrt).
+                              tests/test_oracle_cameras.py measures how far the two forms are apart on CPU (<= 2 ulp).
 """
 from __future__ import annotations
 
@@ -61,6 +63,11 @@ def generate_rays_upstream(c2w: Tensor, fx, fy, cx, cy, pixels: Tensor) -> Tuple
     return origins, d, (dx * dy)[..., None]
 
 
+def _sqrt_rn(x: Tensor) -> Tensor:
+    """Correctly rounded fp32 square root (float64 sqrt carries 53 >= 2 * 24 + 2 bits: rounding it once is exact)."""
+    return torch.sqrt(x.double()).float()
+
+
 def generate_rays(c2w: Tensor, fx, fy, cx, cy, pixels: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     """The same with an explicit fp32 operation order (the kernel's bit-exact target)."""
     cam, cs = _coords(pixels, fx, fy, cx, cy)
@@ -69,14 +76,14 @@ def generate_rays(c2w: Tensor, fx, fy, cx, cy, pixels: Tensor) -> Tuple[Tensor, 
     for k in range(3):
         u, v = cs[k, :, 0], cs[k, :, 1]
         w = [((u * rot[:, i, 0]) + (v * rot[:, i, 1])) + (-1.0 * rot[:, i, 2]) for i in range(3)]
-        nrm = torch.sqrt(((w[0] * w[0]) + (w[1] * w[1])) + (w[2] * w[2]))
+        nrm = _sqrt_rn(((w[0] * w[0]) + (w[1] * w[1])) + (w[2] * w[2]))
         nrm = torch.maximum(nrm, torch.tensor(_EPS, dtype=nrm.dtype))
         out.append(torch.stack([w[0] / nrm, w[1] / nrm, w[2] / nrm], dim=-1))
     d = out[0]
 
     def dist(a, b):
         e = a - b
-        return torch.sqrt(((e[:, 0] * e[:, 0]) + (e[:, 1] * e[:, 1])) + (e[:, 2] * e[:, 2]))
+        return _sqrt_rn(((e[:, 0] * e[:, 0]) + (e[:, 1] * e[:, 1])) + (e[:, 2] * e[:, 2]))
 
     area = dist(d, out[1]) * dist(d, out[2])
     return c2w[cam][:, :3, 3], d, area[..., None]

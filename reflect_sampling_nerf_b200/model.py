@@ -247,7 +247,7 @@ class ReflectSamplingNeRFModel(_BaseModel):
         if self.field is None:
             raise ValueError("populate_fields() must be called before get_outputs")
         from . import train_path
-        if torch.is_grad_enabled() and self.training:
+        if self.training and (torch.is_grad_enabled() or ops.TAPE is not None):
             return train_path.get_outputs(self, ray_bundle, True)     # hand-written backward kernels (autograd.Functions)
         with torch.no_grad():
             return train_path.get_outputs(self, ray_bundle, False)

@@ -62,6 +62,65 @@ class _Prof:
         return False
 
 
+# ----------------------------------------------------------------------------------------- the tape
+# The training step's backward is a fixed sequence of ~20 kernel launches.  torch.autograd can run it (every stage below is an
+# autograd.Function, which is what nerfstudio's Trainer uses through loss.backward()), but the engine hops threads and
+# streams, which costs launch latency and cannot be captured in a CUDA graph on this PyTorch build.  TrainStep therefore
+# records the SAME Function.forward / Function.backward static methods on this minimal tape (under torch.no_grad()) and
+# replays them in reverse itself: one thread, one stream, nothing but the kernels.
+class _Ctx:
+    """What a Function's forward / backward touch on `ctx`."""
+
+    def __init__(self, needs_input_grad) -> None:
+        self.needs_input_grad, self.saved_tensors, self.nondiff = needs_input_grad, (), ()
+
+    def save_for_backward(self, *tensors) -> None:
+        self.saved_tensors = tensors
+
+    def mark_non_differentiable(self, *tensors) -> None:
+        self.nondiff = tuple(id(t) for t in tensors)
+
+    def set_materialize_grads(self, value: bool) -> None:
+        pass
+
+
+class Tape:
+    def __init__(self) -> None:
+        self.records, self.live = [], set()
+
+    def apply(self, fn, *args):
+        ctx = _Ctx(tuple(isinstance(a, Tensor) and id(a) in self.live for a in args))
+        outs = fn.forward(ctx, *args)
+        outs_t = outs if isinstance(outs, tuple) else (outs,)
+        for o in outs_t:
+            if isinstance(o, Tensor) and id(o) not in ctx.nondiff:
+                self.live.add(id(o))
+        self.records.append((fn, ctx, args, outs_t))       # (holds the tensors: their ids stay unique)
+        return outs
+
+    def backward(self, root: Tensor, grad_root: Tensor) -> None:
+        grads = {id(root): grad_root}
+        for fn, ctx, args, outs in reversed(self.records):
+            gouts = tuple(grads.pop(id(o), None) if isinstance(o, Tensor) else None for o in outs)
+            if all(g is None for g in gouts) and not getattr(fn, "always_backward", False):
+                continue
+            gins = fn.backward(ctx, *gouts)
+            gins = gins if isinstance(gins, tuple) else (gins,)
+            for a, g in zip(args, gins):
+                if g is None or not isinstance(a, Tensor):
+                    continue
+                prev = grads.get(id(a))
+                grads[id(a)] = g if prev is None else prev + g
+        self.records.clear()
+
+
+TAPE: Optional[Tape] = None
+
+
+def tape_apply(fn, *args):
+    return fn.apply(*args) if TAPE is None else TAPE.apply(fn, *args)
+
+
 def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
     if t is None:
         return None
@@ -242,12 +301,12 @@ class _Composite16(torch.autograd.Function):
 
 def composite16(sigma: Tensor, bins: Tensor, feat: Tensor, normals: Optional[Tensor] = None,
                 count: Optional[Tensor] = None, blend: bool = False, detach_sigma: bool = False):
-    return _Composite16.apply(sigma, bins, feat, normals, count, blend, detach_sigma)
+    return tape_apply(_Composite16, sigma, bins, feat, normals, count, blend, detach_sigma)
 
 
 def composite(sigma: Tensor, bins: Tensor, feat: Optional[Tensor] = None, count: Optional[Tensor] = None):
     """Alpha compositing of one ray batch (K8).  Returns (weights, accumulation, median_depth, feat_out)."""
-    return _Composite.apply(sigma, bins, feat, count)
+    return tape_apply(_Composite, sigma, bins, feat, count)
 
 
 def render_weights(weights: Tensor, feat: Optional[Tensor] = None, bins: Optional[Tensor] = None,
@@ -582,7 +641,7 @@ class _ReflectBundle(torch.autograd.Function):
 
 
 def reflect_bundle(comp16, idx, inv, count, o2_all, wr_all, ndd):
-    return _ReflectBundle.apply(comp16, idx, inv, count, o2_all, wr_all, _f32c(ndd.reshape(-1)))
+    return tape_apply(_ReflectBundle, comp16, idx, inv, count, o2_all, wr_all, _f32c(ndd.reshape(-1)))
 
 
 class _ReflectCompose(torch.autograd.Function):
@@ -627,7 +686,7 @@ def reflect_compose(acc_fine, diff, tint, inv, comp16, bg, acc_r, depth_r=None, 
     """-> (out [N,3], depth_out [N] or empty).  acc_fine [N] (or [N,1]) carries the gradient of the fallback rows."""
     if comp16.shape[1] != 16:
         raise ValueError("reflect_compose: comp16 must be the composited 16-channel feature rows")
-    return _ReflectCompose.apply(acc_fine, diff, tint, inv, comp16, bg, acc_r, depth_r, clamp_inner)
+    return tape_apply(_ReflectCompose, acc_fine, diff, tint, inv, comp16, bg, acc_r, depth_r, clamp_inner)
 
 
 # ----------------------------------------------------------------------------------------- losses
@@ -670,7 +729,28 @@ def loss_workspace(device) -> Tensor:
 
 
 def fused_loss(rgb_c, rgb_f, refl_c, refl_f, image, pnl_c, pnl_f, ol_c, ol_f, coef: Tensor, workspace: Tensor):
-    return _FusedLoss.apply(rgb_c, rgb_f, refl_c, refl_f, image, pnl_c, pnl_f, ol_c, ol_f, coef, workspace)
+    return tape_apply(_FusedLoss, rgb_c, rgb_f, refl_c, refl_f, image, pnl_c, pnl_f, ol_c, ol_f, coef, workspace)
+
+
+class _InfColorRGB(torch.autograd.Function):
+    """bg = feat[:, 0, 0:3] of the infinity-colour pass ([M,1,16] -> [M,3], contiguous) and its scatter-back."""
+
+    @staticmethod
+    def forward(ctx, feat: Tensor):
+        ctx.shape = feat.shape
+        return feat[:, 0, 0:3].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is None:
+            return None
+        gf = g.new_zeros(ctx.shape)
+        gf[:, 0, 0:3] = g
+        return gf
+
+
+def inf_color_rgb(feat_bg: Tensor) -> Tensor:
+    return tape_apply(_InfColorRGB, feat_bg)
 
 
 # ----------------------------------------------------------------------------------------- f1: ray generation

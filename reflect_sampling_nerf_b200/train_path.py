@@ -120,6 +120,7 @@ def _claim_stash(field, n_points: int, device) -> _StashSlot:
 # ----------------------------------------------------------------------------------------- one field pass
 class _FieldPass(torch.autograd.Function):
     """One fused field evaluation over all samples of a ray batch (mode 0) or the infinity colour (mode 1)."""
+    always_backward = True        # (ops.Tape) the backward also releases the stash slot
 
     @staticmethod
     def forward(ctx, field, mode: int, primary: bool, count: Optional[Tensor], origins, dirs, area, bins, *params):
@@ -168,7 +169,8 @@ class _FieldPass(torch.autograd.Function):
                 field.__dict__["_grad_blob_static"] = blob
             blob.zero_()
             field._grad_blob = blob
-            torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_grads(field))
+            if ops.TAPE is None:          # (the tape's owner flushes explicitly)
+                torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_grads(field))
         g_area = ops.field_backward(wblob_t, slot.buf, mode, origins if mode == 0 else None, dirs, area.reshape(-1),
                                     bins if mode == 0 else None, n, s, None if g_sigma is None else g_sigma.contiguous(),
                                     g_feat.contiguous(), feat, aux, field._dy_buffer, want_area, ctx.count)
@@ -181,7 +183,8 @@ class _FieldPass(torch.autograd.Function):
 
 
 def field_pass(field, mode: int, primary: bool, origins, dirs, area, bins, count: Optional[Tensor] = None):
-    return _FieldPass.apply(field, mode, primary, count, origins, dirs, area, bins, *[p for p in field.parameters()])
+    return ops.tape_apply(_FieldPass, field, mode, primary, count, origins, dirs, area, bins,
+                          *[p for p in field.parameters()])
 
 
 # ----------------------------------------------------------------------------------------- the path
@@ -247,7 +250,7 @@ def get_outputs(model, ray_bundle, grad: bool) -> Dict[str, Tensor]:
     nears2, fars2 = model._bounce_planes(n, dev)                       # zeros * near (App. B Q4), ones * far
     if grad:
         _, feat_bg, _ = field_pass(field, ops.MODE_INF_COLOR, False, None, w_r, sqr, None, count)
-        bg = feat_bg[:, 0, ops.F_RGB]
+        bg = ops.inf_color_rgb(feat_bg)
     else:
         bg = field.get_inf_color(w_r, sqr, count)
     # E. reflected coarse (model.py:292-313)
@@ -291,14 +294,16 @@ def sync_parameters(field, src: int = 0) -> None:
 class TrainStep:
     """One optimizer step of the hot path: get_outputs + get_loss_dict + backward (+ flat-gradient all-reduce)
     + fused RAdam / exponential decay / bf16 re-pack (reflect_sampling_nerf_config.py:50-53).  Used by bench.py and the
-    tests; under nerfstudio the Trainer does the same through the model's public methods and
+    tests; under nerfstudio the Trainer does the same through the model's public methods, torch.autograd and
     reflect_sampling_nerf_b200.optim.FusedRAdam.
 
-    graph=True captures the whole step (forward, backward, all-reduce, optimizer) in a CUDA graph after `warmup` eager
-    steps; inputs are copied into static buffers and the step is one cudaGraphLaunch."""
+    The backward is replayed from ops.Tape (the same Function.backward kernels torch.autograd would call, in the same
+    order, on one thread and one stream); autograd=True runs it through torch.autograd instead (A/B tests).
+    graph=True captures the whole step (forward, backward, all-reduce, optimizer) in a CUDA graph after 3 eager steps;
+    inputs are copied into static buffers and the step is one cudaGraphLaunch."""
 
     def __init__(self, model, world_size: int = 1, lr: float = 1e-3, lr_final: float = 0.0, max_steps: int = 0,
-                 graph: bool = False, torch_optimizer: bool = False) -> None:
+                 graph: bool = False, torch_optimizer: bool = False, autograd: bool = False) -> None:
         from .optim import FusedRAdam
         self.model = model
         model.field.dp_world_size = world_size
@@ -310,20 +315,49 @@ class TrainStep:
         else:
             self.opt = FusedRAdam(params, lr=lr, eps=1e-15, lr_final=lr_final, max_steps=max_steps, field=model.field)
         self.fused = not torch_optimizer
-        self.graph_requested, self.graph, self.static = graph and self.fused, None, None
+        self.autograd = autograd
+        self.graph_requested, self.graph, self.static = graph and self.fused and not autograd, None, None
         self.steps_done = 0
+        self._one = None
+
+    def _forward_backward_tape(self, ray_bundle, image: Tensor) -> Tensor:
+        field = self.model.field
+        if not self.model.training:
+            raise RuntimeError("TrainStep needs the model in training mode")
+        tape = ops.Tape()
+        for p in field.parameters():
+            tape.live.add(id(p))
+        with torch.no_grad():
+            ops.TAPE = tape
+            try:
+                out = self.model(ray_bundle)
+                self.model.get_loss_dict(out, {"image": image})
+                total = self.model.__dict__.pop("_fused_loss_total")
+                if self._one is None or self._one.device != total.device:
+                    self._one = torch.ones((), device=total.device)
+                tape.backward(total, self._one)
+            finally:
+                ops.TAPE = None
+                tape.records.clear()
+            _flush_grads(field)
+        self.last_outputs = out
+        return total
 
     def _eager(self, ray_bundle, image: Tensor) -> Tensor:
-        if not self.fused:
-            self.opt.zero_grad(set_to_none=True)
-        out = self.model(ray_bundle)
-        loss_dict = self.model.get_loss_dict(out, {"image": image})
-        total = self.model.__dict__.pop("_fused_loss_total", None)
-        loss = total if total is not None else sum(loss_dict.values())
-        loss.backward()
+        if self.autograd or not self.fused:
+            if not self.fused:
+                self.opt.zero_grad(set_to_none=True)
+            out = self.model(ray_bundle)
+            loss_dict = self.model.get_loss_dict(out, {"image": image})
+            total = self.model.__dict__.pop("_fused_loss_total", None)
+            loss = total if total is not None else sum(loss_dict.values())
+            loss.backward()
+            self.last_outputs = out
+            loss = loss.detach()
+        else:
+            loss = self._forward_backward_tape(ray_bundle, image)
         self.opt.step()
-        self.last_outputs = out
-        return loss.detach()
+        return loss
 
     def step(self, ray_bundle, image: Tensor) -> Tensor:
         self.steps_done += 1

@@ -131,7 +131,7 @@ def test_composite16_fused_normal_losses(S):
     ((w2 * gw).sum() + (acc2 * gacc).sum() + (fo2 * gfo).sum() + c_pn * pn_loss + c_ol * o_loss
      + (blend2 * gblend).sum()).backward()
     torch.testing.assert_close(blend, blend2, rtol=1e-6, atol=1e-6)
-    assert float((blend2 == 1.0).float().mean()) > 0.02          # the clip is active for some rays
+    assert float((blend2 == 1.0).float().mean()) > 0.005         # the clip is active for some rays
     torch.testing.assert_close(w, w2, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(fo, fo2, rtol=1e-5, atol=1e-6)
     assert torch.equal(depth, depth2)

@@ -56,7 +56,10 @@ def test_ide_encoder_matches_oracle_fp32():
     got = IntegratedSHEncoding()(d.cuda(), rho.cuda()).cpu()
     ref = R.ide(d, rho)
     assert got.shape == ref.shape == (p, 34)
-    torch.testing.assert_close(got, ref, rtol=2e-5, atol=2e-6)
+    # the degree-8 band evaluates polynomials like 6435 z^8 - 12012 z^6 + 6930 z^4 - 1260 z^2 + 35 with heavy cancellation:
+    # two fp32 evaluation orders (oracle: z**8 ...; kernel: products of z^2, z^4) differ by up to ~1e-5 absolute there
+    torch.testing.assert_close(got[:, :17], ref[:, :17], rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(got[:, 17:], ref[:, 17:], rtol=2e-5, atol=3e-5)
 
 
 @pytest.mark.parametrize("kind,area,n,s", [("uniform", 3.2e-6, 96, 64), ("reciprocal", 0.02, 64, 64)])
@@ -85,8 +88,9 @@ def test_stashed_encoding_blocks_are_the_oracle_encodings_at_bf16_half_ulp(kind,
                          for t in range(n_tiles)]).float()
     ide_got = torch.cat([_unswizzle(stash[t, 38 * 16384:39 * 16384]) for t in range(n_tiles)]).float()
     assert float(enc_got[:, 99:].abs().max()) == 0.0 and float(ide_got[:, 34:].abs().max()) == 0.0     # zero padding
-    # bf16 half-ulp: |x_bf16 - x| <= 2^-9 |x| (+ the fp32-level error of the encoder itself)
+    # bf16 half-ulp: 8 significant bits => |x_bf16 - x| <= 2^-9 * 2^ceil(log2 |x|) <= 2^-8 |x| (+ the fp32-level error of the
+    # encoder itself, up to 3e-5 in the cancelling degree-8 IDE band)
     for got, ref, name in ((enc_got[:, :99], ipe, "ipe"), (ide_got[:, :34], ide, "ide")):
-        tol = ref.abs() * 2.0 ** -8 * 0.5 + 4e-6
+        tol = ref.abs() * 2.0 ** -8 * 1.001 + (4e-6 if name == "ipe" else 3e-5)
         bad = (got - ref).abs() > tol
         assert not bool(bad.any()), (name, int(bad.sum()), float((got - ref).abs().max()))

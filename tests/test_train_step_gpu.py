@@ -129,6 +129,27 @@ def test_train_step_is_sync_free_and_graph_replay_matches_eager():
     torch.testing.assert_close(results["graph"][1], results["eager"][1], rtol=0, atol=2e-4)
 
 
+def test_tape_backward_equals_torch_autograd_backward():
+    """TrainStep replays the backward kernels from ops.Tape; torch.autograd (what nerfstudio's Trainer drives through
+    loss.backward()) must produce the same flat gradient up to the order of the wgrad's fp32 atomics."""
+    n = 512
+    o, d, pa, img = [t.cuda() for t in synthetic_rays(n, 61, pixel_area=3.2e-6)]
+    g = torch.Generator().manual_seed(2)
+    jit = {k: torch.rand(n, s, generator=g).cuda() for k, s in (("uniform", 33), ("pdf", 33), ("reciprocal", 17), ("reflect_pdf", 17))}
+    flats, losses = [], []
+    for autograd in (False, True):
+        torch.manual_seed(0)
+        model = ReflectSamplingNeRFModel(ReflectSamplingNeRFModelConfig(**SIZES)).cuda().train()
+        model.set_jitter(**jit)
+        stepper = TrainStep(model, autograd=autograd)
+        losses.append(stepper.step(RayBundle(origins=o, directions=d, pixel_area=pa), img).clone())
+        flats.append(model.field._flat_grad.clone())
+        assert sum(s_.in_flight for s_ in model.field._stash_pool) == 0
+    torch.cuda.synchronize()
+    torch.testing.assert_close(losses[0], losses[1], rtol=1e-6, atol=0)
+    torch.testing.assert_close(flats[0], flats[1], rtol=1e-4, atol=1e-6 * float(flats[1].abs().max()))
+
+
 def test_two_forwards_before_one_backward_use_separate_stashes():
     """a second training forward must not overwrite the activation stash of a graph that has not
     run its backward yet -- gradients of the first graph equal those of a single forward/backward."""
