@@ -326,9 +326,11 @@ def run_b200(args):
         src = "MEASURED_PEAKS.json (bf16_tflops_sustained: kernels timed inside a long step; hbm_gbs)" if peaks \
             else "B200_PROFILING.md fallback"
         by = {}
-        for (name, a, b, flop, nbytes) in prof:
+        for (name, a, b, flop, nbytes, count, cap_rays) in prof:
+            # bounce passes: the launch is sized for the capacity, the work is what the device-side ray count covered
+            scale = min(int(count), cap_rays) / cap_rays if (count is not None and cap_rays) else 1.0
             d = by.setdefault(name, [0.0, 0.0, 0.0, 0])
-            d[0] += a.elapsed_time(b); d[1] += flop; d[2] += nbytes; d[3] += 1
+            d[0] += a.elapsed_time(b); d[1] += flop * scale; d[2] += nbytes * scale; d[3] += 1
         for name, (ms, flop, nbytes, cnt) in by.items():
             tf, gb = flop / ms / 1e9, nbytes / ms / 1e6
             hbm_bound = (gb / bw_peak) > (tf / tf_peak)
@@ -343,7 +345,7 @@ def run_b200(args):
         roof_all.sort(key=lambda r: -r["share_of_step"])
         roof = dict(roof_all[0], peak_source=src,
                     timed_in="an eager pass over the same K steps (the CUDA-graph replay cannot carry per-kernel events); "
-                             "bounce-pass work is counted at the launch capacity N, an upper bound of the M rays it covers")
+                             "bounce-pass work is counted for the M rays the device-side count covered, not the launch capacity")
 
     cpu_base, cuda_base = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

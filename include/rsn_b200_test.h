@@ -21,6 +21,11 @@ int rsn_field_backward_fused(const void* wblob_t, const void* x_stash, int mode,
                              rsn_stream_t stream);
 int64_t rsn_field_backward_fused_workspace_bytes(int64_t n_points);
 
+/* In-kernel cycle trace of the forward field kernel (RSN_FWD_DEBUG & 32): (tag, clock64) pairs of the third tile of CTA 0 of
+ * the last traced launch -> HOST host_out[2 * max_pairs]; returns the number of pairs, resets the trace, synchronises.
+ * Tags: csrc/field_fwd.cu. */
+int rsn_debug_fwd_trace(long long* host_out, int max_pairs);
+
 /* ---- tcgen05 building-block probes (unit tests of csrc/umma.cuh) ---------------------------------- */
 int rsn_probe_umma_kmajor(const void* x_blocks, const void* w_blocks, int64_t n_out, int64_t k_blocks,
                           int64_t n_split, float* out, rsn_stream_t stream);

@@ -67,6 +67,7 @@ _SIGNATURES = {
 _SIGNATURES_DBG = {
     "rsn_field_backward_fused": ([P, P, I32, P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P], c_int),
     "rsn_field_backward_fused_workspace_bytes": ([I64], c_int64),
+    "rsn_debug_fwd_trace": ([P, I32], c_int),
     "rsn_probe_umma_kmajor": ([P, P, I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_2cta": ([P, P, I64, I64, P, P], c_int),
     "rsn_probe_epilogue": ([I64, I64, I64, P, P], c_int),

@@ -87,6 +87,29 @@ struct FwdParams {
   int debug;                // RSN_FWD_DEBUG (test build only; timing experiments): 2 = no trig in the prologue, 4 = no weight streaming, 8 = no stash bulk stores (TS form)
 };
 
+// In-kernel cycle trace (test build, RSN_FWD_DEBUG & 32): (tag, clock64) pairs of the third tile of CTA 0, read back with
+// rsn_debug_fwd_trace.  Tags: 1000 + 10 l + g issuer saw act_ready[g] while issuing layer l | 1500 + l issuer committed
+// layer l | 2000 + l epilogue (warp 6, lane 0) saw acc_full of layer l | 2100 + 10 l + g group g handed over |
+// 2200 + 10 l + g group g staged (stash) | 3000 prologue row encoded.
+#ifdef RSN_DEBUG_SWITCHES
+__device__ long long g_fwd_trace[8192];
+__device__ int g_fwd_trace_n;
+#define RSN_TRACE(on, tag)                                   \
+  do {                                                       \
+    if (on) {                                                \
+      const int i_ = atomicAdd(&g_fwd_trace_n, 2);           \
+      if (i_ < 8190) {                                       \
+        g_fwd_trace[i_] = (long long)(tag);                  \
+        g_fwd_trace[i_ + 1] = clock64();                     \
+      }                                                      \
+    }                                                        \
+  } while (0)
+#else
+#define RSN_TRACE(on, tag) \
+  do {                     \
+  } while (0)
+#endif
+
 constexpr int MAX_STAGES = 6;
 struct Barriers {
   uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
@@ -510,6 +533,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         const int eb = it & 1;
         const uint32_t enc_a = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
         bool acc;
+        const bool tr = (p.debug & 32) && blockIdx.x == 0 && it == 2;
         // ---- base layers 0..7
         for (int l = 0; l < 8; ++l) {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
@@ -529,13 +553,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           if (l > 0) {
             for (int g = 0; g < 4; ++g) {
               wait_act(g);
+              RSN_TRACE(tr, 1000 + 10 * l + g);
               if (g == 3) request_bias(it * WIDE_LAYERS + l + 1);
               const uint32_t w = ring_wait();
+              RSN_TRACE(tr, 1100 + 10 * l + g);
               issue_act(g, w, ID256, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
               ring_release();
             }
           }
           commit(&bars.acc_full[buf]);
+          RSN_TRACE(tr, 1500 + l);
           buf ^= 1;
         }
         // ---- layer 8: bottleneck (N=256) + heads (N=16, other buffer, columns 240..255)
@@ -669,6 +696,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           else epilogue_group<RELU, false, SBIAS, TS, !TS>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, nullptr, a_t);
           publish(&bars.act_ready[g], blk, stash_blk);
         }
+        RSN_TRACE((p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0, 2100 + 10 * (bias_off / 256) + g);
       };
       using T_ = std::integral_constant<bool, true>;
       using F_ = std::integral_constant<bool, false>;
@@ -678,6 +706,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       // two hand-overs of the layer-critical chain.
       auto layer_lag = [&](auto ng_c, int bias_off, uint32_t sb, int mask_layer, int stash_blk0, bool first) {
         constexpr int NG = decltype(ng_c)::value;
+        const bool tr_ = (p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0;
+        (void)tr_;
         if constexpr (TS) {
           uint32_t a2[2][32];
           auto stage = [&](int g, const uint32_t (&a)[32]) {
@@ -697,13 +727,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
                   arrive_issuer(&bars.act_ready[g]);
                 },
                 NoOp());
+            RSN_TRACE(tr_, 2100 + 10 * mask_layer + g);
             if (g > 0) stage(g - 1, a2[(g - 1) & 1]);
+            if (g > 0) RSN_TRACE(tr_, 2200 + 10 * mask_layer + g - 1);
           }
           stage(NG - 1, a2[(NG - 1) & 1]);
         }
       };
+      const bool tr = (p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0;
       for (int l = 0; l < 8; ++l) {
         wait_acc();
+        RSN_TRACE(tr, 2000 + l);
         const uint32_t sb = bias_slot();
         if (TS && st) {
           layer_lag(std::integral_constant<int, 4>{}, BIAS_BASE + l * 256, sb, l, STASH_H + 4 * l, l == 0);
@@ -1006,3 +1040,18 @@ extern "C" int rsn_field_forward_points(const void* wblob, const float* bias, co
   p.aux = aux;
   return launch_fwd(p, stream);
 }
+
+#ifdef RSN_DEBUG_SWITCHES
+// Test build: copies the (tag, clock) trace of the last traced launch to host_out[2 * max_pairs]; returns the pair count
+// and resets the trace.  Synchronises the device.
+extern "C" int rsn_debug_fwd_trace(long long* host_out, int max_pairs) {
+  int n = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  cudaMemcpyFromSymbol(&n, g_fwd_trace_n, sizeof(int));
+  n = std::min(n / 2, std::min(max_pairs, 4095));
+  cudaMemcpyFromSymbol(host_out, g_fwd_trace, (size_t)n * 2 * sizeof(long long));
+  const int zero = 0;
+  cudaMemcpyToSymbol(g_fwd_trace_n, &zero, sizeof(int));
+  return n;
+}
+#endif

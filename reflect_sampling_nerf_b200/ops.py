@@ -43,10 +43,13 @@ KERNEL_WORK = {
 
 
 class _Prof:
-    """CUDA-event bracket around one kernel launch on the launching stream, active only while PROFILE is a list."""
+    """CUDA-event bracket around one kernel launch on the launching stream, active only while PROFILE is a list.
+    n_units = work units (points / samples / bins) at the launch capacity; with a device-side ray `count` the entry also
+    carries (count tensor, rays at capacity) so that the reader can scale the work to the rays actually processed."""
 
-    def __init__(self, name: str, n_units: int):
+    def __init__(self, name: str, n_units: int, count: Optional[Tensor] = None, cap_rays: int = 0):
         self.name, self.n, self.on = name, n_units, PROFILE is not None
+        self.count, self.cap_rays = count, cap_rays
 
     def __enter__(self):
         if self.on:
@@ -58,7 +61,7 @@ class _Prof:
         if self.on and PROFILE is not None:
             self.e1.record()
             flop, nbytes = KERNEL_WORK[self.name]
-            PROFILE.append((self.name, self.e0, self.e1, self.n * flop, self.n * nbytes))
+            PROFILE.append((self.name, self.e0, self.e1, self.n * flop, self.n * nbytes, self.count, self.cap_rays))
         return False
 
 
@@ -164,7 +167,7 @@ def sample_spaced(nears: Tensor, fars: Tensor, n_samples: int, kind: int, t_rand
     cols = 0 if t_rand is None else t_rand.shape[-1]
     if t_rand is not None and t_rand.shape[0] != n:
         raise ValueError(f"t_rand has {t_rand.shape[0]} rows for {n} rays")
-    with _Prof("sample_spaced_kernel", n * (n_samples + 1)):
+    with _Prof("sample_spaced_kernel", n * (n_samples + 1), count, n):
         _lib.call("rsn_sample_spaced", _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(_linspace_bins(n_samples, dev)),
                   _lib.ptr(t_rand), cols, kind, float(tan), _lib.ptr(spacing), _lib.ptr(euclid), n, n_samples, _cnt(count),
                   _lib.stream())
@@ -193,7 +196,7 @@ def pdf_resample(weights: Tensor, spacing_bins: Tensor, nears: Tensor, fars: Ten
     out_s = torch.empty(n, n_out + 1, device=dev, dtype=torch.float32)
     out_e = torch.empty_like(out_s)
     inds = torch.empty(n, n_out + 1, device=dev, dtype=torch.int64) if return_inds else None
-    with _Prof("pdf_resample_kernel", n * (n_out + 1)):
+    with _Prof("pdf_resample_kernel", n * (n_out + 1), count, n):
         _lib.call("rsn_pdf_resample", _lib.ptr(weights), weights.stride(0), _lib.ptr(spacing_bins), _lib.ptr(nears),
                   _lib.ptr(fars), _lib.ptr(_pdf_u_base(n_out, bool(train), dev)), _lib.ptr(rand), kind, float(tan),
                   float(histogram_padding), _lib.ptr(out_s), _lib.ptr(out_e), _lib.ptr(inds), n, s, n_out,
@@ -269,7 +272,7 @@ class _Composite16(torch.autograd.Function):
         pnl, ol = (torch.empty(n if normals is not None else 0, device=dev, dtype=torch.float32) for _ in range(2))
         feat_out = torch.empty(n, 16, device=dev, dtype=torch.float32)
         rgb = torch.empty(n if blend else 0, 3, device=dev, dtype=torch.float32)
-        with _Prof("composite_fwd_kernel", n * s):
+        with _Prof("composite_fwd_kernel", n * s, count, n):
             _lib.call("rsn_composite16_fwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1, _lib.ptr(feat),
                       _lib.ptr(normals), _lib.ptr(weights), _lib.ptr(acc), _lib.ptr(depth), _lib.ptr(feat_out),
                       _lib.ptr(pnl) if normals is not None else None, _lib.ptr(ol) if normals is not None else None,
@@ -290,7 +293,7 @@ class _Composite16(torch.autograd.Function):
         # keep the contiguous copies alive until the launch is enqueued (a freed temporary's block is handed to the
         # next allocation at once)
         g_w, g_acc, g_feat_out, g_pnl, g_ol, g_rgb = (_f32c(t) for t in (g_w, g_acc, g_feat_out, g_pnl, g_ol, g_rgb))
-        with _Prof("composite_bwd_kernel", n * s):
+        with _Prof("composite_bwd_kernel", n * s, ctx.count, n):
             _lib.call("rsn_composite16_bwd", _lib.ptr(sigma), bins.data_ptr(), bins.data_ptr() + 4, s + 1, _lib.ptr(feat),
                       _lib.ptr(normals) if ctx.has_normals else None, _lib.ptr(g_w), _lib.ptr(g_acc), _lib.ptr(g_feat_out),
                       _lib.ptr(g_pnl) if ctx.has_normals else None, _lib.ptr(g_ol) if ctx.has_normals else None,
@@ -370,7 +373,7 @@ def field_forward(wblob: Tensor, bias: Tensor, origins: Tensor, dirs: Tensor, pi
     sigma = torch.empty(n, s, device=bins.device, dtype=torch.float32)
     feat = torch.empty(n, s, N_FEAT, device=bins.device, dtype=torch.float32)
     aux = torch.empty(n, s, 8, device=bins.device, dtype=torch.float32) if want_aux else None
-    with _Prof("field_fwd_kernel", n * s):
+    with _Prof("field_fwd_kernel", n * s, count, n):
         _lib.call("rsn_field_forward_train", _lib.ptr(wblob), _lib.ptr(bias), MODE_SAMPLES, _lib.ptr(origins),
                   _lib.ptr(dirs), _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), None,
                   _lib.ptr(aux), _cnt(count), _lib.stream())
@@ -455,7 +458,7 @@ def field_forward_train(wblob: Tensor, bias: Tensor, mode: int, origins: Optiona
         stash = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     elif stash.numel() < nbytes or stash.dtype != torch.uint8 or stash.device != dev:
         raise ValueError("field_forward_train: stash workspace too small")
-    with _Prof("field_fwd_kernel[train]", n * s):
+    with _Prof("field_fwd_kernel[train]", n * s, count, n):
         _lib.call("rsn_field_forward_train", _lib.ptr(wblob), _lib.ptr(bias), mode, _lib.ptr(origins), _lib.ptr(dirs),
                   _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(sigma), _lib.ptr(feat), _lib.ptr(stash),
                   _lib.ptr(aux), _cnt(count), _lib.stream())
@@ -477,7 +480,7 @@ def field_backward(wblob_t: Tensor, stash: Tensor, mode: int, origins, dirs, are
     """K5 dgrad chain: fills dy_stash; returns dL/d pixel_area (mode 0) / dL/d sqradius (mode 1) per POINT [n,s]
     when want_area."""
     g_area = torch.empty(n, s, device=stash.device, dtype=torch.float32) if want_area else None
-    with _Prof("field_chain_kernel<backward+area>" if want_area else "field_chain_kernel<backward>", n * s):
+    with _Prof("field_chain_kernel<backward+area>" if want_area else "field_chain_kernel<backward>", n * s, count, n):
         _lib.call("rsn_field_backward", _lib.ptr(wblob_t), _lib.ptr(stash), mode, _lib.ptr(origins), _lib.ptr(dirs),
                   _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(g_sigma), _lib.ptr(g_feat), _lib.ptr(feat),
                   _lib.ptr(aux), _lib.ptr(dy_stash), _lib.ptr(g_area), _cnt(count), _lib.stream())
@@ -503,7 +506,7 @@ def field_backward_fused(wblob_t: Tensor, stash: Tensor, mode: int, origins, dir
 def field_wgrad(stash: Tensor, dy_stash: Tensor, n_points: int, grad_blob: Tensor, count: Optional[Tensor] = None,
                 points_per_ray: int = 1) -> None:
     """K5 wgrad: accumulates dW / db of every Linear over the pass into grad_blob (fp32, wgrad_layout())."""
-    with _Prof("field_wgrad_kernel", n_points):
+    with _Prof("field_wgrad_kernel", n_points, count, n_points // max(points_per_ray, 1)):
         _lib.call("rsn_field_wgrad", _lib.ptr(stash), _lib.ptr(dy_stash), n_points, _lib.ptr(grad_blob), _cnt(count),
                   points_per_ray, _lib.stream())
 

@@ -79,9 +79,14 @@ def test_stashed_encoding_blocks_are_the_oracle_encodings_at_bf16_half_ulp(kind,
     stash = stash.cpu().reshape(-1, tile_bytes)
     ex = lambda x: x[:, None, :].expand(n, s, x.shape[-1])  # noqa: E731
     with torch.no_grad():
-        mean, cov = R.frustum_gaussian(ex(o), ex(d), bins[:, :-1, None], bins[:, 1:, None], ex(pa))
-        mean, cov = R.contract(mean, cov)
-        ipe = R.ipe(mean, cov).reshape(-1, 99)
+        # The Gaussians the fused prologue computed (same device arithmetic: csrc/blob.cu mirrors it operation by operation;
+        # tests/test_field_api_gpu.py pins them against the oracle's at 1e-6).  Feeding the ORACLE's own Gaussians instead
+        # would add their 1-ulp differences in x (ATen's CPU sqrt / reduction order) times 2 pi f -- up to 1e-3 at the
+        # undamped frequencies -- to what is meant to be a test of the encoding and its bf16 rounding.
+        mean_g, cov_g = ops.contract(*ops.frustum_gaussians(o.cuda(), d.cuda(), pa.cuda(), bins.cuda()))
+        mean_o, cov_o = R.contract(*R.frustum_gaussian(ex(o), ex(d), bins[:, :-1, None], bins[:, 1:, None], ex(pa)))
+        torch.testing.assert_close(mean_g.cpu(), mean_o, rtol=2e-6, atol=2e-6)
+        ipe = R.ipe(mean_g.cpu(), cov_g.cpu()).reshape(-1, 99)
         ide = R.ide(ex(d), feat[..., ops.F_ROUGH_SOFTPLUS, None].cpu()).reshape(-1, 34)
     n_tiles = (n * s) // 128
     enc_got = torch.cat([torch.cat([_unswizzle(stash[t, 0:16384]), _unswizzle(stash[t, 16384:32768])], dim=1)

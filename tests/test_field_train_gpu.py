@@ -251,8 +251,40 @@ def test_gradients_against_the_bf16_emulated_autograd_oracle():
         rows.append((_cos(got, p.grad), float(got.norm() / p.grad.norm()), name))
     print("\n".join(f"{c:.5f} {r:.4f} {nme}" for c, r, nme in sorted(rows)))
     for c, r, name in rows:
-        assert c > 0.999, (name, c, r)
-        assert abs(r - 1) < 0.02, (name, c, r)
+        assert c > 0.9998, (name, c, r)          # measured: >= 0.99993
+        assert abs(r - 1) < 0.005, (name, c, r)  # measured: within 0.25 %
+
+
+def test_pixel_area_gradient_against_fp32_and_bf16_emulated_oracles():
+    """d loss / d pixel_area of a reflected pass (the roughness -> cone-width path, model.py:272,286): the chain kernel
+    continues through layer 0 and the IPE damping using the bf16-stashed encodings.  Per-ray values against (i) fp32
+    autograd and (ii) autograd of the bf16-operand emulation (same forward rounding)."""
+    n, s = 96, 64
+    field, o, d, pa, bins, g = _setup(n, s, 33, "reciprocal", 1.0)
+    ex = lambda x: x[:, None, :].expand(n, s, x.shape[-1])  # noqa: E731
+    g_rgb = torch.randn(n, s, 3, generator=g) * 0.1
+    refs = {}
+    for kind in ("fp32", "bf16"):
+        pa_k = pa.clone().requires_grad_(True)
+        mean, cov = R.frustum_gaussian(ex(o), ex(d), bins[:, :-1, None], bins[:, 1:, None], ex(pa_k))
+        mean, cov = R.contract(mean, cov)
+        heads = field.point_heads(mean, cov, ex(d), primary=False) if kind == "fp32" else _bf16_heads(field, mean, cov, ex(d))
+        (g_rgb * heads["rgb"]).sum().backward()
+        refs[kind] = pa_k.grad[:, 0].clone()
+        field.zero_grad()
+    g_feat = torch.zeros(n, s, 16)
+    g_feat[..., 0:3] = g_rgb
+    _, _, _, _, _, g_area = _run_mine(field, 0, o, d, pa, bins, torch.zeros(n, s), g_feat, True)
+    got = g_area.cpu().sum(-1)
+    for kind, ref in refs.items():
+        c, r = _cos(got, ref), float(got.norm() / ref.norm())
+        med = float(((got - ref).abs() / (ref.abs() + 1e-3 * float(ref.abs().max()))).median())
+        print(f"d pixel_area vs {kind} oracle: cosine {c:.5f}, norm ratio {r:.4f}, median relative error {med:.4f}, sum ratio {float(got.sum() / ref.sum()):.4f}")
+    # measured on B200: fp32 oracle cosine 0.9996 / norm +6.5 %; bf16-emulated oracle cosine 0.99999 / norm +0.09 % / median
+    # per-ray error 0.5 % => the kernel follows the bf16 network's own gradient; the distance to fp32 autograd is the
+    # forward's bf16 rounding (north_star prescribes the bf16 MLP), not the damping-Jacobian shortcut
+    assert _cos(got, refs["fp32"]) > 0.995 and abs(float(got.norm() / refs["fp32"].norm()) - 1) < 0.10
+    assert _cos(got, refs["bf16"]) > 0.9999 and abs(float(got.norm() / refs["bf16"].norm()) - 1) < 0.005
 
 
 def test_field_kernels_accept_empty_batches():

@@ -16,8 +16,12 @@ SIZES = dict(num_coarse_samples=32, num_importance_samples=32, num_reflect_coars
              num_reflect_importance_samples=16)
 C2 = dict(num_coarse_samples=128, num_importance_samples=128, num_reflect_coarse_samples=64, num_reflect_importance_samples=64)
 # thresholds quoted in DESIGN.md §2: (min cosine, max |norm ratio - 1|) over the parameter tensors of a whole step
-GATE_COS, GATE_NORM = 0.995, 0.03
-GATE_ROUGHNESS_NORM = 0.10      # field_output_roughness: heavy-tailed sum over rays of the bf16 d pixel_area path
+# (measured on B200, 2026-10-18: cosine >= 0.9988, norm within 1.0 % for every tensor but the roughness head)
+GATE_COS, GATE_NORM = 0.998, 0.02
+# field_output_roughness ([1,256] + [1]): its gradient is the sum over bouncing rays of d loss / d pixel_area, each the
+# difference of ~100 large damping-Jacobian terms of the bf16 chain -- 6.5 % low at 512 rays x 16 samples, 1.3 % high at
+# C2's sample counts; tests/test_field_train_gpu.py bounds the per-pass error against an fp32 and a bf16-emulated oracle
+GATE_ROUGHNESS_NORM = 0.10
 
 
 def _cos(a, b):
