@@ -92,21 +92,29 @@ struct FwdParams {
 // layer l | 2000 + l epilogue (warp 6, lane 0) saw acc_full of layer l | 2100 + 10 l + g group g handed over |
 // 2200 + 10 l + g group g staged (stash) | 3000 prologue row encoded.
 #ifdef RSN_DEBUG_SWITCHES
+// fire-and-forget stores into a per-role region (issuer: pairs 0..2047, epilogue: 2048..4095) with the index in a register:
+// nothing on the traced warp's critical path but the clock read and one st.global
 __device__ long long g_fwd_trace[8192];
-__device__ int g_fwd_trace_n;
-#define RSN_TRACE(on, tag)                                   \
-  do {                                                       \
-    if (on) {                                                \
-      const int i_ = atomicAdd(&g_fwd_trace_n, 2);           \
-      if (i_ < 8190) {                                       \
-        g_fwd_trace[i_] = (long long)(tag);                  \
-        g_fwd_trace[i_ + 1] = clock64();                     \
-      }                                                      \
-    }                                                        \
+__device__ int g_fwd_trace_n[2];
+#define RSN_TRACE(on, tag)                                            \
+  do {                                                                \
+    if ((on) && trace_i < 2047) {                                     \
+      g_fwd_trace[trace_base + 2 * trace_i] = (long long)(tag);       \
+      g_fwd_trace[trace_base + 2 * trace_i + 1] = clock64();          \
+      ++trace_i;                                                      \
+    }                                                                 \
   } while (0)
+#define RSN_TRACE_DECL(role) int trace_i = 0; const int trace_base = (role) * 4096; (void)trace_base
+#define RSN_TRACE_END(on, role) do { if (on) g_fwd_trace_n[role] = trace_i; } while (0)
 #else
 #define RSN_TRACE(on, tag) \
   do {                     \
+  } while (0)
+#define RSN_TRACE_DECL(role) \
+  do {                       \
+  } while (0)
+#define RSN_TRACE_END(on, role) \
+  do {                          \
   } while (0)
 #endif
 
@@ -529,6 +537,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       };
       request_bias(0);
       request_bias(1);
+      RSN_TRACE_DECL(0);
       for (int it = 0; it < n_my_tiles; ++it) {
         const int eb = it & 1;
         const uint32_t enc_a = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
@@ -622,6 +631,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           commit(&bars.acc_full[buf]);
           buf ^= 1;
         }
+        RSN_TRACE_END(tr, 0);
       }
     }
   } else if (warp >= 6) {
@@ -633,6 +643,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     uint32_t af_phase = 0;
     int buf = 0;
     int jw = 0;   // wide layers converted so far
+    RSN_TRACE_DECL(1);
     // bias slot of the wide layer about to be converted (waits until its bulk copy has landed)
     auto bias_slot = [&]() -> uint32_t {
       mbar_wait(&bars.bias_full[jw & 1], (uint32_t)(jw >> 1) & 1u);
@@ -867,6 +878,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         }
         buf ^= 1;
       }
+      RSN_TRACE_END(tr, 1);
     }
   } else {
     // ===================================================================== prologue warps (next tile's IPE)
@@ -1045,13 +1057,17 @@ extern "C" int rsn_field_forward_points(const void* wblob, const float* bias, co
 // Test build: copies the (tag, clock) trace of the last traced launch to host_out[2 * max_pairs]; returns the pair count
 // and resets the trace.  Synchronises the device.
 extern "C" int rsn_debug_fwd_trace(long long* host_out, int max_pairs) {
-  int n = 0;
+  int n[2] = {0, 0};
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-  cudaMemcpyFromSymbol(&n, g_fwd_trace_n, sizeof(int));
-  n = std::min(n / 2, std::min(max_pairs, 4095));
-  cudaMemcpyFromSymbol(host_out, g_fwd_trace, (size_t)n * 2 * sizeof(long long));
-  const int zero = 0;
-  cudaMemcpyToSymbol(g_fwd_trace_n, &zero, sizeof(int));
-  return n;
+  cudaMemcpyFromSymbol(n, g_fwd_trace_n, sizeof(n));
+  int total = 0;
+  for (int r = 0; r < 2; ++r) {
+    const int k = std::min(std::min(n[r], 2047), max_pairs - total);
+    if (k > 0) cudaMemcpyFromSymbol(host_out + 2 * total, g_fwd_trace, (size_t)k * 2 * sizeof(long long), (size_t)r * 4096 * sizeof(long long));
+    total += std::max(k, 0);
+  }
+  const int zero[2] = {0, 0};
+  cudaMemcpyToSymbol(g_fwd_trace_n, zero, sizeof(zero));
+  return total;
 }
 #endif
