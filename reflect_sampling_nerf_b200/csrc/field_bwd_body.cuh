@@ -330,9 +330,13 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // (whole warp: control flow and barrier waits; tcgen05.mma / tcgen05.commit under elect_one_sync(), see umma.cuh)
+    {
       int stage = 0;
       uint32_t wphase = 0, ar_phase = 0;
+      auto mma_commit = [&](uint64_t* bar) {
+        if (elect_one_sync()) umma::mma_commit(bar);
+      };
       int buf = 0;
       constexpr uint32_t ID256 = instr_desc_bf16(128, 256, 0, 0);
       constexpr uint32_t ID128 = instr_desc_bf16(128, 128, 0, 0);
@@ -356,11 +360,13 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
       constexpr uint32_t HI = desc_hi_sw128(1024);
       auto issue_kb = [&](uint32_t a_addr, uint32_t b_addr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool& acc) {
         const uint32_t a_lo = desc_lo(a_addr, 16), b_lo = desc_lo(b_addr, 16);
-        mma_bf16_ss_lo(tmem_d, a_lo, b_lo, HI, idesc, acc ? 1u : 0u);
-        if (ksteps == 4) {
-          mma_bf16_ss_lo(tmem_d, a_lo + 2, b_lo + 2, HI, idesc, 1u);
-          mma_bf16_ss_lo(tmem_d, a_lo + 4, b_lo + 4, HI, idesc, 1u);
-          mma_bf16_ss_lo(tmem_d, a_lo + 6, b_lo + 6, HI, idesc, 1u);
+        if (elect_one_sync()) {
+          mma_bf16_ss_lo(tmem_d, a_lo, b_lo, HI, idesc, acc ? 1u : 0u);
+          if (ksteps == 4) {
+            mma_bf16_ss_lo(tmem_d, a_lo + 2, b_lo + 2, HI, idesc, 1u);
+            mma_bf16_ss_lo(tmem_d, a_lo + 4, b_lo + 4, HI, idesc, 1u);
+            mma_bf16_ss_lo(tmem_d, a_lo + 6, b_lo + 6, HI, idesc, 1u);
+          }
         }
         acc = true;
       };
@@ -371,10 +377,12 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           issue_kb(s_act + g * BLOCK_BYTES, b_addr, 4, idesc, tmem_d, acc);
         } else {
           const uint32_t b_lo = desc_lo(b_addr, 16), a0 = tmem + (uint32_t)(buf ^ 1) * 256 + (uint32_t)g * 32u;
-          mma_bf16_ts_lo(tmem_d, a0, b_lo, HI, idesc, acc ? 1u : 0u);
-          mma_bf16_ts_lo(tmem_d, a0 + 8, b_lo + 2, HI, idesc, 1u);
-          mma_bf16_ts_lo(tmem_d, a0 + 16, b_lo + 4, HI, idesc, 1u);
-          mma_bf16_ts_lo(tmem_d, a0 + 24, b_lo + 6, HI, idesc, 1u);
+          if (elect_one_sync()) {
+            mma_bf16_ts_lo(tmem_d, a0, b_lo, HI, idesc, acc ? 1u : 0u);
+            mma_bf16_ts_lo(tmem_d, a0 + 8, b_lo + 2, HI, idesc, 1u);
+            mma_bf16_ts_lo(tmem_d, a0 + 16, b_lo + 4, HI, idesc, 1u);
+            mma_bf16_ts_lo(tmem_d, a0 + 24, b_lo + 6, HI, idesc, 1u);
+          }
           acc = true;
         }
       };

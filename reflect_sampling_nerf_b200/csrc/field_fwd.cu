@@ -459,7 +459,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the control flow and the barrier waits; every single-thread instruction (tcgen05.mma,
+    // tcgen05.commit, the bias bulk copies) is issued under elect_one_sync() by the warp's elected lane.
+    {
       int stage = 0;
       uint32_t wphase = 0;
       uint32_t ar_phase = 0;  // bit g: parity of the next completion of act_ready[g]
@@ -469,7 +471,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       constexpr uint32_t ID128 = instr_desc_bf16(MM, 128, 0, 0);
       constexpr uint32_t ID16 = instr_desc_bf16(MM, 16, 0, 0);
       constexpr uint32_t BDIV = 1;
-      auto commit = [&](uint64_t* bar) { mma_commit(bar); };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one_sync()) mma_commit(bar);
+      };
       auto wait_in = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
       auto ring_wait = [&]() -> uint32_t {
         mbar_wait(&bars.w_full[stage], wphase);
@@ -495,10 +499,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         auto mma = [&](uint32_t k2, uint32_t accum) {
           mma_bf16_ss_lo(tmem_d, a_lo + k2, b_lo + k2, HI, idesc, accum);
         };
-        mma(0, acc ? 1u : 0u);
-        mma(2, 1u);
-        mma(4, 1u);
-        if (ksteps == 4) mma(6, 1u);
+        if (elect_one_sync()) {
+          mma(0, acc ? 1u : 0u);
+          mma(2, 1u);
+          mma(4, 1u);
+          if (ksteps == 4) mma(6, 1u);
+        }
         acc = true;
       };
       // K-block g of the hidden activations: shared-memory block g (SS) or TMEM columns [32 g, 32 g + 32) of the buffer
@@ -508,17 +514,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           issue_kb(s_act + g * BLOCK_BYTES, b_addr, 4, idesc, tmem_d, acc);
         } else {
           const uint32_t b_lo = desc_lo(b_addr, 16), a0 = a_tm + (uint32_t)g * 32u;
-          mma_bf16_ts_lo(tmem_d, a0, b_lo, HI, idesc, acc ? 1u : 0u);
-          mma_bf16_ts_lo(tmem_d, a0 + 8, b_lo + 2, HI, idesc, 1u);
-          mma_bf16_ts_lo(tmem_d, a0 + 16, b_lo + 4, HI, idesc, 1u);
-          mma_bf16_ts_lo(tmem_d, a0 + 24, b_lo + 6, HI, idesc, 1u);
+          if (elect_one_sync()) {
+            mma_bf16_ts_lo(tmem_d, a0, b_lo, HI, idesc, acc ? 1u : 0u);
+            mma_bf16_ts_lo(tmem_d, a0 + 8, b_lo + 2, HI, idesc, 1u);
+            mma_bf16_ts_lo(tmem_d, a0 + 16, b_lo + 4, HI, idesc, 1u);
+            mma_bf16_ts_lo(tmem_d, a0 + 24, b_lo + 6, HI, idesc, 1u);
+          }
           acc = true;
         }
       };
       // Bias of wide layer j (10 per tile) -> slot j & 1, requested as soon as the epilogue of layer j - 2 has published
       // its last group (the issuer sees that as the last act_ready wait of layer j - 1).
       auto request_bias = [&](int j) {
-        if (j >= n_my_tiles * WIDE_LAYERS) return;
+        if (j >= n_my_tiles * WIDE_LAYERS || !elect_one_sync()) return;
         const int jl = j % WIDE_LAYERS;
         uint8_t* const slot = smem + SMEM_BIAS + (j & 1) * BIAS_SLOT_BYTES;
         if (jl < 8) {
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         const int eb = it & 1;
         const uint32_t enc_a = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
         bool acc;
-        const bool tr = (p.debug & 32) && blockIdx.x == 0 && it == 2;
+        const bool tr = (p.debug & 32) && blockIdx.x == 0 && it == 2 && lane == 0;
         // ---- base layers 0..7
         for (int l = 0; l < 8; ++l) {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
@@ -567,7 +575,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
               const uint32_t w = ring_wait();
               RSN_TRACE(tr, 1100 + 10 * l + g);
               issue_act(g, w, ID256, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
+              RSN_TRACE(tr, 1200 + 10 * l + g);
               ring_release();
+              RSN_TRACE(tr, 1300 + 10 * l + g);
             }
           }
           commit(&bars.acc_full[buf]);
@@ -724,7 +734,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           auto stage = [&](int g, const uint32_t (&a)[32]) {
             const uint32_t blk = s_act + g * BLOCK_BYTES;
             if (first) warp_store_guard<1>(lane); else warp_store_guard<3>(lane);
+            RSN_TRACE(tr_, 2300 + 10 * mask_layer + g);
             stage_row<true>(a, blk, row, masks + mask_entry(mask_layer, g, row));
+            RSN_TRACE(tr_, 2400 + 10 * mask_layer + g);
             if (!(p.debug & 8)) warp_store_rows(sblk(stash_blk0 + g), blk, q, lane);
           };
 #pragma unroll

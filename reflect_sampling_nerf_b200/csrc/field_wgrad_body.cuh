@@ -145,7 +145,8 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_slabs > 0) {
+    // (whole warp: control flow and barrier waits; tcgen05.mma / tcgen05.commit under elect_one_sync(), see umma.cuh)
+    if (n_slabs > 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t idesc = instr_desc_bf16(128, nb * 64, 1, 1);
@@ -157,7 +158,7 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
         // one K=16 step (16 points) advances the start address by 2048 bytes
         constexpr uint32_t HI = desc_hi_sw128(1024);
         const uint32_t a_lo = desc_lo(base, SLAB_BLOCK_BYTES), b_lo = desc_lo(base + mb * SLAB_BLOCK_BYTES, SLAB_BLOCK_BYTES);
-        if ((p.debug & 3) != 2) {
+        if ((p.debug & 3) != 2 && elect_one_sync()) {
           // all K-steps of the slab into one accumulator, then the other: interleaving the two accumulators MMA by
           // MMA is measurably slower (2.6 vs 4.2 ms for the MMA stream alone at C2)
 #pragma unroll
@@ -169,13 +170,13 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
               mma_bf16_ss_lo(tmem + 256, a_lo + (2 * SLAB_BLOCK_BYTES >> 4) + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
           }
         }
-        mma_commit(&bars.empty[stage]);
+        if (elect_one_sync()) mma_commit(&bars.empty[stage]);
         if (++stage == W_STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      mma_commit(&bars.acc_full);
+      if (elect_one_sync()) mma_commit(&bars.acc_full);
     }
   } else if (warp < 6) {   // (the fused backward kernel launches one more warp than this role uses)
     // ---- db: column sums of the dY slabs while they sit in shared memory; then the dW flush.

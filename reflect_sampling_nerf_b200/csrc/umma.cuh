@@ -52,6 +52,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of the (fully converged) warp, the same one for the same member mask every time.  Code under `if
+// (elect_one_sync())` is known to ptxas to run on exactly one thread: its operands go to uniform registers with a plain
+// R2UR, where code under `if (lane == 0)` gets an ELECT / BRA.U.ANY waterfall loop around every tcgen05.mma, commit and
+// bulk copy (measured: ~620 cycles of issue work per 4-MMA group against 512 cycles of tensor time).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ proxies / fences
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads, bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -32,7 +32,8 @@ for rep in range(2):
 ev = sorted(((buf[2 * i + 1], buf[2 * i]) for i in range(npairs)))
 t0 = ev[0][0]
 print(f"# {mode}: {npairs} events; cycles relative to the first event")
-names = {10: "issuer act_ready", 11: "issuer ring_ready", 15: "issuer commit", 20: "epi acc_full", 21: "epi handover", 22: "epi staged"}
+names = {10: "issuer act_ready", 11: "issuer ring_ready", 12: "issuer mma issued", 13: "issuer ring released", 15: "issuer commit",
+         20: "epi acc_full", 21: "epi handover", 22: "epi staged", 23: "epi  stage: guard done", 24: "epi  stage: row in smem"}
 for t, tag in ev:
     kind = tag // 100
     l, g = (tag % 100) // 10, tag % 10
