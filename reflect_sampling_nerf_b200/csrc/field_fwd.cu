@@ -122,12 +122,10 @@ constexpr int MAX_STAGES = 6;
 struct Barriers {
   uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
   uint64_t enc_full[2], enc_empty[2];
-  uint64_t act_ready[8];         // [accumulator buffer of the producing layer use][64-column group]: two sets, so that a
-                                 // waiter may lag by more than one layer use without aliasing the phase parity
+  uint64_t act_ready[4];
   uint64_t ide_ready;
   uint64_t acc_full[2];
   uint64_t bias_full[2];         // the bias slot (wide layer j -> slot j & 1) has landed
-  uint64_t a_free[2];            // training (TS): the stash warps have read the A operand that lived in accumulator buffer b
   uint32_t tmem_slot;
 };
 static_assert(sizeof(Barriers) <= 256, "Barriers must fit their shared-memory slot");
@@ -419,8 +417,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         mbar_init(&bars.acc_full[i], 1);
         mbar_init(&bars.bias_full[i], 1);
       }
-      for (int i = 0; i < 8; ++i) mbar_init(&bars.act_ready[i], ARRIVALS);
-      for (int i = 0; i < 2; ++i) mbar_init(&bars.a_free[i], 4);
+      for (int i = 0; i < 4; ++i) mbar_init(&bars.act_ready[i], ARRIVALS);
       mbar_init(&bars.ide_ready, ARRIVALS);
       fence_barrier_init();
     }
@@ -433,14 +430,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
   const uint32_t tmem = bars.tmem_slot;
   // tiles of this CTA: blockIdx.x + it * gridDim.x
   const int n_my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  // Training in the TS form: the activation stash is written by the PROLOGUE warps, not by the epilogue.  The epilogue hands
-  // layer l's bf16 output to the next layer through TMEM exactly as in inference; warps 2-5 (idle once the next tile's
-  // encoding is done) read the same packed operand back out of TMEM (tcgen05.ld), derive the ReLU bit masks, stage the rows
-  // in shared memory and bulk-store them -- ~900 cycles per 64-column group that used to sit between two hand-overs of the
-  // layer-critical chain (in-kernel trace).  The issuer re-uses an accumulator buffer only after the stash
-  // warps have released the operand that lived in it (a_free).
-  constexpr int LAYER_USES = 11;               // accumulator-buffer uses per tile: base 0-7, bottleneck, mid, rgb
-  const bool offload = TS && p.stash != nullptr;
   auto tile_of = [&](int it) -> int { return (int)blockIdx.x + it * (int)gridDim.x; };
   auto arrive_issuer = [&](uint64_t* bar) { mbar_arrive(bar); };
 
@@ -475,7 +464,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     {
       int stage = 0;
       uint32_t wphase = 0;
-      uint32_t ar_phase = 0;  // bit 4 b + g: parity of the next completion of act_ready[4 b + g]
+      uint32_t ar_phase = 0;  // bit g: parity of the next completion of act_ready[g]
       int buf = 0;
       constexpr int MM = 128;
       constexpr uint32_t ID256 = instr_desc_bf16(MM, 256, 0, 0);
@@ -499,9 +488,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         }
       };
       auto wait_act = [&](int g) {
-        const int i = (buf ^ 1) * 4 + g;     // handed over by the previous layer use, which accumulated into the other buffer
-        wait_in(&bars.act_ready[i], (ar_phase >> i) & 1u);
-        ar_phase ^= (1u << i);
+        wait_in(&bars.act_ready[g], (ar_phase >> g) & 1u);
+        ar_phase ^= (1u << g);
         tc_fence_after();
       };
       // K-major operands: LBO unused (16), SBO = 1024; one K=16 step advances both start addresses by 32 bytes
@@ -558,12 +546,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       request_bias(0);
       request_bias(1);
       RSN_TRACE_DECL(0);
-      int use = 0;     // accumulator-buffer uses so far (use u accumulates into buffer u & 1)
-      // before the first MMA of use u overwrites buffer u & 1: the A operand of use u - 2 must have been stashed
-      auto wait_a_free = [&]() {
-        if (offload && use >= 2) mbar_wait(&bars.a_free[use & 1], (uint32_t)((use - 2) >> 1) & 1u);
-        ++use;
-      };
       for (int it = 0; it < n_my_tiles; ++it) {
         const int eb = it & 1;
         const uint32_t enc_a = s_enc + (uint32_t)eb * 2 * BLOCK_BYTES;
@@ -573,7 +555,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         for (int l = 0; l < 8; ++l) {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
-          wait_a_free();
           if (l == 0) {
             wait_in(&bars.enc_full[eb], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
@@ -607,7 +588,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
-          wait_a_free();
           const uint32_t a_tm = tmem + (uint32_t)(buf ^ 1) * 256;
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
@@ -629,7 +609,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
-          wait_a_free();
           for (int c = 0; c < 2; ++c) {
             wait_act(2 * c);
             wait_act(2 * c + 1);
@@ -652,7 +631,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
-          wait_a_free();
           wait_act(0);
           wait_act(1);
           request_bias(it * WIDE_LAYERS + 11);
@@ -728,7 +706,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
                 [&]() {
                   tmem_st_wait();
                   tc_fence_before();
-                  arrive_issuer(&bars.act_ready[buf * 4 + g]);
+                  arrive_issuer(&bars.act_ready[g]);
                 },
                 guard_g);
             if (!(p.debug & 8)) warp_store_rows(stash_blk, blk, q, lane);   // 8: timing experiment without the stash stores
@@ -737,7 +715,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           if (!TS) guard_g();
           if (st && stash_blk) epilogue_group<RELU, MASKS, SBIAS, TS, true>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, mask_ptr, a_t);
           else epilogue_group<RELU, false, SBIAS, TS, !TS>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, nullptr, a_t);
-          publish(&bars.act_ready[buf * 4 + g], blk, stash_blk);
+          publish(&bars.act_ready[g], blk, stash_blk);
         }
         RSN_TRACE((p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0, 2100 + 10 * (bias_off / 256) + g);
       };
@@ -769,7 +747,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
                 [&]() {
                   tmem_st_wait();
                   tc_fence_before();
-                  arrive_issuer(&bars.act_ready[buf * 4 + g]);
+                  arrive_issuer(&bars.act_ready[g]);
                 },
                 NoOp());
             RSN_TRACE(tr_, 2100 + 10 * mask_layer + g);
@@ -784,9 +762,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         RSN_TRACE(tr, 2000 + l);
         const uint32_t sb = bias_slot();
-        if (offload) {
-          for (int g = 0; g < 4; ++g) convert(T_{}, F_{}, BIAS_BASE + l * 256, sb, g, nullptr, nullptr, false);
-        } else if (TS && st) {
+        if (TS && st) {
           layer_lag(std::integral_constant<int, 4>{}, BIAS_BASE + l * 256, sb, l, STASH_H + 4 * l, l == 0);
         } else {
           for (int g = 0; g < 4; ++g)
@@ -879,9 +855,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       {
         wait_acc();
         const uint32_t sb = bias_slot();
-        if (offload) {
-          for (int g = 0; g < 2; ++g) convert(T_{}, F_{}, BIAS_MID, sb, g, nullptr, nullptr, false);
-        } else if (TS && st) {
+        if (TS && st) {
           layer_lag(std::integral_constant<int, 2>{}, BIAS_MID, sb, 8, STASH_MIDH, false);
         } else {
           for (int g = 0; g < 2; ++g)
@@ -919,56 +893,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       RSN_TRACE_END(tr, 1);
     }
   } else {
-    // ===================================================================== prologue warps (next tile's IPE; training: the stash)
+    // ===================================================================== prologue warps (next tile's IPE)
     const int row = (warp - 2) * 32 + lane;
-    const int q = warp & 3;                                   // TMEM lane quarter this warp may touch (rows 32 q ..)
-    const int srow = q * 32 + lane;                           // the row this thread stashes (its TMEM lane)
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t ar_phase = 0;                                    // bit 4 b + g: parity of the next completion of act_ready[4 b + g]
-    int sbuf = 0;                                             // accumulator buffer of the layer use being stashed
-    // Stash duty for one tile: follow the epilogue's hand-overs layer use by layer use, copy each handed-over 64-column
-    // group out of TMEM (it stays valid until the issuer re-uses the buffer two layer uses later, which waits for a_free),
-    // derive the ReLU bit masks, stage the rows and bulk-store the layer's blocks behind ONE proxy fence.
-    auto stash_tile = [&](int tile) {
-      uint8_t* const st = p.stash + (size_t)tile * STASH_TILE_BYTES;
-      uint2* const masks = reinterpret_cast<uint2*>(st + STASH_MASK_OFF);
-      auto wait_group = [&](int g) {
-        const int i = sbuf * 4 + g;
-        mbar_wait(&bars.act_ready[i], (ar_phase >> i) & 1u);
-        ar_phase ^= (1u << i);
-        tc_fence_after();
-      };
-      auto release = [&]() {                                  // this warp no longer reads the operand in buffer sbuf
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.a_free[sbuf]);
-        sbuf ^= 1;
-      };
-      // one layer use with NG stashed groups: mask layer ml, stash blocks blk0 .. blk0 + NG - 1
-      auto stash_layer = [&](int ng, int ml, int blk0) {
-        warp_store_guard<0>(lane);                            // the previous layer's bulk stores have read the staging slices
-        for (int g = 0; g < ng; ++g) {
-          wait_group(g);
-          uint32_t a[32];
-          tmem_ld32(tlane + (uint32_t)sbuf * 256 + (uint32_t)g * 32u, a);
-          tmem_ld_wait();
-          stage_row<true>(a, s_act + g * BLOCK_BYTES, srow, masks + mask_entry(ml, g, srow));
-        }
-        release();
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0 && !(p.debug & 8)) {
-          for (int g = 0; g < ng; ++g)
-            bulk_s2g_u32(st + (size_t)(blk0 + g) * BLOCK_BYTES + q * 4096, s_act + g * BLOCK_BYTES + (uint32_t)q * 4096u, 4096);
-          bulk_commit();
-        }
-      };
-      for (int l = 0; l < 8; ++l) stash_layer(4, l, STASH_H + 4 * l);
-      for (int g = 0; g < 4; ++g) wait_group(g);              // bottleneck: not stashed (csrc/field_wgrad.cu), only observed
-      release();
-      stash_layer(2, 8, STASH_MIDH);                          // mid hidden
-      release();                                              // rgb: nothing handed over; keeps one release per layer use
-    };
     for (int it = 0; it < n_my_tiles; ++it) {
       const int eb = it & 1;
       const int tile = tile_of(it);
@@ -1026,9 +952,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         fence_proxy_async();
       }
       arrive_issuer(&bars.enc_full[eb]);
-      if (offload && it > 0) stash_tile(tile_of(it - 1));
     }
-    if (offload && n_my_tiles > 0) stash_tile(tile_of(n_my_tiles - 1));
   }
 
   if (p.stash && lane == 0 && warp >= 2) bulk_wait_all<0>();
