@@ -731,13 +731,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         (void)tr_;
         if constexpr (TS) {
           uint32_t a2[2][32];
+          // The layer's NG blocks leave through ONE proxy fence and one bulk group at the end of the layer: per group the
+          // fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) + bulk issue cost ~430 cycles and the wait_group.read guard ~210 in
+          // the in-kernel trace, between two hand-overs of the layer-critical chain.
+          (void)first;
           auto stage = [&](int g, const uint32_t (&a)[32]) {
             const uint32_t blk = s_act + g * BLOCK_BYTES;
-            if (first) warp_store_guard<1>(lane); else warp_store_guard<3>(lane);
+            if (g == 0) warp_store_guard<0>(lane);     // the previous layer's bulk stores have read the staging slices
             RSN_TRACE(tr_, 2300 + 10 * mask_layer + g);
             stage_row<true>(a, blk, row, masks + mask_entry(mask_layer, g, row));
             RSN_TRACE(tr_, 2400 + 10 * mask_layer + g);
-            if (!(p.debug & 8)) warp_store_rows(sblk(stash_blk0 + g), blk, q, lane);
           };
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
@@ -755,6 +758,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
             if (g > 0) RSN_TRACE(tr_, 2200 + 10 * mask_layer + g - 1);
           }
           stage(NG - 1, a2[(NG - 1) & 1]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 8)) {           // 8: timing experiment without the stash stores
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+              bulk_s2g_u32(sblk(stash_blk0 + g) + q * 4096, s_act + g * BLOCK_BYTES + (uint32_t)q * 4096u, 4096);
+            bulk_commit();
+          }
+          RSN_TRACE(tr_, 2200 + 10 * mask_layer + NG - 1);
         }
       };
       const bool tr = (p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0;
