@@ -124,7 +124,7 @@ struct Barriers {
   uint64_t enc_full[2], enc_empty[2];
   uint64_t act_ready[4];
   uint64_t ide_ready;
-  uint64_t acc_full[2];
+  uint64_t acc_full[4];          // [accumulator buffer][output half: columns 0-127 | 128-255]
   uint64_t bias_full[2];         // the bias slot (wide layer j -> slot j & 1) has landed
   uint32_t tmem_slot;
 };
@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars.enc_full[i], ARRIVALS);
         mbar_init(&bars.enc_empty[i], 1);
-        mbar_init(&bars.acc_full[i], 1);
+        mbar_init(&bars.acc_full[2 * i], 1);
+        mbar_init(&bars.acc_full[2 * i + 1], 1);
         mbar_init(&bars.bias_full[i], 1);
       }
       for (int i = 0; i < 4; ++i) mbar_init(&bars.act_ready[i], ARRIVALS);
@@ -471,6 +472,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       constexpr uint32_t ID128 = instr_desc_bf16(MM, 128, 0, 0);
       constexpr uint32_t ID16 = instr_desc_bf16(MM, 16, 0, 0);
       constexpr uint32_t BDIV = 1;
+      constexpr uint32_t HALF_B = 128u * 128u;   // bytes of 128 weight rows (one output half) inside a [256][64] K-block image
       auto commit = [&](uint64_t* bar) {
         if (elect_one_sync()) mma_commit(bar);
       };
@@ -480,13 +482,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         tc_fence_after();
         return s_w + (uint32_t)stage * STB;
       };
-      auto ring_release = [&]() {
-        commit(&bars.w_empty[stage]);
+      auto ring_advance = [&]() -> int {     // -> the slot just consumed (to be released with ring_release_slot)
+        const int s_ = stage;
         if (++stage == NS) {
           stage = 0;
           wphase ^= 1;
         }
+        return s_;
       };
+      auto ring_release_slot = [&](int s_) { commit(&bars.w_empty[s_]); };
+      auto ring_release = [&]() { ring_release_slot(ring_advance()); };
       auto wait_act = [&](int g) {
         wait_in(&bars.act_ready[g], (ar_phase >> g) & 1u);
         ar_phase ^= (1u << g);
@@ -559,28 +564,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
             wait_in(&bars.enc_full[eb], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
           }
+          // The 256 outputs of a wide layer are two N = 128 accumulations (columns 0-127 | 128-255 of the buffer, weight rows
+          // 0-127 | 128-255 of every K-block image).  Same tensor time as N = 256, but the first half is COMMITTED while the
+          // tensor pipe still works on the second: the epilogue converts groups 0, 1 (and the next layer's first K-blocks
+          // start) two K-block times earlier -- with one tile in flight, the stretch between the last hand-over of layer l
+          // and the first of layer l + 1 is where the tensor pipe idled (in-kernel trace: ~1,100 of ~3,200 cycles per layer).
+          // Issue order: [kb0: h0 h1] [kb1: h0 h1] [kb2: h0] [kb3: h0] commit(h0) [kb2: h1] [kb3: h1] commit(h1).
+          bool acc1 = false;                                  // (acc = half 0, acc1 = half 1)
+          const uint32_t a_tm = tmem + (uint32_t)(buf ^ 1) * 256;
           if (l == 0 || l == 4) {
             uint32_t w = ring_wait();
-            issue_kb(enc_a, w, 4, ID256, tm, acc);
+            issue_kb(enc_a, w, 4, ID128, tm, acc);
+            issue_kb(enc_a, w + HALF_B, 4, ID128, tm + 128, acc1);
             ring_release();
             w = ring_wait();
-            issue_kb(enc_a + BLOCK_BYTES, w, ENC_KSTEPS_B1, ID256, tm, acc);
+            issue_kb(enc_a + BLOCK_BYTES, w, ENC_KSTEPS_B1, ID128, tm, acc);
+            if (l == 0) commit(&bars.acc_full[2 * buf]);
+            issue_kb(enc_a + BLOCK_BYTES, w + HALF_B, ENC_KSTEPS_B1, ID128, tm + 128, acc1);
             ring_release();
+            if (l == 0) commit(&bars.acc_full[2 * buf + 1]);
           }
           if (l > 0) {
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
               wait_act(g);
               RSN_TRACE(tr, 1000 + 10 * l + g);
-              if (g == 3) request_bias(it * WIDE_LAYERS + l + 1);
               const uint32_t w = ring_wait();
-              RSN_TRACE(tr, 1100 + 10 * l + g);
-              issue_act(g, w, ID256, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
-              RSN_TRACE(tr, 1200 + 10 * l + g);
+              issue_act(g, w, ID128, tm, a_tm, acc);
+              issue_act(g, w + HALF_B, ID128, tm + 128, a_tm, acc1);
               ring_release();
-              RSN_TRACE(tr, 1300 + 10 * l + g);
             }
+            wait_act(2);
+            RSN_TRACE(tr, 1000 + 10 * l + 2);
+            const uint32_t w2 = ring_wait();
+            const int s2 = ring_advance();
+            issue_act(2, w2, ID128, tm, a_tm, acc);
+            wait_act(3);
+            RSN_TRACE(tr, 1000 + 10 * l + 3);
+            request_bias(it * WIDE_LAYERS + l + 1);
+            const uint32_t w3 = ring_wait();
+            const int s3 = ring_advance();
+            issue_act(3, w3, ID128, tm, a_tm, acc);
+            commit(&bars.acc_full[2 * buf]);
+            issue_act(2, w2 + HALF_B, ID128, tm + 128, a_tm, acc1);
+            ring_release_slot(s2);
+            issue_act(3, w3 + HALF_B, ID128, tm + 128, a_tm, acc1);
+            ring_release_slot(s3);
+            commit(&bars.acc_full[2 * buf + 1]);
           }
-          commit(&bars.acc_full[buf]);
           RSN_TRACE(tr, 1500 + l);
           buf ^= 1;
         }
@@ -589,20 +619,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
           const uint32_t a_tm = tmem + (uint32_t)(buf ^ 1) * 256;
-          for (int g = 0; g < 4; ++g) {
+          bool acc1 = false;
+          for (int g = 0; g < 2; ++g) {
             wait_act(g);
-            if (g == 3) request_bias(it * WIDE_LAYERS + 9);
             const uint32_t w = ring_wait();
-            issue_act(g, w, ID256, tm, a_tm, acc);
+            issue_act(g, w, ID128, tm, a_tm, acc);
+            issue_act(g, w + HALF_B, ID128, tm + 128, a_tm, acc1);
             ring_release();
           }
+          wait_act(2);
+          const uint32_t w2 = ring_wait();
+          const int s2 = ring_advance();
+          issue_act(2, w2, ID128, tm, a_tm, acc);
+          wait_act(3);
+          request_bias(it * WIDE_LAYERS + 9);
+          const uint32_t w3 = ring_wait();
+          const int s3 = ring_advance();
+          issue_act(3, w3, ID128, tm, a_tm, acc);
+          commit(&bars.acc_full[2 * buf]);
+          issue_act(2, w2 + HALF_B, ID128, tm + 128, a_tm, acc1);
+          ring_release_slot(s2);
+          issue_act(3, w3 + HALF_B, ID128, tm + 128, a_tm, acc1);
+          ring_release_slot(s3);
+          // the heads ride behind the second half: its commit covers them (the epilogue reads them after groups 2, 3)
           const uint32_t w = ring_wait();
           bool acc_h = false;
           for (int kb = 0; kb < 4; ++kb)
             issue_act(kb, w + kb * (N_HEAD * 128 / BDIV), ID16, tmem + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, a_tm,
                       acc_h);
           ring_release();
-          commit(&bars.acc_full[buf]);
+          commit(&bars.acc_full[2 * buf + 1]);
           buf ^= 1;
         }
         // ---- layer 9: mid MLP, A = [bottleneck 256 | IDE 48], N = 128
@@ -623,7 +669,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           const uint32_t w = ring_wait();
           issue_kb(enc_a, w, IDE_KSTEPS, ID128, tm, acc);
           ring_release();
-          commit(&bars.acc_full[buf]);
+          commit(&bars.acc_full[2 * buf]);
           commit(&bars.enc_empty[eb]);
           buf ^= 1;
         }
@@ -638,7 +684,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           issue_act(0, w, ID16, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
           issue_act(1, w + N_HEAD * 128 / BDIV, ID16, tm, tmem + (uint32_t)(buf ^ 1) * 256, acc);
           ring_release();
-          commit(&bars.acc_full[buf]);
+          commit(&bars.acc_full[2 * buf]);
           buf ^= 1;
         }
         RSN_TRACE_END(tr, 0);
@@ -668,9 +714,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       const bool valid = pt < n_points;
       uint8_t* const st = (p.stash && tile < n_tiles) ? p.stash + (size_t)tile * STASH_TILE_BYTES : nullptr;
       auto sblk = [&](int b) -> uint8_t* { return st ? st + (size_t)b * BLOCK_BYTES : nullptr; };
-      auto wait_acc = [&]() {
-        mbar_wait(&bars.acc_full[buf], (af_phase >> buf) & 1u);
-        af_phase ^= (1u << buf);
+      auto wait_acc = [&](int h = 0) {     // output half h of the layer accumulating into `buf` is complete
+        const int i = 2 * buf + h;
+        mbar_wait(&bars.acc_full[i], (af_phase >> i) & 1u);
+        af_phase ^= (1u << i);
         tc_fence_after();
       };
       // publish a freshly written block (rows of this warp): optional coalesced stash store, then the barrier
@@ -744,6 +791,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           };
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
+            if (g == 2) wait_acc(1);
             const uint32_t acc_c = tlane + (uint32_t)buf * 256 + g * 64, a_t = tlane + (uint32_t)buf * 256 + g * 32;
             epilogue_group_core<true, true, SBIAS, true, true, true, true>(
                 acc_c, bias_off + g * 64, s_act + g * BLOCK_BYTES, row, sb + g * 256, nullptr, a_t, a2[g & 1],
@@ -777,8 +825,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         if (TS && st) {
           layer_lag(std::integral_constant<int, 4>{}, BIAS_BASE + l * 256, sb, l, STASH_H + 4 * l, l == 0);
         } else {
-          for (int g = 0; g < 4; ++g)
+          for (int g = 0; g < 4; ++g) {
+            if (g == 2) wait_acc(1);
             convert(T_{}, T_{}, BIAS_BASE + l * 256, sb, g, masks + mask_entry(l, g, row), sblk(STASH_H + 4 * l + g), l == 0);
+          }
         }
         buf ^= 1;
       }
@@ -788,7 +838,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         wait_acc();
         const uint32_t sb = bias_slot();
         // (not stashed: the wgrad derives everything that involves the bottleneck from h7, csrc/field_wgrad.cu)
-        for (int g = 0; g < 4; ++g) convert(F_{}, F_{}, BIAS_BOTT, sb, g, nullptr, nullptr, false);
+        for (int g = 0; g < 4; ++g) {
+          if (g == 2) wait_acc(1);
+          convert(F_{}, F_{}, BIAS_BOTT, sb, g, nullptr, nullptr, false);
+        }
         uint32_t hv[16];
         tmem_ld16(tlane + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, hv);
         float hb[12];   // head biases: behind the bottleneck bias in this layer's slot (only this layer's request writes there)
