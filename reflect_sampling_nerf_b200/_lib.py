@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RSN_B200_LIB") or os.path.join(_HERE, "librsn_b200.so")   # env override: kernel experiments
-LIB_DBG_PATH = os.path.join(_HERE, "librsn_b200_dbg.so")
+LIB_DBG_PATH = os.environ.get("RSN_B200_LIB_DBG") or os.path.join(_HERE, "librsn_b200_dbg.so")
 _lib = None
 _lib_dbg = None
 
@@ -76,6 +76,7 @@ _SIGNATURES_DBG = {
     "rsn_probe_umma_rate_2cta": ([I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_rate": ([I32, I32, I64, I64, P, P], c_int),
     "rsn_probe_umma_mnmajor": ([P, P, I64, I64, P, P], c_int),
+    "rsn_probe_umma_mnmajor_cm": ([P, P, I64, I64, I64, P, I64, P, P], c_int),
 }
 
 

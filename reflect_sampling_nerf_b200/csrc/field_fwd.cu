@@ -17,10 +17,13 @@
 //               wide layer's fp32 bias into a two-slot shared-memory buffer two layers ahead
 //   warps 6-9   epilogue: tcgen05.ld the accumulator row of "their" point, bias + ReLU, bf16, and hand the row to the next
 //               layer as its A operand -- by default back into TMEM (tcgen05.st over accumulator columns already read;
-//               the next MMA is tcgen05.mma [d], [a], b-desc), optionally (RSN_FWD_TS=0) in place into the swizzled
-//               shared-memory activation blocks; then, in training, stage the row for the activation stash (bulk store)
-//               and emit the ReLU bit masks; heads, IDE, outputs
+//               the next MMA is tcgen05.mma [d], [a], b-desc), optionally (RSN_FWD_TS=0, inference only) in place into the
+//               swizzled shared-memory activation blocks; heads, IDE, outputs
 //   warps 2-5   prologue for the NEXT tile: frustum gaussian, contraction, IPE -> bf16 A operand (shared memory)
+//   warps 10-13 (training launches only) stash: read the handed-over bf16 operand back out of TMEM (it stays valid until the
+//               issuer re-uses the accumulator buffer two layers later, which waits for a_free), derive the ReLU bit masks
+//               and write the row straight to the activation stash with coalesced st.global.v4 (chunk-major block image,
+//               field_layout.cuh) -- no shared-memory staging, no proxy fence, nothing on the layer-critical path
 // The two 256-column TMEM accumulator buffers alternate by layer, and every layer's epilogue publishes
 // its output per 64-column group (mbarrier act_ready[g]) so that the next layer's K-block g is issued as
 // soon as that group is written: MMA of layer l+1 overlaps the epilogue of layer l.
@@ -53,7 +56,8 @@ constexpr int BIAS_SLOT_BYTES = 1152;
 constexpr int SMEM_BIAS = SMEM_BARS + 256;
 constexpr int SMEM_TOTAL = SMEM_BIAS + 2 * BIAS_SLOT_BYTES;      // 231,936 of the 232,448 a CTA may have
 constexpr int WIDE_LAYERS = 10;                                  // per tile: base 0..7, bottleneck, mid
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 320;          // inference launches
+constexpr int NUM_THREADS_TRAIN = 448;    // + the four stash warps
 
 // (Biases never live in __constant__ memory: every layer's fp32 bias reaches the epilogue through a two-slot shared-memory
 // buffer filled by bulk copies from the caller's bias vector, so two launches with different parameters on two streams
@@ -118,11 +122,13 @@ __device__ int g_fwd_trace_n[2];
   } while (0)
 #endif
 
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 5;
 struct Barriers {
   uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
   uint64_t enc_full[2], enc_empty[2];
-  uint64_t act_ready[4];
+  uint64_t act_ready[8];         // [accumulator buffer the producing layer used][64-column group]: two sets, so that the
+                                 // stash warps may lag the issuer by up to two layers without aliasing the phase parity
+  uint64_t a_free[2];            // training: the stash warps have read the operand that lived in accumulator buffer b
   uint64_t ide_ready;
   uint64_t acc_full[4];          // [accumulator buffer][output half: columns 0-127 | 128-255]
   uint64_t bias_full[2];         // the bias slot (wide layer j -> slot j & 1) has landed
@@ -251,30 +257,15 @@ __device__ __forceinline__ void encode_row(uint32_t enc_saddr, int row, const fl
 }
 
 // ---------------------------------------------------------------------------------------------- epilogue
-// 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> activation block `blk`.
-// MASKS (training): also emit the ReLU bit masks of the group (a separate instantiation, so that the inference path keeps
-// its branch-free schedule: a runtime test of the mask pointer inside the chunk loop cost 0.47 ms of 2.62 at C2)
+// 64 accumulator columns of this thread's row (+bias, optional ReLU) -> bf16 -> the next layer's A operand.
 // The 64 biases come from shared memory (bias_saddr; every lane reads the same 16 bytes: one broadcast wavefront per
 // load).  (A __constant__ table was an INDEXED load -- the layer is a run-time value -- of 10 KB that cycles once per
-// tile: 32 LDC per group, 0.5 ms of 2.66 at C2, measured by replacing the bias with a register constant.)  SBIAS is kept
-// as a template parameter for the call sites' readability; it is always true.
-// TS: the packed row also goes back into TMEM (columns a_taddr..+31) as the next layer's A operand; SMEM: it is written to
-// the shared-memory block (the A operand of the SS form and / or the staging copy of the activation stash).
-// DEFER (TS + stash): the MMA does not read the shared-memory copy, so the row is handed to the next layer first
-// (tcgen05.st, then `early()` = wait::st + fence + arrive) and only then staged for the stash (`guard()`, 8 x st.shared,
-// masks): the staging is off the layer-critical path.
-struct NoOp {
-  __device__ __forceinline__ void operator()() const {}
-};
-// LAG (with DEFER): stop after the hand-over and leave the packed row in `a`; the caller stages it (stage_row) after the
-// NEXT group's hand-over, so that no staging work sits between two groups of the layer-critical chain.
-template <bool RELU, bool MASKS, bool SBIAS, bool TS, bool SMEM, bool DEFER, bool LAG, class Early, class Guard>
-__device__ __forceinline__ void epilogue_group_core(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
-                                                    uint32_t bias_saddr, uint2* mask_out, uint32_t a_taddr,
-                                                    uint32_t (&a)[32], Early early, Guard guard) {
-  static_assert(!DEFER || (TS && SMEM), "DEFER is the TS + stash form");
-  static_assert(!LAG || DEFER, "LAG refines DEFER");
-  uint32_t mbits[2] = {0u, 0u};
+// tile: 32 LDC per group, 0.5 ms of 2.66 at C2, measured by replacing the bias with a register constant.)
+// TS: the packed row goes back into TMEM (columns a_taddr..+31, over accumulator columns this thread has already read);
+// otherwise (SS form, inference in the test build) it is written in place into the swizzled shared-memory block.
+template <bool RELU, bool TS>
+__device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, uint32_t blk_saddr, int row, uint32_t bias_saddr,
+                                               uint32_t a_taddr) {
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
@@ -287,6 +278,7 @@ __device__ __forceinline__ void epilogue_group_core(uint32_t tmem_row_col, int b
   }
   tmem_ld_wait();
   const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
+  uint32_t a[32];   // TS: the 64 bf16 of this row, two per 32-bit TMEM column
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -303,71 +295,34 @@ __device__ __forceinline__ void epilogue_group_core(uint32_t tmem_row_col, int b
         pk[q * 2 + 1] = RELU ? pack_relu_bf16x2(x2, x3) : pack_bf16x2(x2, x3);
       }
       const int chunk = h * 4 + c;
-      if (SMEM && !DEFER) sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      if (!TS) sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
       if (TS) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) a[chunk * 4 + j] = pk[j];
       }
-      if (RELU && MASKS && !DEFER) {
-        // ReLU mask bits of the 8 columns just packed: one packed compare (0xFFFF per half > 0) and one LOP3 per
-        // word; word i of the 32-column half contributes bits i and 16 + i
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = c * 4 + j;
-          __nv_bfloat162 hv;
-          *reinterpret_cast<uint32_t*>(&hv) = pk[j];
-          mbits[h] |= __hgt2_mask(hv, __nv_bfloat162(__float2bfloat16(0.f), __float2bfloat16(0.f))) & (0x00010001u << i);
-        }
-      }
     }
   }
-  // TS: over accumulator columns [32 g, 32 g + 32) of the same buffer, which this thread has already read
   if (TS) tmem_st32(a_taddr, a);
-  if (DEFER) {
-    early();
-    if (LAG) return;
-    if (RELU && MASKS) {   // the mask bits, from the packed words, after the hand-over: off the layer-critical path
-#pragma unroll
-      for (int w = 0; w < 32; ++w) {
-        __nv_bfloat162 hv;
-        *reinterpret_cast<uint32_t*>(&hv) = a[w];
-        mbits[w >> 4] |= __hgt2_mask(hv, __nv_bfloat162(__float2bfloat16(0.f), __float2bfloat16(0.f))) & (0x00010001u << (w & 15));
-      }
-    }
-    guard();
-#pragma unroll
-    for (int chunk = 0; chunk < 8; ++chunk)
-      sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), a[chunk * 4 + 0], a[chunk * 4 + 1], a[chunk * 4 + 2],
-             a[chunk * 4 + 3]);
-  }
-  if (RELU && MASKS) *mask_out = make_uint2(mbits[0], mbits[1]);
 }
-template <bool RELU, bool MASKS = false, bool SBIAS = false, bool TS = false, bool SMEM = true, bool DEFER = false,
-          class Early = NoOp, class Guard = NoOp>
-__device__ __forceinline__ void epilogue_group(uint32_t tmem_row_col, int bias_off, uint32_t blk_saddr, int row,
-                                               uint32_t bias_saddr = 0, uint2* mask_out = nullptr, uint32_t a_taddr = 0,
-                                               Early early = Early(), Guard guard = Guard()) {
-  uint32_t a[32];   // TS: the 64 bf16 of this row, two per 32-bit TMEM column
-  epilogue_group_core<RELU, MASKS, SBIAS, TS, SMEM, DEFER, false>(tmem_row_col, bias_off, blk_saddr, row, bias_saddr, mask_out,
-                                                                  a_taddr, a, early, guard);
-}
-// The staging half of a LAG group: ReLU mask bits from the packed row, the row into its shared-memory block.
-template <bool MASKS>
-__device__ __forceinline__ void stage_row(const uint32_t (&a)[32], uint32_t blk_saddr, int row, uint2* mask_out) {
-  const uint32_t row_saddr = blk_saddr + (uint32_t)row * 128u;
+
+// Stash warps: the packed row (32 words = 64 bf16 of one 64-column group) -> its place in the stash block (chunk-major image:
+// a warp-level st.global.v4 writes 512 contiguous bytes) and the ReLU bit masks of the group (one packed compare + one LOP3
+// per word; word i of a 32-column half contributes bits i and 16 + i).
+__device__ __forceinline__ void stash_row(const uint32_t (&a)[32], uint8_t* blk, int row, uint2* mask_out) {
+  uint8_t* const dst = blk + stash_chunk_off(row, 0);
 #pragma unroll
-  for (int chunk = 0; chunk < 8; ++chunk)
-    sts128(row_saddr + (uint32_t)((chunk ^ (row & 7)) << 4), a[chunk * 4 + 0], a[chunk * 4 + 1], a[chunk * 4 + 2], a[chunk * 4 + 3]);
-  if (MASKS) {
-    uint32_t mbits[2] = {0u, 0u};
+  for (int c = 0; c < 8; ++c)
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * STASH_CHUNK_STRIDE), "r"(a[c * 4 + 0]),
+                 "r"(a[c * 4 + 1]), "r"(a[c * 4 + 2]), "r"(a[c * 4 + 3])
+                 : "memory");
+  uint32_t mbits[2] = {0u, 0u};
 #pragma unroll
-    for (int w = 0; w < 32; ++w) {
-      __nv_bfloat162 hv;
-      *reinterpret_cast<uint32_t*>(&hv) = a[w];
-      mbits[w >> 4] |= __hgt2_mask(hv, __nv_bfloat162(__float2bfloat16(0.f), __float2bfloat16(0.f))) & (0x00010001u << (w & 15));
-    }
-    *mask_out = make_uint2(mbits[0], mbits[1]);
+  for (int w = 0; w < 32; ++w) {
+    __nv_bfloat162 hv;
+    *reinterpret_cast<uint32_t*>(&hv) = a[w];
+    mbits[w >> 4] |= __hgt2_mask(hv, __nv_bfloat162(__float2bfloat16(0.f), __float2bfloat16(0.f))) & (0x00010001u << (w & 15));
   }
+  *mask_out = make_uint2(mbits[0], mbits[1]);
 }
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __expf(-x)); }
@@ -382,14 +337,16 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __ex
 // (The cta_group::2 CTA-pair form and the cluster-multicast weight stream of round 1 were validated bit for bit and
 // lost -- 2.86 vs 2.63 ms and no change, DESIGN.md §4 -- and are no longer part of this kernel; their building blocks stay
 // in umma.cuh and csrc/probe.cu.)
-template <bool TS>
-__global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdParams p) {
+// TRAIN (needs TS): the launch carries four more warps that write the activation stash (see the header); p.stash != NULL.
+template <bool TS, bool TRAIN>
+__global__ void __launch_bounds__(TRAIN ? NUM_THREADS_TRAIN : NUM_THREADS, 1) field_fwd_kernel(const FwdParams p) {
+  static_assert(TS || !TRAIN, "the training form takes its operands from TMEM");
   extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the window starts here
   Barriers& bars = *reinterpret_cast<Barriers*>(smem + SMEM_BARS);
   constexpr bool SBIAS = true;
-  // weight ring: 3 x 32 KB; TS without a stash: the activation blocks are free -> 5 x 32 KB
-  const int NS = (TS && !p.stash) ? 5 : NUM_STAGES;
-  const int ring_off = (TS && !p.stash) ? SMEM_ACT : SMEM_W;
+  // weight ring: 3 x 32 KB behind the shared-memory activation blocks (SS form); TS: no activation blocks -> 5 x 32 KB
+  constexpr int NS = TS ? 5 : NUM_STAGES;
+  constexpr int ring_off = TS ? SMEM_ACT : SMEM_W;
   constexpr uint32_t STB = W_STAGE_BYTES;
   constexpr uint32_t ARRIVALS = TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -418,7 +375,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         mbar_init(&bars.acc_full[2 * i + 1], 1);
         mbar_init(&bars.bias_full[i], 1);
       }
-      for (int i = 0; i < 4; ++i) mbar_init(&bars.act_ready[i], ARRIVALS);
+      for (int i = 0; i < 8; ++i) mbar_init(&bars.act_ready[i], ARRIVALS);
+      for (int i = 0; i < 2; ++i) mbar_init(&bars.a_free[i], 4);
       mbar_init(&bars.ide_ready, ARRIVALS);
       fence_barrier_init();
     }
@@ -448,7 +406,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
             mbar_arrive(&bars.w_full[stage]);     // timing experiment: no weight traffic at all (results are garbage)
           } else {
             mbar_expect_tx(&bars.w_full[stage], bytes);
-            bulk_g2s(smem + ring_off + stage * STB, p.wblob + off, bytes, &bars.w_full[stage]);
+            bulk_g2s(smem + ring_off + stage * (int)STB, p.wblob + off, bytes, &bars.w_full[stage]);
           }
           off += bytes;
           if (++stage == NS) {
@@ -465,8 +423,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     {
       int stage = 0;
       uint32_t wphase = 0;
-      uint32_t ar_phase = 0;  // bit g: parity of the next completion of act_ready[g]
+      uint32_t ar_phase = 0;  // bit 4 b + g: parity of the next completion of act_ready[4 b + g]
       int buf = 0;
+      int use = 0;            // accumulator-buffer uses so far (use u accumulates into buffer u & 1)
+      // TRAIN: before the first MMA of use u overwrites buffer u & 1, the stash warps must have read the operand that the
+      // epilogue of use u - 2 left in its first 128 columns
+      auto wait_a_free = [&]() {
+        if (TRAIN && use >= 2) mbar_wait(&bars.a_free[use & 1], (uint32_t)((use - 2) >> 1) & 1u);
+        ++use;
+      };
       constexpr int MM = 128;
       constexpr uint32_t ID256 = instr_desc_bf16(MM, 256, 0, 0);
       constexpr uint32_t ID128 = instr_desc_bf16(MM, 128, 0, 0);
@@ -493,8 +458,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       auto ring_release_slot = [&](int s_) { commit(&bars.w_empty[s_]); };
       auto ring_release = [&]() { ring_release_slot(ring_advance()); };
       auto wait_act = [&](int g) {
-        wait_in(&bars.act_ready[g], (ar_phase >> g) & 1u);
-        ar_phase ^= (1u << g);
+        const int i = (buf ^ 1) * 4 + g;     // handed over by the previous use, which accumulated into the other buffer
+        wait_in(&bars.act_ready[i], (ar_phase >> i) & 1u);
+        ar_phase ^= (1u << i);
         tc_fence_after();
       };
       // K-major operands: LBO unused (16), SBO = 1024; one K=16 step advances both start addresses by 32 bytes
@@ -560,6 +526,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         for (int l = 0; l < 8; ++l) {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
+          wait_a_free();
           if (l == 0) {
             wait_in(&bars.enc_full[eb], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
@@ -618,6 +585,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
+          wait_a_free();
           const uint32_t a_tm = tmem + (uint32_t)(buf ^ 1) * 256;
           bool acc1 = false;
           for (int g = 0; g < 2; ++g) {
@@ -655,6 +623,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
+          wait_a_free();
           for (int c = 0; c < 2; ++c) {
             wait_act(2 * c);
             wait_act(2 * c + 1);
@@ -677,6 +646,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         {
           const uint32_t tm = tmem + (uint32_t)buf * 256;
           acc = false;
+          wait_a_free();
           wait_act(0);
           wait_act(1);
           request_bias(it * WIDE_LAYERS + 11);
@@ -690,9 +660,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         RSN_TRACE_END(tr, 0);
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 6 && warp < 10) {
     // ===================================================================== epilogue warps (thread = point row)
-    // (highest warp ids: the per-SMSP arbiter favours them over the prologue warps on the layer-critical path)
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
@@ -712,123 +681,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       const int tile = tile_of(it);
       const int pt = tile * TILE + row;
       const bool valid = pt < n_points;
-      uint8_t* const st = (p.stash && tile < n_tiles) ? p.stash + (size_t)tile * STASH_TILE_BYTES : nullptr;
-      auto sblk = [&](int b) -> uint8_t* { return st ? st + (size_t)b * BLOCK_BYTES : nullptr; };
+      uint8_t* const st = TRAIN ? p.stash + (size_t)tile * STASH_TILE_BYTES : nullptr;
       auto wait_acc = [&](int h = 0) {     // output half h of the layer accumulating into `buf` is complete
         const int i = 2 * buf + h;
         mbar_wait(&bars.acc_full[i], (af_phase >> i) & 1u);
         af_phase ^= (1u << i);
         tc_fence_after();
       };
-      // publish a freshly written block (rows of this warp): optional coalesced stash store, then the barrier
-      auto publish = [&](uint64_t* bar, uint32_t blk_saddr, uint8_t* stash_blk, bool drain = false) {
-        if (stash_blk) {
-          warp_store_rows(stash_blk, blk_saddr, q, lane);
-          if (drain) warp_store_guard<0>(lane);   // another warp role overwrites this block later
-        } else if (!TS || drain) {
-          fence_proxy_async();
-        }
-        if (TS && !drain) tmem_st_wait();
-        tc_fence_before();
-        arrive_issuer(bar);
-      };
-      // Guard depths: the slice about to be overwritten was handed to the TMA engine 4 bulk groups ago (layer l-1, same
-      // g), except in layer 0, where blocks 0/1 were last stored by the previous tile's mid layer, 2 groups ago.
-      // One 64-column group of a wide layer: convert, hand to the issuer (act_ready[g]), stash.  `first` = layer 0 (guard
-      // depth, see above).
-      auto convert = [&](auto relu_c, auto masks_c, int bias_off, uint32_t sb, int g, uint2* mask_ptr, uint8_t* stash_blk,
-                         bool first) {
-        constexpr bool RELU = decltype(relu_c)::value, MASKS = decltype(masks_c)::value;
+      // One 64-column group of a wide layer: convert and hand to the issuer (and, in training, to the stash warps):
+      // act_ready[buf][g]
+      auto convert = [&](auto relu_c, uint32_t sb, int g) {
+        constexpr bool RELU = decltype(relu_c)::value;
         const uint32_t acc_c = tlane + (uint32_t)buf * 256 + g * 64, a_t = tlane + (uint32_t)buf * 256 + g * 32;
-        const uint32_t blk = s_act + g * BLOCK_BYTES;
-        auto guard_g = [&]() {
-          if (st) {   // (a group that is not stashed commits no bulk group: drain instead of counting)
-            if (!stash_blk) warp_store_guard<0>(lane); else if (first) warp_store_guard<1>(lane); else warp_store_guard<3>(lane);
-          }
-        };
-        if (TS && st && stash_blk) {
-          if constexpr (TS) {
-            epilogue_group<RELU, MASKS, SBIAS, true, true, true>(
-                acc_c, bias_off + g * 64, blk, row, sb + g * 256, mask_ptr, a_t,
-                [&]() {
-                  tmem_st_wait();
-                  tc_fence_before();
-                  arrive_issuer(&bars.act_ready[g]);
-                },
-                guard_g);
-            if (!(p.debug & 8)) warp_store_rows(stash_blk, blk, q, lane);   // 8: timing experiment without the stash stores
-          }
-        } else {
-          if (!TS) guard_g();
-          if (st && stash_blk) epilogue_group<RELU, MASKS, SBIAS, TS, true>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, mask_ptr, a_t);
-          else epilogue_group<RELU, false, SBIAS, TS, !TS>(acc_c, bias_off + g * 64, blk, row, sb + g * 256, nullptr, a_t);
-          publish(&bars.act_ready[g], blk, stash_blk);
-        }
-        RSN_TRACE((p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0, 2100 + 10 * (bias_off / 256) + g);
+        epilogue_group<RELU, TS>(acc_c, s_act + g * BLOCK_BYTES, row, sb + g * 256, a_t);
+        if (TS) tmem_st_wait(); else fence_proxy_async();
+        tc_fence_before();
+        arrive_issuer(&bars.act_ready[buf * 4 + g]);
+        RSN_TRACE((p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0, 2100 + 10 * (jw - 1) + g);
       };
       using T_ = std::integral_constant<bool, true>;
       using F_ = std::integral_constant<bool, false>;
-      uint2* const masks = st ? reinterpret_cast<uint2*>(st + STASH_MASK_OFF) : nullptr;
-      // TS + stash: a whole ReLU layer of NG groups with LAGGED staging -- group g is converted and handed to the issuer,
-      // and only then is group g-1 staged (masks, 8 x st.shared, bulk store): nothing but the conversion itself separates
-      // two hand-overs of the layer-critical chain.
-      auto layer_lag = [&](auto ng_c, int bias_off, uint32_t sb, int mask_layer, int stash_blk0, bool first) {
-        constexpr int NG = decltype(ng_c)::value;
-        const bool tr_ = (p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0;
-        (void)tr_;
-        if constexpr (TS) {
-          uint32_t a2[2][32];
-          // The layer's NG blocks leave through ONE proxy fence and one bulk group at the end of the layer: per group the
-          // fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) + bulk issue cost ~430 cycles and the wait_group.read guard ~210 in
-          // the in-kernel trace, between two hand-overs of the layer-critical chain.
-          (void)first;
-          auto stage = [&](int g, const uint32_t (&a)[32]) {
-            const uint32_t blk = s_act + g * BLOCK_BYTES;
-            if (g == 0) warp_store_guard<0>(lane);     // the previous layer's bulk stores have read the staging slices
-            RSN_TRACE(tr_, 2300 + 10 * mask_layer + g);
-            stage_row<true>(a, blk, row, masks + mask_entry(mask_layer, g, row));
-            RSN_TRACE(tr_, 2400 + 10 * mask_layer + g);
-          };
-#pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            if (g == 2) wait_acc(1);
-            const uint32_t acc_c = tlane + (uint32_t)buf * 256 + g * 64, a_t = tlane + (uint32_t)buf * 256 + g * 32;
-            epilogue_group_core<true, true, SBIAS, true, true, true, true>(
-                acc_c, bias_off + g * 64, s_act + g * BLOCK_BYTES, row, sb + g * 256, nullptr, a_t, a2[g & 1],
-                [&]() {
-                  tmem_st_wait();
-                  tc_fence_before();
-                  arrive_issuer(&bars.act_ready[g]);
-                },
-                NoOp());
-            RSN_TRACE(tr_, 2100 + 10 * mask_layer + g);
-            if (g > 0) stage(g - 1, a2[(g - 1) & 1]);
-            if (g > 0) RSN_TRACE(tr_, 2200 + 10 * mask_layer + g - 1);
-          }
-          stage(NG - 1, a2[(NG - 1) & 1]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && !(p.debug & 8)) {           // 8: timing experiment without the stash stores
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-              bulk_s2g_u32(sblk(stash_blk0 + g) + q * 4096, s_act + g * BLOCK_BYTES + (uint32_t)q * 4096u, 4096);
-            bulk_commit();
-          }
-          RSN_TRACE(tr_, 2200 + 10 * mask_layer + NG - 1);
-        }
-      };
       const bool tr = (p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0;
       for (int l = 0; l < 8; ++l) {
         wait_acc();
         RSN_TRACE(tr, 2000 + l);
         const uint32_t sb = bias_slot();
-        if (TS && st) {
-          layer_lag(std::integral_constant<int, 4>{}, BIAS_BASE + l * 256, sb, l, STASH_H + 4 * l, l == 0);
-        } else {
-          for (int g = 0; g < 4; ++g) {
-            if (g == 2) wait_acc(1);
-            convert(T_{}, T_{}, BIAS_BASE + l * 256, sb, g, masks + mask_entry(l, g, row), sblk(STASH_H + 4 * l + g), l == 0);
-          }
+        for (int g = 0; g < 4; ++g) {
+          if (g == 2) wait_acc(1);
+          convert(T_{}, sb, g);
         }
         buf ^= 1;
       }
@@ -840,7 +720,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
         // (not stashed: the wgrad derives everything that involves the bottleneck from h7, csrc/field_wgrad.cu)
         for (int g = 0; g < 4; ++g) {
           if (g == 2) wait_acc(1);
-          convert(F_{}, F_{}, BIAS_BOTT, sb, g, nullptr, nullptr, false);
+          convert(F_{}, sb, g);
         }
         uint32_t hv[16];
         tmem_ld16(tlane + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, hv);
@@ -900,7 +780,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
           store_chunk(ide_row, row, 6, z8);
           store_chunk(ide_row, row, 7, z8);
         }
-        publish(&bars.ide_ready, ide_blk, sblk(STASH_IDE), true);
+        // publish the IDE block (rows of this warp): in training, bulk-store the slice first and wait until the TMA engine has
+        // read it (the prologue warps overwrite the block with the next-but-one tile's encoding)
+        if (TRAIN) {
+          warp_store_rows(st + (size_t)STASH_IDE * BLOCK_BYTES, ide_blk, q, lane);
+          warp_store_guard<0>(lane);
+        } else {
+          fence_proxy_async();
+        }
+        tc_fence_before();
+        arrive_issuer(&bars.ide_ready);
         if (valid && p.aux) {
           p.aux[(size_t)pt * 8 + 3] = h[1];
           p.aux[(size_t)pt * 8 + 4] = h[2];
@@ -920,12 +809,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       {
         wait_acc();
         const uint32_t sb = bias_slot();
-        if (TS && st) {
-          layer_lag(std::integral_constant<int, 2>{}, BIAS_MID, sb, 8, STASH_MIDH, false);
-        } else {
-          for (int g = 0; g < 2; ++g)
-            convert(T_{}, T_{}, BIAS_MID, sb, g, masks + mask_entry(8, g, row), sblk(STASH_MIDH + g), false);
-        }
+        for (int g = 0; g < 2; ++g) convert(T_{}, sb, g);
         buf ^= 1;
       }
       // ---- layer 10: rgb
@@ -957,6 +841,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       }
       RSN_TRACE_END(tr, 1);
     }
+  } else if (warp >= 10) {
+    // ===================================================================== stash warps (training launches only)
+    if constexpr (TRAIN) {
+      const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
+      const int row = q * 32 + lane;
+      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+      uint32_t ar_phase = 0;                                    // bit 4 b + g: parity of the next completion of act_ready[4 b + g]
+      int sbuf = 0;                                             // accumulator buffer of the layer use being stashed
+      auto wait_group = [&](int g) {
+        const int i = sbuf * 4 + g;
+        mbar_wait(&bars.act_ready[i], (ar_phase >> i) & 1u);
+        ar_phase ^= (1u << i);
+        tc_fence_after();
+      };
+      auto release = [&]() {                                    // this warp no longer reads the operand in buffer sbuf
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.a_free[sbuf]);
+        sbuf ^= 1;
+      };
+      for (int it = 0; it < n_my_tiles; ++it) {
+        uint8_t* const st = p.stash + (size_t)tile_of(it) * STASH_TILE_BYTES;
+        uint2* const masks = reinterpret_cast<uint2*>(st + STASH_MASK_OFF);
+        // one layer use with NG stashed groups: mask layer ml, stash blocks blk0 .. blk0 + NG - 1
+        auto stash_layer = [&](int ng, int ml, int blk0) {
+          for (int g = 0; g < ng; ++g) {
+            wait_group(g);
+            uint32_t a[32];
+            tmem_ld32(tlane + (uint32_t)sbuf * 256 + (uint32_t)g * 32u, a);
+            tmem_ld_wait();
+            if (g == ng - 1) release();
+            stash_row(a, st + (size_t)(blk0 + g) * BLOCK_BYTES, row, masks + mask_entry(ml, g, row));
+          }
+        };
+        for (int l = 0; l < 8; ++l) stash_layer(4, l, STASH_H + 4 * l);
+        for (int g = 0; g < 4; ++g) wait_group(g);              // bottleneck: not stashed (csrc/field_wgrad.cu), only observed
+        release();
+        stash_layer(2, 8, STASH_MIDH);                          // mid hidden
+        release();                                              // rgb: hands nothing over; one release per layer use
+      }
+    }
   } else {
     // ===================================================================== prologue warps (next tile's IPE)
     const int row = (warp - 2) * 32 + lane;
@@ -964,7 +889,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
       const int eb = it & 1;
       const int tile = tile_of(it);
       const int pt = tile * TILE + row;
-      const bool stash_on = p.stash && tile < n_tiles;
+      const bool stash_on = TRAIN;
       float xm[3] = {0.f, 0.f, 0.f}, dg[3] = {0.f, 0.f, 0.f};
       if (pt < n_points) {
         if (p.mode == 0) {
@@ -1020,7 +945,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_fwd_kernel(const FwdPara
     }
   }
 
-  if (p.stash && lane == 0 && warp >= 2) bulk_wait_all<0>();
+  if (TRAIN && lane == 0 && warp >= 2 && warp < 10) bulk_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
@@ -1042,24 +967,30 @@ extern "C" int64_t rsn_field_stash_bytes(int64_t n_points) {
 }
 
 namespace {
-std::atomic<unsigned long long> g_fwd_smem_done[2];
+std::atomic<unsigned long long> g_fwd_smem_done[3];
 
 int launch_fwd(FwdParams& p, cudaStream_t stream) {
   p.n_tiles = (p.n_points + TILE - 1) / TILE;
   p.debug = rsn_env_int("RSN_FWD_DEBUG", 0);
   const size_t smem = SMEM_TOTAL;
-  RSN_CUDA(rsn_ensure_smem(field_fwd_kernel<true>, (int)smem, g_fwd_smem_done[0]));
   const int grid = std::min(p.n_tiles, rsn_num_sms());
+  if (p.stash) {   // training: four more warps write the activation stash
+    RSN_CUDA(rsn_ensure_smem(field_fwd_kernel<true, true>, (int)smem, g_fwd_smem_done[0]));
+    field_fwd_kernel<true, true><<<grid, NUM_THREADS_TRAIN, smem, stream>>>(p);
+    RSN_LAUNCH_CHECK("field_fwd_kernel");
+    return 0;
+  }
 #ifdef RSN_DEBUG_SWITCHES
-  // RSN_FWD_TS=0 selects the shared-memory (SS) operand form (same results bit for bit; test build only)
+  // RSN_FWD_TS=0 selects the shared-memory (SS) operand form (same results bit for bit; test build, inference only)
   if (rsn_env_int("RSN_FWD_TS", 1) == 0) {
-    RSN_CUDA(rsn_ensure_smem(field_fwd_kernel<false>, (int)smem, g_fwd_smem_done[1]));
-    field_fwd_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
+    RSN_CUDA(rsn_ensure_smem(field_fwd_kernel<false, false>, (int)smem, g_fwd_smem_done[2]));
+    field_fwd_kernel<false, false><<<grid, NUM_THREADS, smem, stream>>>(p);
     RSN_LAUNCH_CHECK("field_fwd_kernel");
     return 0;
   }
 #endif
-  field_fwd_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(p);
+  RSN_CUDA(rsn_ensure_smem(field_fwd_kernel<true, false>, (int)smem, g_fwd_smem_done[1]));
+  field_fwd_kernel<true, false><<<grid, NUM_THREADS, smem, stream>>>(p);
   RSN_LAUNCH_CHECK("field_fwd_kernel");
   return 0;
 }

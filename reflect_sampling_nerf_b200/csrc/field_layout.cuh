@@ -60,12 +60,31 @@ constexpr int BIAS_MID = 2320;        // 128
 constexpr int BIAS_RGB = 2448;        // 16
 constexpr int N_BIAS = 2464;
 
+// ---- the two block images of the training stashes ----------------------------------------------------
+// Every stash block holds [128 points][64 features] bf16 = 16 KB, in one of two images:
+//  * "swizzled" (umma.cuh block_off): the K-major 128-byte-swizzled shared-memory operand image, bulk-stored as it sits
+//    in shared memory.  Used for the blocks that exist in shared memory anyway: the IPE / IDE encodings (forward A
+//    operands) -- STASH_ENC, STASH_IDE.
+//  * "chunk-major": the 16-byte chunk c (features 8c..8c+7) of point r at
+//        (r / 64) * 8192 + c * 1024 + (r % 64) * 16
+//    i.e. two 64-point slabs (the wgrad's pipeline unit), inside a slab one 1 KB run per chunk with the points
+//    contiguous.  Written straight from registers: the 32 lanes of a warp (32 consecutive points) store 512 contiguous
+//    bytes per st.global.v4.  Read by the wgrad as a NO-swizzle MN-major UMMA operand (core matrix = 8 points x 16 B =
+//    128 contiguous bytes; 1024 B between core matrices along the features, 128 B along the points).
+//    Used for everything the epilogues produce: the hidden activations (STASH_H, STASH_MIDH) and every dY block.
+constexpr int STASH_SLAB_ROWS = 64;
+constexpr int STASH_CHUNK_STRIDE = STASH_SLAB_ROWS * 16;          // 1024
+constexpr int STASH_SLAB_BYTES = 8 * STASH_CHUNK_STRIDE;          // 8192
+__host__ __device__ constexpr uint32_t stash_chunk_off(int r, int c) {
+  return (uint32_t)(r / STASH_SLAB_ROWS) * STASH_SLAB_BYTES + (uint32_t)c * STASH_CHUNK_STRIDE + (uint32_t)(r % STASH_SLAB_ROWS) * 16u;
+}
+
 // ---- training stash: per tile, STASH_BLOCKS activation block images of 16 KB (written by the forward) ----
-constexpr int STASH_ENC = 0;     // 2 blocks: IPE (columns 99..127 zero)
-constexpr int STASH_H = 2;       // + 4*l + g : post-ReLU output of base layer l, 64-column group g
+constexpr int STASH_ENC = 0;     // 2 blocks: IPE (columns 99..127 zero)                         [swizzled image]
+constexpr int STASH_H = 2;       // + 4*l + g : post-ReLU output of base layer l, 64-column group g   [chunk-major]
 constexpr int STASH_BOTT = 34;   // 4 blocks: bottleneck (no activation)
-constexpr int STASH_IDE = 38;    // 1 block: IDE (columns 34..63 zero)
-constexpr int STASH_MIDH = 39;   // 2 blocks: mid hidden (post-ReLU)
+constexpr int STASH_IDE = 38;    // 1 block: IDE (columns 34..63 zero)                            [swizzled image]
+constexpr int STASH_MIDH = 39;   // 2 blocks: mid hidden (post-ReLU)                              [chunk-major]
 constexpr int STASH_BLOCKS = 41;
 // ... followed by the ReLU bit masks of the 8 hidden layers and the mid hidden layer: [9 layers][4 groups][128 rows]
 // x 8 bytes; bit i (i < 16) of word w (w = 0, 1) of a row's entry = column 32 w + 2 i of the 64-column group is > 0,
@@ -77,12 +96,13 @@ constexpr int STASH_MASK_BYTES = MASK_LAYERS * 4 * TILE * 8;               // 36
 constexpr int STASH_TILE_BYTES = STASH_MASK_OFF + STASH_MASK_BYTES;        // 708,608 per 128-point tile
 __host__ __device__ constexpr int mask_entry(int layer, int group, int row) { return ((layer * 4 + group) * TILE + row); }
 
-// ---- dgrad stash: per tile, DY_BLOCKS block images of the pre-activation gradients (written by the dgrad chain)
+// ---- dgrad stash: per tile, DY_BLOCKS chunk-major block images of the pre-activation gradients (written by the dgrad chain)
 constexpr int DY_SEED = 0;       // 1 block: columns 0-15 d(rgb head pre-activation), 16-31 d(heads pre-activation)
 constexpr int DY_MID = 1;        // 2 blocks: d(mid hidden pre-activation), 128 columns
 constexpr int DY_BOTT = 3;       // 4 blocks: d(bottleneck)
 constexpr int DY_H = 7;          // + 4*l + g : d(pre-activation of base layer l)
 constexpr int DY_BLOCKS = 39;
+constexpr bool DY_CHUNK_MAJOR = false;   // image of the dY blocks (the dgrad chain still stages them in shared memory)
 
 // ---- per-point feature row written by the forward kernel ([P][16] fp32) ------------------------------
 // 0-2 rgb = diff + tint*mid | 3-5 diff | 6-8 tint | 9-11 pred_normal | 12 sigmoid(rough) | 13 n.d

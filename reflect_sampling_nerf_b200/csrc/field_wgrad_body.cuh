@@ -31,6 +31,7 @@ struct WJob {
   int a_blk, m_blocks;   // first dY block of the job inside a dY tile; 2 (M=128) or 4 (M=256)
   int a_load;            // dY blocks actually loaded (m_blocks, or 3: the MMA's fourth A block is then the first X block)
   int b_blk, n_blocks;   // first X block inside a stash tile; 1, 2 or 4 (N = 64, 128, 256)
+  int a_cm, b_cm;        // 1: the dY / X blocks are chunk-major images (field_layout.cuh), 0: swizzled images
   int out_off, db_off;   // float offsets into the gradient blob: dW [64 m_blocks][64 n_blocks], db or -1
   int cta_begin, n_ctas;
 };
@@ -154,20 +155,28 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
         if ((p.debug & 3) != 1) mbar_wait(&bars.full[stage], phase);
         tc_fence_after();
         const uint32_t base = smem_u32(smem + (size_t)stage * SLAB_BYTES);
-        // MN-major operands: LBO = stride between the 64-feature blocks of the slab, SBO = 1024 (8 points);
-        // one K=16 step (16 points) advances the start address by 2048 bytes
-        constexpr uint32_t HI = desc_hi_sw128(1024);
-        const uint32_t a_lo = desc_lo(base, SLAB_BLOCK_BYTES), b_lo = desc_lo(base + mb * SLAB_BLOCK_BYTES, SLAB_BLOCK_BYTES);
+        // MN-major operands (the 64 features of a block are the contiguous dimension), two block images:
+        //   swizzled    (128-byte swizzle): LBO = stride between the 64-feature blocks of the slab, SBO = 1024 (8 points);
+        //               one K = 16 step (16 points) advances the start address by 2048 bytes
+        //   chunk-major (no swizzle): core matrix = 8 points x 16 B = 128 contiguous bytes; LBO = 128 (next 8 points),
+        //               SBO = 1024 (next 8 features -- across the slab's blocks too: 8 chunks x 1024 B = one block);
+        //               one K = 16 step advances the start address by 256 bytes
+        const uint32_t a_hi = job.a_cm ? desc_hi_noswz(STASH_CHUNK_STRIDE) : desc_hi_sw128(1024);
+        const uint32_t b_hi = job.b_cm ? desc_hi_noswz(STASH_CHUNK_STRIDE) : desc_hi_sw128(1024);
+        const uint32_t a_lo = desc_lo(base, job.a_cm ? 128 : SLAB_BLOCK_BYTES);
+        const uint32_t b_lo = desc_lo(base + mb * SLAB_BLOCK_BYTES, job.b_cm ? 128 : SLAB_BLOCK_BYTES);
+        const uint32_t a_ks = job.a_cm ? 16u : 128u, b_ks = job.b_cm ? 16u : 128u;   // K-step advance in 16-byte units
         if ((p.debug & 3) != 2 && elect_one_sync()) {
           // all K-steps of the slab into one accumulator, then the other: interleaving the two accumulators MMA by
           // MMA is measurably slower (2.6 vs 4.2 ms for the MMA stream alone at C2)
 #pragma unroll
           for (int ks = 0; ks < SLAB_ROWS / 16; ++ks)
-            mma_bf16_ss_lo(tmem, a_lo + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
+            mma_bf16_ss_lo2(tmem, a_lo + ks * a_ks, a_hi, b_lo + ks * b_ks, b_hi, idesc, (s | ks) != 0);
           if (m_out == 4) {
 #pragma unroll
             for (int ks = 0; ks < SLAB_ROWS / 16; ++ks)
-              mma_bf16_ss_lo(tmem + 256, a_lo + (2 * SLAB_BLOCK_BYTES >> 4) + ks * 128, b_lo + ks * 128, HI, idesc, (s | ks) != 0);
+              mma_bf16_ss_lo2(tmem + 256, a_lo + (2 * SLAB_BLOCK_BYTES >> 4) + ks * a_ks, a_hi, b_lo + ks * b_ks, b_hi, idesc,
+                              (s | ks) != 0);
           }
         }
         if (elect_one_sync()) mma_commit(&bars.empty[stage]);
@@ -283,6 +292,7 @@ const JobSpec kJobs[] = {
 };
 constexpr int kNumJobs = sizeof(kJobs) / sizeof(kJobs[0]);
 static_assert(kNumJobs <= MAX_JOBS, "job table too small");
+static_assert(SLAB_ROWS == STASH_SLAB_ROWS, "the chunk-major image is laid out in the wgrad's slabs");
 
 // Job table of one pass for `cta_budget` wgrad CTAs: CTAs per job proportional to the job's bytes per tile (the kernel
 // is HBM-bound).  Returns the number of CTAs used (<= cta_budget, one wave).
@@ -328,6 +338,10 @@ inline int fill_wgrad_params(WParams& p, const void* x_stash, const void* dy_sta
     WJob& w = p.jobs[j];
     w.a_blk = kJobs[j].a_blk, w.m_blocks = kJobs[j].m_blocks, w.b_blk = kJobs[j].b_blk, w.n_blocks = kJobs[j].n_blocks;
     w.a_load = kJobs[j].a_load ? kJobs[j].a_load : kJobs[j].m_blocks;
+    // block images (field_layout.cuh): the encodings are stashed as they sit in shared memory (swizzled), everything the
+    // epilogues produce is chunk-major
+    w.a_cm = DY_CHUNK_MAJOR ? 1 : 0;
+    w.b_cm = (kJobs[j].b_blk == STASH_ENC || kJobs[j].b_blk == STASH_IDE) ? 0 : 1;
     w.out_off = (int)off;
     off += (int64_t)w.m_blocks * 64 * w.n_blocks * 64;
     w.db_off = kJobs[j].has_db ? (int)off : -1;

@@ -162,6 +162,89 @@ extern "C" int rsn_probe_umma_mnmajor(const void* u_blocks, const void* v_blocks
   return 0;
 }
 
+// ---- the wgrad's operand form for chunk-major stash blocks (field_layout.cuh): NO-swizzle MN-major descriptors.
+// D[M = 128, N = 64 NB] = U[128 points, 128]^T * V[128 points, 64 NB]; U / V arrive as chunk-major block images (two
+// 64-point slabs per block).  Per slab the blocks sit in shared memory the way the wgrad stages them: [MB + NB blocks][8 KB],
+// so the 16-byte chunk column j (8 features) of the slab's A (or B) operand starts at j * 1024 and its points follow at
+// 16 B: core matrix (8 points x 8 features) = 128 contiguous bytes, `mn_stride` = 1024 between core matrices along the
+// features, `k_stride` = 128 along the points; one K = 16 step advances the start address by 256 B.
+// `lbo` / `sbo` are passed in so that the test pins which descriptor field carries which stride.
+namespace {
+__global__ void __launch_bounds__(160, 1) probe_mnmajor_cm_kernel(const uint8_t* __restrict__ u_blocks,
+                                                                  const uint8_t* __restrict__ v_blocks, int NB, int lbo, int sbo,
+                                                                  float* __restrict__ out, int iters, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int MB = 2;
+  const int N = NB * 64;
+  const int slab_bytes = (MB + NB) * 8192;
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(&bar_load, 1);
+      mbar_init(&bar_mma, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  if (warp == 4 && lane == 0) {
+    mbar_expect_tx(&bar_load, 2u * (uint32_t)slab_bytes);
+    for (int s = 0; s < 2; ++s) {
+      for (int b = 0; b < MB; ++b) bulk_g2s(smem + s * slab_bytes + b * 8192, u_blocks + (size_t)b * 16384 + s * 8192, 8192, &bar_load);
+      for (int b = 0; b < NB; ++b)
+        bulk_g2s(smem + s * slab_bytes + (MB + b) * 8192, v_blocks + (size_t)b * 16384 + s * 8192, 8192, &bar_load);
+    }
+    mbar_wait(&bar_load, 0);
+    tc_fence_after();
+    const uint32_t idesc = instr_desc_bf16(128, N, 1, 1);
+    const long long t0 = clock64();
+    for (int it = 0; it < (iters > 0 ? iters : 1); ++it)
+      for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = smem_desc_noswz(smem_u32(smem + s * slab_bytes) + k * 256, lbo, sbo);
+          const uint64_t db = smem_desc_noswz(smem_u32(smem + s * slab_bytes + MB * 8192) + k * 256, lbo, sbo);
+          mma_bf16_ss(tmem, da, db, idesc, (it | s | k) != 0);
+        }
+    mma_commit(&bar_mma);
+    mbar_wait(&bar_mma, 0);
+    if (out_cycles) *out_cycles = clock64() - t0;
+  }
+  if (warp < 4) {
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) out[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" int rsn_probe_umma_mnmajor_cm(const void* u_blocks, const void* v_blocks, int64_t n_blocks, int64_t lbo, int64_t sbo,
+                                         float* out, int64_t iters, long long* out_cycles, cudaStream_t stream) {
+  RSN_ARG(n_blocks >= 1 && n_blocks <= 4, "rsn_probe_umma_mnmajor_cm: n_blocks in [1,4]");
+  size_t smem = (size_t)2 * (2 + n_blocks) * 8192 + 1024;
+  RSN_CUDA(cudaFuncSetAttribute(probe_mnmajor_cm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_mnmajor_cm_kernel<<<1, 160, smem, stream>>>((const uint8_t*)u_blocks, (const uint8_t*)v_blocks, (int)n_blocks, (int)lbo,
+                                                    (int)sbo, out, (int)iters, out_cycles);
+  RSN_LAUNCH_CHECK("probe_mnmajor_cm_kernel");
+  return 0;
+}
+
 // ---- A-from-TMEM probe: D[128, N] = X[128, K] * W[N, K]^T with X written into TMEM by the four epilogue-style warps
 // (tcgen05.st, two bf16 per 32-bit column) and read by tcgen05.mma as its A operand; W from shared memory.
 // `iters` > 0 additionally times `iters` back-to-back MMAs of the same form (cycles -> out_cycles).

@@ -192,6 +192,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;  // layout type: SWIZZLE_128B
   return d;
 }
+// The same descriptor without swizzling (layout type 0).  MN-major operand whose core matrices (8 K-rows of 16 bytes = 128
+// contiguous bytes) are `sbo_bytes` apart along M/N and `lbo_bytes` apart along K -- the chunk-major stash blocks.
+__device__ __forceinline__ uint64_t smem_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;
+}
+__host__ __device__ constexpr uint32_t desc_hi_noswz(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
 // Instruction descriptor for kind::f16, BF16 x BF16 -> FP32.  major: 0 = K-major, 1 = MN-major.
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N, int a_major, int b_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16) |
@@ -232,6 +243,21 @@ __device__ __forceinline__ void mma_bf16_ss_lo(uint32_t tmem_d, uint32_t a_lo, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same with one high word per operand (the wgrad mixes swizzled and chunk-major block images)
+__device__ __forceinline__ void mma_bf16_ss_lo2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // A operand from TMEM ("TS" form): rows = the 128 lanes, one 32-bit column = two consecutive K elements (even K in

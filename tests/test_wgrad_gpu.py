@@ -4,10 +4,11 @@ import pytest
 import torch
 
 from reflect_sampling_nerf_b200 import _lib, ops
-from reflect_sampling_nerf_b200.blocks import pack_blocks
+from reflect_sampling_nerf_b200.blocks import pack_blocks, pack_blocks_cm
 
 pytestmark = pytest.mark.gpu
 STASH_BLOCKS, DY_BLOCKS = 41, 39
+SWIZZLED_X_BLOCKS = (0, 1, 38)      # csrc/field_layout.cuh: STASH_ENC, STASH_IDE
 # (dY first block, m_blocks, X first block, n_blocks, has_db) -- csrc/field_wgrad.cu kJobs
 JOBS = [(7, 4, 0, 2, 1), (11, 4, 2, 4, 1), (15, 4, 6, 4, 1), (19, 4, 10, 4, 1), (23, 4, 0, 2, 0), (23, 4, 14, 4, 1),
         (27, 4, 18, 4, 1), (31, 4, 22, 4, 1), (35, 4, 26, 4, 1), None, (0, 3, 30, 4, 1), (0, 2, 39, 2, 0),
@@ -23,10 +24,14 @@ def test_wgrad_matches_matmul(n_tiles):
     pts = n_tiles * 128
     x = (torch.randn(pts, STASH_BLOCKS * 64, generator=g) * 0.5).bfloat16()
     dy = (torch.randn(pts, DY_BLOCKS * 64, generator=g) * 0.1).bfloat16()
-    # stash layout: [tile][block][16 KB]; pack_blocks gives [K/64 blocks][rows][128] for a [rows, K] matrix
-    # (each forward-stash tile is followed by 36,864 bytes of ReLU bit masks the wgrad does not read)
-    xs = torch.stack([torch.cat([pack_blocks(x[t * 128:(t + 1) * 128]).reshape(-1),
-                                 torch.zeros(36864, dtype=torch.uint8)]) for t in range(n_tiles)]).cuda()
+    # stash layout: [tile][block][16 KB]; the encoding blocks (IPE 0-1, IDE 38) are swizzled images (pack_blocks gives
+    # [K/64 blocks][rows][128] for a [rows, K] matrix), everything the epilogues write is chunk-major (pack_blocks_cm gives
+    # [tile][K/64 blocks][16 KB]); each forward-stash tile is followed by 36,864 bytes of ReLU bit masks the wgrad does not read
+    x_sw = torch.stack([pack_blocks(x[t * 128:(t + 1) * 128]).reshape(STASH_BLOCKS, 16384) for t in range(n_tiles)])
+    x_img = pack_blocks_cm(x)
+    for b in SWIZZLED_X_BLOCKS:
+        x_img[:, b] = x_sw[:, b]
+    xs = torch.cat([x_img.reshape(n_tiles, -1), torch.zeros(n_tiles, 36864, dtype=torch.uint8)], dim=1).cuda()
     dys = torch.stack([pack_blocks(dy[t * 128:(t + 1) * 128]) for t in range(n_tiles)]).cuda()
     offs, shapes, total = ops.wgrad_layout()
     assert len(shapes) == len(JOBS)
