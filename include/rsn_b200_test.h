@@ -1,7 +1,7 @@
 /* rsn_b200_test.h -- entry points that exist ONLY in the test build librsn_b200_dbg.so
  * (python -m reflect_sampling_nerf_b200.build compiles csrc/ a second time with -DRSN_DEBUG_SWITCHES + csrc/probe.cu).
- * That build also honours the RSN_FWD_TS / RSN_BWD_TS / RSN_*_DEBUG environment switches (alternative operand forms
- * that must stay bit-identical, timing ablations whose results are wrong by design); the product library
+ * That build also honours the RSN_FWD_TS (inference) / RSN_BWD_TS / RSN_*_DEBUG environment switches (alternative operand
+ * forms that must stay bit-identical, timing ablations whose results are wrong by design); the product library
  * librsn_b200.so (include/rsn_b200.h) contains none of this. */
 #ifndef RSN_B200_TEST_H
 #define RSN_B200_TEST_H
@@ -9,17 +9,6 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-
-/* rsn_field_backward + rsn_field_wgrad in ONE launch: the dgrad-chain CTAs and the wgrad CTAs share the grid, the
- * chain publishes each tile's dY blocks with a per-tile flag (workspace: rsn_field_backward_fused_workspace_bytes,
- * zeroed by the call) and the wgrad picks them up from L2.  Same arguments and results as the two calls; validated,
- * slower (8.2 vs 6.4 ms at C2). */
-int rsn_field_backward_fused(const void* wblob_t, const void* x_stash, int mode, const float* origins,
-                             const float* dirs, const float* area, const float* bins, int64_t n_rays,
-                             int64_t n_samples, const float* g_sigma, const float* g_feat, const float* feat,
-                             const float* aux, void* dy_stash, float* g_area, float* grad_blob, void* workspace,
-                             rsn_stream_t stream);
-int64_t rsn_field_backward_fused_workspace_bytes(int64_t n_points);
 
 /* In-kernel cycle trace of the forward field kernel (RSN_FWD_DEBUG & 32): (tag, clock64) pairs of the third tile of CTA 0 of
  * the last traced launch -> HOST host_out[2 * max_pairs]; returns the number of pairs, resets the trace, synchronises.
@@ -31,6 +20,12 @@ int rsn_probe_umma_kmajor(const void* x_blocks, const void* w_blocks, int64_t n_
                           int64_t n_split, float* out, rsn_stream_t stream);
 int rsn_probe_umma_mnmajor(const void* u_blocks, const void* v_blocks, int64_t m_blocks, int64_t n_blocks,
                            float* out, rsn_stream_t stream);
+/* The wgrad's operand form for CHUNK-MAJOR stash blocks (csrc/field_layout.cuh): out [128, 64 n_blocks] = U^T V with U
+ * [128 points, 128] and V [128 points, 64 n_blocks] given as chunk-major block images and read through NO-swizzle MN-major
+ * descriptors whose LBO / SBO fields are passed in (128 / 1024 is the pair the wgrad uses).  iters > 0 also times the MMA
+ * stream into *cycles_out (DEVICE int64). */
+int rsn_probe_umma_mnmajor_cm(const void* u_blocks, const void* v_blocks, int64_t n_blocks, int64_t lbo, int64_t sbo,
+                              float* out, int64_t iters, long long* cycles_out, rsn_stream_t stream);
 
 /* A-from-TMEM probe (tcgen05.mma [d], [a], b-desc): out [128, n_out] = X * W^T with X staged into TMEM by tcgen05.st.
  * iters > 0 also times `iters` back-to-back MMAs of that form into *cycles_out (DEVICE int64). */

@@ -65,8 +65,6 @@ _SIGNATURES = {
 }
 # include/rsn_b200_test.h: the test build exports everything above plus these
 _SIGNATURES_DBG = {
-    "rsn_field_backward_fused": ([P, P, I32, P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P], c_int),
-    "rsn_field_backward_fused_workspace_bytes": ([I64], c_int64),
     "rsn_debug_fwd_trace": ([P, I32], c_int),
     "rsn_probe_umma_kmajor": ([P, P, I64, I64, I64, P, P], c_int),
     "rsn_probe_umma_2cta": ([P, P, I64, I64, P, P], c_int),

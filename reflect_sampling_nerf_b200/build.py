@@ -5,7 +5,7 @@
   librsn_b200.so      the product: include/rsn_b200.h, no environment switches, no probes
   librsn_b200_dbg.so  the test build: the same sources with -DRSN_DEBUG_SWITCHES (alternative kernel forms and timing
                       ablations selected by RSN_* environment variables) + csrc/probe.cu (tcgen05 building-block
-                      probes) + the one-launch backward; include/rsn_b200_test.h.  Loaded only by tests/ and scripts/.
+                      probes); include/rsn_b200_test.h.  Loaded only by tests/ and scripts/.
 
 nvcc cross-compiles without a GPU.  The .so files are git-ignored but travel to the GPU box with gpurun.
 """
@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
-TEST_ONLY = {"probe.cu", "field_bwd_fused.cu"}     # sources of the test build only
+TEST_ONLY = {"probe.cu"}     # sources of the test build only
 
 
 def _stale(lib: str) -> bool:

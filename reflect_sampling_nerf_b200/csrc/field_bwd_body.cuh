@@ -1,4 +1,4 @@
-// Body of the dgrad-chain kernels (see field_bwd.cu for the description); shared with the fused backward kernel.
+// Body of the dgrad-chain kernels (see field_bwd.cu for the description).
 #pragma once
 #include "rsn_common.cuh"
 #include "umma.cuh"
@@ -13,14 +13,19 @@ using namespace umma;
 using namespace rsnf;
 
 constexpr int KIND_NORMALS = 0, KIND_BACKWARD = 1;
-constexpr int B_THREADS = 224;
+constexpr int B_THREADS = 224;                    // warps 0 weights, 1 issuer, 2-5 epilogue, 6 stashed-encoding producer
+constexpr int B_THREADS_STASH = 352;              // BACKWARD (TS form): + warps 7-10, which write the dY stash
 constexpr int NUM_WSTAGES = 3, NUM_MSTAGES = 2;   // the second ring only carries the two stashed enc blocks
-constexpr int MAX_WSTAGES = 5;                    // NORMALS in the TS form: activation + seed blocks are free -> 5 stages
-constexpr int SM_ACT = 0;                                  // 4 blocks: dY, rewritten in place step by step
+constexpr int MAX_WSTAGES = 5;                    // TS form: no shared-memory activation blocks -> 5 stages
+// SS form: [4 dY blocks, rewritten in place step by step][seed block][3-stage weight ring][stashed-encoding ring]
+// TS form: [5-stage weight ring][seed block (BACKWARD)][stashed-encoding ring]
+constexpr int SM_ACT = 0;
 constexpr int SM_SEED = 4 * BLOCK_BYTES;                   // 1 block: d(rgb head) cols 0-15, d(heads) cols 16-31
 constexpr int SM_W = SM_SEED + BLOCK_BYTES;                // weight ring
 constexpr int SM_M = SM_W + NUM_WSTAGES * W_STAGE_BYTES;   // stashed-encoding ring (IPE Jacobians)
 constexpr int SM_TOTAL = SM_M + NUM_MSTAGES * BLOCK_BYTES; // 212,992
+constexpr int SM_SEED_TS = MAX_WSTAGES * W_STAGE_BYTES;    // TS form: the seed block sits behind the 5-stage ring
+static_assert(SM_SEED_TS + BLOCK_BYTES <= SM_M, "TS layout: ring + seed block overlap the encoding ring");
 
 __constant__ float c_freq_b[16] = {
     0x1.0000000000000p+0f,  0x1.0c1b780000000p+1f,  0x1.18c9880000000p+2f,  0x1.26111c0000000p+3f,
@@ -50,14 +55,16 @@ struct BwdParams {
   const float* aux;         // [P,8]    forward aux (mid rgb, raw normal head)
   uint8_t* dy_stash;        // [n_tiles][DY_BLOCKS][16 KB]
   float* g_area;            // [P]      dL/d pixel_area (or sqradius) contribution of each point, or NULL
-  int debug;                // RSN_BWD_DEBUG (timing experiments only; results are wrong): 1 = no dY bulk stores,
-                            // 4 = no wait for the TMA engine before a staged slice is overwritten, 8 = no weight streaming
+  int debug;                // RSN_BWD_DEBUG (test build, timing experiments only; results are wrong): 1 = no dY stores,
+                            // 8 = no weight streaming
 };
 
 struct BBarriers {
   uint64_t w_full[MAX_WSTAGES], w_empty[MAX_WSTAGES];
   uint64_t m_full[NUM_MSTAGES], m_empty[NUM_MSTAGES];
-  uint64_t act_ready[4];
+  uint64_t act_ready[8];      // [accumulator buffer of the producing step][64-column group]: two sets, so that the stash warps
+                              // may lag the issuer by up to two steps without aliasing the phase parity
+  uint64_t a_free[2];         // BACKWARD: the stash warps have read the dY operand that lived in accumulator buffer b
   uint64_t seed_ready;
   uint64_t acc_full[2];
   uint32_t tmem_slot;
@@ -90,15 +97,15 @@ __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w <<
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 // 64 accumulator columns of this row -> (optional ReLU mask from the stashed bit masks) -> bf16 -> the next step's A
-// operand: SS form: the shared-memory activation block, in place; TS form: TMEM columns a_taddr..+31 (over accumulator
-// columns this thread has already read).  DEFER (TS + dY stash): hand over first (`early()` = wait::st, fence, arrive),
-// then `guard()` and stage the row in shared memory for the bulk store -- off the step-critical path.
-struct NoOpB {
-  __device__ __forceinline__ void operator()() const {}
-};
-template <bool MASK, bool TS = false, bool DEFER = false, class Early = NoOpB, class Guard = NoOpB>
-__device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_saddr, uint2 mbits, int row,
-                                            uint32_t a_taddr = 0, Early early = Early(), Guard guard = Guard()) {
+// operand: TS form: TMEM columns a_taddr..+31 (over accumulator columns this thread has already read); SS form (test
+// build): the shared-memory activation block, in place -- and, when `dy_blk` is given, the row's place in the chunk-major
+// dY stash block straight from the registers (in the TS form the stash warps write it, see chain_body).
+__device__ __forceinline__ void stg128b(uint8_t* gaddr, uint4 v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gaddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <bool MASK, bool TS>
+__device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_saddr, uint2 mbits, int row, uint32_t a_taddr,
+                                            uint8_t* dy_blk) {
   uint32_t v[2][32];
   tmem_ld32(tmem_row_col, v[0]);
   tmem_ld32(tmem_row_col + 32, v[1]);
@@ -118,17 +125,14 @@ __device__ __forceinline__ void dgrad_group(uint32_t tmem_row_col, uint32_t blk_
       pk.z &= relu_mask_word(bits, i0 + 2);
       pk.w &= relu_mask_word(bits, i0 + 3);
     }
-    if (!TS) sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), pk);
-    else a[c * 4 + 0] = pk.x, a[c * 4 + 1] = pk.y, a[c * 4 + 2] = pk.z, a[c * 4 + 3] = pk.w;
+    if (!TS) {
+      sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), pk);
+      if (dy_blk) stg128b(dy_blk + stash_chunk_off(row, c), pk);
+    } else {
+      a[c * 4 + 0] = pk.x, a[c * 4 + 1] = pk.y, a[c * 4 + 2] = pk.z, a[c * 4 + 3] = pk.w;
+    }
   }
   if (TS) tmem_st32(a_taddr, a);
-  if (DEFER) {
-    early();
-    guard();
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      sts128b(row_saddr + (uint32_t)((c ^ (row & 7)) << 4), make_uint4(a[c * 4], a[c * 4 + 1], a[c * 4 + 2], a[c * 4 + 3]));
-  }
 }
 
 // Geometry of one frustum sample needed by the area Jacobian: d diag_a / d pixel_area for the contracted
@@ -221,23 +225,26 @@ __device__ __forceinline__ void enc_contract(uint32_t tmem_row, uint32_t enc0_sa
   }
 }
 
-// `vbid` / `vgrid`: index of this CTA among the chain CTAs and their number (the fused backward kernel runs wgrad CTAs
-// beside them); `tile_done` (or NULL): per-tile flags this chain sets once a tile's dY blocks are in global memory.
 // TS: the dY operand of every step comes from TMEM (tcgen05.mma [d], [a], b-desc), written there by the previous step's
-// epilogue; the shared-memory activation blocks then only stage the dY stash (BACKWARD) or are unused (NORMALS).
+// epilogue; there are no shared-memory activation blocks.  BACKWARD in the TS form launches four more warps (7-10) that read
+// each handed-over 64-column group back out of TMEM (it stays valid until the issuer re-uses the accumulator buffer two
+// steps later, which waits for a_free) and write it to the dY stash with coalesced st.global.v4 (chunk-major block image,
+// field_layout.cuh) -- nothing of the stash sits on the step-critical path.  SS form (test build): the epilogue writes the
+// stash rows itself.
 template <int KIND, bool TS = false>
-__device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, const int vgrid, int* tile_done) {
+__device__ __forceinline__ void chain_body(const BwdParams& p) {
+  const int vbid = (int)blockIdx.x, vgrid = (int)gridDim.x;
+  constexpr bool STASHW = TS && KIND == KIND_BACKWARD;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ BBarriers bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_act = smem_u32(smem + SM_ACT);
-  const uint32_t s_seed = smem_u32(smem + SM_SEED);
-  // weight ring: 3 x 32 KB after the activation and seed blocks; the TS form of NORMALS uses neither block: 5 x 32 KB
-  // from the start of the buffer
-  constexpr int NWS = (TS && KIND == KIND_NORMALS) ? MAX_WSTAGES : NUM_WSTAGES;
-  constexpr int RING_OFF = (TS && KIND == KIND_NORMALS) ? SM_ACT : SM_W;
-  static_assert(RING_OFF + NWS * W_STAGE_BYTES <= SM_M, "weight ring overlaps the encoding ring");
+  const uint32_t s_seed = smem_u32(smem + (TS ? SM_SEED_TS : SM_SEED));
+  // weight ring: SS form 3 x 32 KB after the activation and seed blocks; TS form 5 x 32 KB from the start of the buffer
+  constexpr int NWS = TS ? MAX_WSTAGES : NUM_WSTAGES;
+  constexpr int RING_OFF = TS ? SM_ACT : SM_W;
+  static_assert(RING_OFF + NWS * W_STAGE_BYTES <= (TS ? SM_SEED_TS : SM_M), "weight ring overlaps what follows it");
   const uint32_t s_w = smem_u32(smem + RING_OFF);
   const uint32_t s_m = smem_u32(smem + SM_M);
   const bool with_enc = (KIND == KIND_NORMALS) || p.want_area;
@@ -252,7 +259,8 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         mbar_init(&bars.m_full[i], 1);
         mbar_init(&bars.m_empty[i], TILE);
       }
-      for (int i = 0; i < 4; ++i) mbar_init(&bars.act_ready[i], TILE);
+      for (int i = 0; i < 8; ++i) mbar_init(&bars.act_ready[i], TILE);
+      for (int i = 0; i < 2; ++i) mbar_init(&bars.a_free[i], 4);
       mbar_init(&bars.seed_ready, TILE);
       mbar_init(&bars.acc_full[0], 1);
       mbar_init(&bars.acc_full[1], 1);
@@ -353,9 +361,17 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         }
       };
       auto wait_act = [&](int g) {
-        mbar_wait(&bars.act_ready[g], (ar_phase >> g) & 1u);
-        ar_phase ^= (1u << g);
+        const int i = (buf ^ 1) * 4 + g;     // handed over by the previous step, which accumulated into the other buffer
+        mbar_wait(&bars.act_ready[i], (ar_phase >> i) & 1u);
+        ar_phase ^= (1u << i);
         tc_fence_after();
+      };
+      int use = 0;     // accumulator-buffer uses so far (use u accumulates into buffer u & 1)
+      // STASHW: before the first MMA of use u overwrites buffer u & 1, the stash warps must have read the dY operand that
+      // the epilogue of use u - 2 left in its first 128 columns
+      auto wait_a_free = [&]() {
+        if (STASHW && use >= 2) mbar_wait(&bars.a_free[use & 1], (uint32_t)((use - 2) >> 1) & 1u);
+        ++use;
       };
       constexpr uint32_t HI = desc_hi_sw128(1024);
       auto issue_kb = [&](uint32_t a_addr, uint32_t b_addr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool& acc) {
@@ -394,6 +410,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           mbar_wait(&bars.seed_ready, (uint32_t)it & 1u);
           tc_fence_after();
           acc = false;
+          wait_a_free();
           uint32_t w = ring_wait();
           issue_kb(s_seed, w, 1, ID128, tmem + (uint32_t)buf * 256, acc);
           ring_release();
@@ -401,6 +418,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           buf ^= 1;
           // S1: d bottleneck = dY_mid (K=128) x Wmid[:,34:]^T, N = 256
           acc = false;
+          wait_a_free();
           for (int g = 0; g < 2; ++g) {
             wait_act(g);
             w = ring_wait();
@@ -411,6 +429,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           buf ^= 1;
           // S2: d emb = dY_bott (K=256) x Wbott^T + dY_heads (K=16, seed block columns 16-31) x Wheads^T
           acc = false;
+          wait_a_free();
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
             w = ring_wait();
@@ -426,6 +445,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         // base layers 7..1: d h_{l-1} = dY_l x W_l^T  (layer 4: hidden part, then the encoding part)
         for (int l = 7; l >= 1; --l) {
           acc = false;
+          wait_a_free();
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
             const uint32_t w = ring_wait();
@@ -452,6 +472,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         if (with_enc) {
           // layer 0: d enc = dY_0 x W0^T, N = 128
           acc = false;
+          wait_a_free();
           for (int g = 0; g < 4; ++g) {
             wait_act(g);
             const uint32_t w = ring_wait();
@@ -481,43 +502,14 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         af_phase ^= (1u << buf);
         tc_fence_after();
       };
-      // publish a freshly written block (rows of this warp): optional coalesced stash store, then the barrier
-      auto publish = [&](uint64_t* bar, uint32_t blk_saddr = 0, uint8_t* stash_blk = nullptr) {
-        if (stash_blk && !(p.debug & 1)) {
-          warp_store_rows(stash_blk, blk_saddr, q, lane);
-        } else {
-          fence_proxy_async();
-        }
-        tc_fence_before();
-        mbar_arrive(bar);
-      };
-      // the act slice about to be overwritten was handed to the TMA engine at most 4 bulk groups ago
-      auto guard = [&]() {
-        if (KIND == KIND_BACKWARD && !(p.debug & 4)) warp_store_guard<3>(lane);
-      };
-      // one 64-column group of a step: convert, hand to the issuer (act_ready[g]), stash (BACKWARD)
-      auto convert = [&](auto mask_c, int g, uint2 mbits, uint8_t* stash_blk, auto guard_fn) {
+      // one 64-column group of a step: convert and hand to the issuer (and, BACKWARD, to the stash warps): act_ready[buf][g]
+      auto convert = [&](auto mask_c, int g, uint2 mbits, uint8_t* stash_blk) {
         constexpr bool MASK = decltype(mask_c)::value;
         const uint32_t acc_c = tlane + (uint32_t)buf * 256 + g * 64, a_t = tlane + (uint32_t)buf * 256 + g * 32;
-        const uint32_t blk = s_act + g * BLOCK_BYTES;
-        if constexpr (!TS) {
-          guard_fn();
-          dgrad_group<MASK>(acc_c, blk, mbits, row);
-          publish(&bars.act_ready[g], blk, stash_blk);
-        } else {
-          auto early = [&]() {
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars.act_ready[g]);
-          };
-          if (KIND == KIND_BACKWARD && stash_blk) {
-            dgrad_group<MASK, true, true>(acc_c, blk, mbits, row, a_t, early, guard_fn);
-            if (!(p.debug & 1)) warp_store_rows(stash_blk, blk, q, lane);
-          } else {
-            dgrad_group<MASK, true, false>(acc_c, blk, mbits, row, a_t);
-            early();
-          }
-        }
+        dgrad_group<MASK, TS>(acc_c, s_act + g * BLOCK_BYTES, mbits, row, a_t, (p.debug & 1) ? nullptr : stash_blk);
+        if (TS) tmem_st_wait(); else fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bars.act_ready[buf * 4 + g]);
       };
       using T_ = std::integral_constant<bool, true>;
       using F_ = std::integral_constant<bool, false>;
@@ -584,25 +576,28 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
         const uint4 c2 = make_uint4(pack2(dh[0], dh[1]), pack2(dh[2], dh[3]), pack2(dh[4], dh[5]), pack2(dh[6], dh[7]));
         const uint4 c3 = make_uint4(pack2(dh[8], dh[9]), pack2(dh[10], 0.f), 0u, 0u);
         const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
+        // (the previous tile's S0 / S2 have read the block: its last accumulator was waited for)
         const uint32_t srow = s_seed + (uint32_t)row * 128u;
-        warp_store_guard<0>(lane);   // previous tile's seed store (and everything older) has left shared memory
+        uint8_t* const sdst = dblk(DY_SEED);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 v = (c == 0) ? c0 : (c == 2) ? c2 : (c == 3) ? c3 : zz;
-          sts128b(srow + (uint32_t)((c ^ (row & 7)) << 4), v);
+          sts128b(srow + (uint32_t)((c ^ (row & 7)) << 4), v);            // swizzled: the A operand of S0 / S2
+          if (!(p.debug & 1)) stg128b(sdst + stash_chunk_off(row, c), v);  // chunk-major: the dY stash
         }
-        publish(&bars.seed_ready, s_seed, dblk(DY_SEED));
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bars.seed_ready);
         // ---- E0: d mid_hidden * (mid_hidden > 0) -> dY_mid (act blocks 0,1)
         uint2 mk0[4];
         load_masks(8, 2, mk0);
         wait_acc();
-        for (int g = 0; g < 2; ++g) convert(T_{}, g, mk0[g], dblk(DY_MID + g), []() {});
+        for (int g = 0; g < 2; ++g) convert(T_{}, g, mk0[g], dblk(DY_MID + g));
         buf ^= 1;
         // ---- E1: d bottleneck (no activation) -> dY_bott
         wait_acc();
-        // (dY_bott is not stashed: the wgrad derives the bottleneck layer's gradients from dY_mid and h7.  SS form: blocks
-        // 0/1 were handed to the TMA engine by E0 and this step commits no bulk groups of its own: drain)
-        for (int g = 0; g < 4; ++g) convert(F_{}, g, make_uint2(0u, 0u), nullptr, [&]() { warp_store_guard<0>(lane); });
+        // (dY_bott is not stashed: the wgrad derives the bottleneck layer's gradients from dY_mid and h7)
+        for (int g = 0; g < 4; ++g) convert(F_{}, g, make_uint2(0u, 0u), nullptr);
         buf ^= 1;
       } else {
         // ---- NORMALS seed: dY_7 = w_density * (h7 > 0)
@@ -624,11 +619,11 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           if (TS) {   // the first step accumulates into `buf`: its A operand goes to the other buffer
             tmem_st32(tlane + (uint32_t)(buf ^ 1) * 256 + g * 32, a);
             tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars.act_ready[g]);
           } else {
-            publish(&bars.act_ready[g]);
+            fence_proxy_async();
           }
+          tc_fence_before();
+          mbar_arrive(&bars.act_ready[(buf ^ 1) * 4 + g]);
         }
       }
       // ---- chain: (BACKWARD: E2 = d emb) then layers 7..1; each: acc * (h_{l-1} > 0) -> dY_{l-1}
@@ -654,11 +649,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           mask_release();
         }
         for (int g = 0; g < 4; ++g)   // output = dY_{l-1}: stash block DY_H + 4 (l-1) + g
-          convert(T_{}, g, mk[g], (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr, [&]() {
-            // l == 8 (BACKWARD): the previous commits of this warp are seed, E0 g0, E0 g1 (E1 stores nothing), so block
-            // g < 2 was handed over at most 2 groups ago
-            if (KIND == KIND_BACKWARD && l == 8) warp_store_guard<1>(lane); else guard();
-          });
+          convert(T_{}, g, mk[g], (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr);
         buf ^= 1;
       }
       if (with_enc) {
@@ -710,28 +701,54 @@ __device__ __forceinline__ void chain_body(const BwdParams& p, const int vbid, c
           }
         }
       }
-      if (KIND == KIND_BACKWARD && tile_done) {
-        // publish the tile to the wgrad CTAs: every dY block store of the four epilogue warps has completed
-        if (lane == 0) bulk_wait_all<0>();
-        __syncwarp();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          __threadfence();
-          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(tile_done + tile), "r"(1) : "memory");
-        }
+    }
+  }
+  if constexpr (STASHW) {
+    if (warp >= 7) {
+      // ===================================================================== dY stash warps
+      const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
+      const int row = q * 32 + lane;
+      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+      uint32_t ar_phase = 0;                                    // bit 4 b + g: parity of the next completion of act_ready[4 b + g]
+      int sbuf = 0;                                             // accumulator buffer of the step being stashed
+      for (int it = 0; it < n_my_tiles; ++it) {
+        uint8_t* const dyt = p.dy_stash + (size_t)(vbid + it * vgrid) * DY_BLOCKS * BLOCK_BYTES;
+        // one step: `ng` groups handed over by its epilogue; stashed to blocks blk0 .. (blk0 < 0: only observed)
+        auto follow = [&](int ng, int blk0) {
+          for (int g = 0; g < ng; ++g) {
+            const int i = sbuf * 4 + g;
+            mbar_wait(&bars.act_ready[i], (ar_phase >> i) & 1u);
+            ar_phase ^= (1u << i);
+            if (blk0 < 0 || (p.debug & 1)) continue;
+            tc_fence_after();
+            uint32_t a[32];
+            tmem_ld32(tlane + (uint32_t)sbuf * 256 + (uint32_t)g * 32u, a);
+            tmem_ld_wait();
+            uint8_t* const dst = dyt + (size_t)(blk0 + g) * BLOCK_BYTES + stash_chunk_off(row, 0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) stg128b(dst + c * STASH_CHUNK_STRIDE, make_uint4(a[c * 4], a[c * 4 + 1], a[c * 4 + 2], a[c * 4 + 3]));
+          }
+          tc_fence_before();                                    // this warp no longer reads the operand in buffer sbuf
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.a_free[sbuf]);
+          sbuf ^= 1;
+        };
+        follow(2, DY_MID);                                      // S0 -> E0: dY_mid
+        follow(4, -1);                                          // S1 -> E1: d bottleneck, not stashed
+        for (int l = 8; l >= 1; --l) follow(4, DY_H + 4 * (l - 1));   // S2, layers 7..1 -> dY_{l-1}
+        if (with_enc) follow(0, -1);                            // layer 0 (encoding Jacobian): hands nothing over
       }
     }
   }
-  if (KIND == KIND_BACKWARD && lane == 0 && warp >= 2 && warp < 6) bulk_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 template <int KIND, bool TS>
-__global__ void __launch_bounds__(B_THREADS, 1) field_chain_kernel(const __grid_constant__ BwdParams p) {
-  chain_body<KIND, TS>(p, (int)blockIdx.x, (int)gridDim.x, nullptr);
+__global__ void __launch_bounds__((TS && KIND == KIND_BACKWARD) ? B_THREADS_STASH : B_THREADS, 1)
+    field_chain_kernel(const __grid_constant__ BwdParams p) {
+  chain_body<KIND, TS>(p);
 }
 
 template <int KIND>
@@ -749,7 +766,7 @@ int launch_chain(const BwdParams& p, cudaStream_t stream) {
     return 0;
   }
 #endif
-  field_chain_kernel<KIND, true><<<grid, B_THREADS, smem, stream>>>(p);
+  field_chain_kernel<KIND, true><<<grid, KIND == KIND_BACKWARD ? B_THREADS_STASH : B_THREADS, smem, stream>>>(p);
   RSN_LAUNCH_CHECK("field_chain_kernel");
   return 0;
 }

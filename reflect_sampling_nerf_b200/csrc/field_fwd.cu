@@ -604,18 +604,33 @@ __global__ void __launch_bounds__(TRAIN ? NUM_THREADS_TRAIN : NUM_THREADS, 1) fi
           const uint32_t w3 = ring_wait();
           const int s3 = ring_advance();
           issue_act(3, w3, ID128, tm, a_tm, acc);
+          // The heads (N = 16, all four K-blocks of h7).  TS form: they ride behind the second half, whose commit covers them
+          // (the epilogue reads them after groups 2, 3).  SS form: the epilogue overwrites the shared-memory blocks 0, 1 in
+          // place as soon as the FIRST half is committed, so every MMA that reads them -- the heads too -- goes before it.
+          auto issue_heads = [&](uint32_t w) {
+            bool acc_h = false;
+            for (int kb = 0; kb < 4; ++kb)
+              issue_act(kb, w + kb * (N_HEAD * 128 / BDIV), ID16, tmem + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, a_tm,
+                        acc_h);
+          };
+          int sh = -1;
+          if (!TS) {
+            const uint32_t w = ring_wait();
+            sh = ring_advance();
+            issue_heads(w);
+          }
           commit(&bars.acc_full[2 * buf]);
           issue_act(2, w2 + HALF_B, ID128, tm + 128, a_tm, acc1);
           ring_release_slot(s2);
           issue_act(3, w3 + HALF_B, ID128, tm + 128, a_tm, acc1);
           ring_release_slot(s3);
-          // the heads ride behind the second half: its commit covers them (the epilogue reads them after groups 2, 3)
-          const uint32_t w = ring_wait();
-          bool acc_h = false;
-          for (int kb = 0; kb < 4; ++kb)
-            issue_act(kb, w + kb * (N_HEAD * 128 / BDIV), ID16, tmem + (uint32_t)(buf ^ 1) * 256 + HEAD_TMEM_COL, a_tm,
-                      acc_h);
-          ring_release();
+          if (TS) {
+            const uint32_t w = ring_wait();
+            issue_heads(w);
+            ring_release();
+          } else {
+            ring_release_slot(sh);
+          }
           commit(&bars.acc_full[2 * buf + 1]);
           buf ^= 1;
         }

@@ -102,7 +102,7 @@ constexpr int DY_MID = 1;        // 2 blocks: d(mid hidden pre-activation), 128 
 constexpr int DY_BOTT = 3;       // 4 blocks: d(bottleneck)
 constexpr int DY_H = 7;          // + 4*l + g : d(pre-activation of base layer l)
 constexpr int DY_BLOCKS = 39;
-constexpr bool DY_CHUNK_MAJOR = false;   // image of the dY blocks (the dgrad chain still stages them in shared memory)
+constexpr bool DY_CHUNK_MAJOR = true;    // every dY block is a chunk-major image
 
 // ---- per-point feature row written by the forward kernel ([P][16] fp32) ------------------------------
 // 0-2 rgb = diff + tint*mid | 3-5 diff | 6-8 tint | 9-11 pred_normal | 12 sigmoid(rough) | 13 n.d

@@ -1,4 +1,4 @@
-// Body of the wgrad kernel (see field_wgrad.cu for the description); shared with the fused backward kernel.
+// Body of the wgrad kernel (see field_wgrad.cu for the description).
 #pragma once
 #include "rsn_common.cuh"
 #include "umma.cuh"
@@ -7,12 +7,6 @@
 #include <stdlib.h>
 
 namespace {
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 using namespace umma;
 using namespace rsnf;
@@ -56,9 +50,8 @@ struct WBarriers {
   uint32_t tmem_slot;
 };
 
-// `vbid` = index of this CTA among the wgrad CTAs (the fused backward kernel runs dgrad-chain CTAs beside them);
-// `tile_done` (or NULL): per-tile flags set by the dgrad chain once the tile's dY blocks are in global memory.
-__device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, const int* tile_done) {
+__device__ __forceinline__ void wgrad_body(const WParams& p) {
+  const int vbid = (int)blockIdx.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ WBarriers bars;
@@ -115,17 +108,6 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t0; t < t1; t += tstep) {
-        if (tile_done) {   // fused backward: wait until the dgrad chain has published this tile's dY blocks
-          const long long w0 = clock64();
-          while (ld_acquire_gpu(tile_done + t) == 0) {
-            __nanosleep(200);
-            if (clock64() - w0 > RSN_MBAR_TIMEOUT_CYCLES) {
-              printf("rsn_b200: wgrad timed out waiting for dY tile %d\n", t);
-              __trap();
-            }
-          }
-          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic acquire -> async-proxy (TMA) reads
-        }
         const uint8_t* dyt = p.dy + ((size_t)t * DY_BLOCKS + job.a_blk) * BLOCK_BYTES;
         const uint8_t* xt = p.x + (size_t)t * STASH_TILE_BYTES + (size_t)job.b_blk * BLOCK_BYTES;
         for (int s = 0; s < TILE / SLAB_ROWS; ++s) {
@@ -187,37 +169,41 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
       }
       if (elect_one_sync()) mma_commit(&bars.acc_full);
     }
-  } else if (warp < 6) {   // (the fused backward kernel launches one more warp than this role uses)
+  } else {
     // ---- db: column sums of the dY slabs while they sit in shared memory; then the dW flush.
-    // Thread -> one 16-byte chunk column (8 features) of one dY block, every 4th row: within a warp the 32 lanes
-    // read the 8 chunks of one row of each of the 4 blocks = conflict-free 128-bit shared loads.
-    const int t = threadIdx.x - 64;
-    const int cc = t & 31, rphase = t >> 5;
-    const int blk = cc >> 3, ch = cc & 7;
+    // The dY blocks are chunk-major images: inside a slab block the 16-byte chunk c (8 features) of point r sits at
+    // c * 1024 + r * 16.  Warp w sums block w; lane = point (r = lane, lane + 32), so every 128-bit shared load of a warp
+    // reads 512 contiguous bytes (conflict-free); 8 chunks x 8 features = 64 partial sums per thread, reduced across the
+    // lanes once at the end.
+    static_assert(DY_CHUNK_MAJOR && SLAB_ROWS == 64, "db sums are written for chunk-major dY slabs of 64 points");
+    const int blk = warp - 2;
     const bool db_active = blk < mb;
-    float acc[8];
+    float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
     int stage = 0;
     uint32_t phase = 0;
     for (int s = 0; s < ((p.debug & 3) == 1 ? 0 : n_slabs); ++s) {
       mbar_wait(&bars.full[stage], phase);
       if (db_active && (p.debug & 3) != 3) {
-        const uint32_t src = smem_u32(smem + (size_t)stage * SLAB_BYTES) + blk * SLAB_BLOCK_BYTES;
-        uint4 v[SLAB_ROWS / 4];
+        const uint32_t src = smem_u32(smem + (size_t)stage * SLAB_BYTES) + blk * SLAB_BLOCK_BYTES + (uint32_t)lane * 16u;
 #pragma unroll
-        for (int i = 0; i < SLAB_ROWS / 4; ++i) {
-          const int r = rphase + 4 * i;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
-                       : "r"(src + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4)));
-        }
+        for (int h = 0; h < 2; ++h) {
+          uint4 v[8];
 #pragma unroll
-        for (int i = 0; i < SLAB_ROWS / 4; ++i) {
-          acc[0] += __uint_as_float(v[i].x << 16), acc[1] += __uint_as_float(v[i].x & 0xffff0000u);
-          acc[2] += __uint_as_float(v[i].y << 16), acc[3] += __uint_as_float(v[i].y & 0xffff0000u);
-          acc[4] += __uint_as_float(v[i].z << 16), acc[5] += __uint_as_float(v[i].z & 0xffff0000u);
-          acc[6] += __uint_as_float(v[i].w << 16), acc[7] += __uint_as_float(v[i].w & 0xffff0000u);
+          for (int c = 0; c < 8; ++c)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[c].x), "=r"(v[c].y), "=r"(v[c].z), "=r"(v[c].w)
+                         : "r"(src + (uint32_t)c * STASH_CHUNK_STRIDE + (uint32_t)h * 512u));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            acc[c][0] += __uint_as_float(v[c].x << 16), acc[c][1] += __uint_as_float(v[c].x & 0xffff0000u);
+            acc[c][2] += __uint_as_float(v[c].y << 16), acc[c][3] += __uint_as_float(v[c].y & 0xffff0000u);
+            acc[c][4] += __uint_as_float(v[c].z << 16), acc[c][5] += __uint_as_float(v[c].z & 0xffff0000u);
+            acc[c][6] += __uint_as_float(v[c].w << 16), acc[c][7] += __uint_as_float(v[c].w & 0xffff0000u);
+          }
         }
       }
       __syncwarp();
@@ -229,8 +215,17 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
     }
     if (n_slabs > 0) {
       if (db_active && job.db_off >= 0 && (p.debug & 3) != 1) {
+        // feature c * 8 + i of the block: summed over the lanes, kept by lane (c * 8 + i) & 31 in mine[(c * 8 + i) >> 5]
+        float mine[2] = {0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(p.grad + job.db_off + blk * 64 + ch * 8 + i, acc[i]);
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float t = warp_sum(acc[c][i]);
+            if (lane == ((c * 8 + i) & 31)) mine[(c * 8 + i) >> 5] = t;
+          }
+        atomicAdd(p.grad + job.db_off + blk * 64 + lane, mine[0]);
+        atomicAdd(p.grad + job.db_off + blk * 64 + 32 + lane, mine[1]);
       }
       mbar_wait(&bars.acc_full, 0);
       tc_fence_after();
@@ -263,7 +258,7 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int vbid, con
 }
 
 __global__ void __launch_bounds__(W_THREADS, 1) field_wgrad_kernel(const __grid_constant__ WParams p) {
-  wgrad_body(p, (int)blockIdx.x, nullptr);
+  wgrad_body(p);
 }
 
 // The 12 jobs of one pass.  Gradient blob regions (fp32): dW [64 m_blocks][64 n_blocks] row-major, then db.

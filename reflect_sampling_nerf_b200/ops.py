@@ -487,22 +487,6 @@ def field_backward(wblob_t: Tensor, stash: Tensor, mode: int, origins, dirs, are
     return g_area
 
 
-def field_backward_fused(wblob_t: Tensor, stash: Tensor, mode: int, origins, dirs, area, bins, n: int, s: int,
-                         g_sigma: Optional[Tensor], g_feat: Tensor, feat: Tensor, aux: Tensor, dy_stash: Tensor,
-                         want_area: bool, grad_blob: Tensor) -> Optional[Tensor]:
-    """field_backward + field_wgrad in one launch (csrc/field_bwd_fused.cu) -- TEST BUILD only (librsn_b200_dbg.so)."""
-    dbg = _lib.lib_dbg()
-    g_area = torch.empty(n, s, device=stash.device, dtype=torch.float32) if want_area else None
-    ws = torch.empty(dbg.rsn_field_backward_fused_workspace_bytes(n * s), dtype=torch.uint8, device=stash.device)
-    code = dbg.rsn_field_backward_fused(_lib.ptr(wblob_t), _lib.ptr(stash), mode, _lib.ptr(origins), _lib.ptr(dirs),
-                                        _lib.ptr(area), _lib.ptr(bins), n, s, _lib.ptr(g_sigma), _lib.ptr(g_feat),
-                                        _lib.ptr(feat), _lib.ptr(aux), _lib.ptr(dy_stash), _lib.ptr(g_area),
-                                        _lib.ptr(grad_blob), _lib.ptr(ws), _lib.stream())
-    if code != 0:
-        raise RuntimeError(f"rsn_field_backward_fused failed with code {code}: {dbg.rsn_last_error().decode()}")
-    return g_area
-
-
 def field_wgrad(stash: Tensor, dy_stash: Tensor, n_points: int, grad_blob: Tensor, count: Optional[Tensor] = None,
                 points_per_ray: int = 1) -> None:
     """K5 wgrad: accumulates dW / db of every Linear over the pass into grad_blob (fp32, wgrad_layout())."""

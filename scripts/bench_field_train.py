@@ -59,6 +59,3 @@ timeit(lambda: ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sig
 timeit(lambda: ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, True),
        P * 1229056, P * (288 + 4 * 128 + 35 * 128 + 164), "field_chain<backward+area>")
 timeit(lambda: ops.field_wgrad(stash, dy, P, blob), P * 1230592, P * 72 * 128, "field_wgrad")
-blob2 = torch.zeros(ops.wgrad_layout()[2], device="cuda")
-timeit(lambda: ops.field_backward_fused(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, dy, False, blob2),
-       P * (1179904 + 1230592), P * (288 + 35 * 128 + 160 + 52 * 128), "field_bwd_fused (chain+wgrad)")

@@ -99,9 +99,10 @@ def test_inf_color_matches_oracle():
 
 
 def test_tmem_operand_form_is_bit_identical(monkeypatch):
-    """Product forward (A operand of the hidden layers from TMEM, stash staged after the hand-over) against the
-    shared-memory operand form of the TEST BUILD (librsn_b200_dbg.so, RSN_FWD_TS=0): same arithmetic in the same order =>
-    identical outputs, stash and aux.  Also pins product == test build for the default form."""
+    """Product forward (A operand of the hidden layers from TMEM) against the shared-memory operand form of the TEST BUILD
+    (librsn_b200_dbg.so, RSN_FWD_TS=0; inference launches only -- a training launch always takes the TMEM form): same
+    arithmetic in the same order => identical outputs.  Also pins product == test build for the default form, stash and
+    aux included, and that repeated launches are bit-identical (no race between the roles of the kernel)."""
     from reflect_sampling_nerf_b200 import _lib
     field, o, d, pa, bins = _setup(37, 24, 5, "uniform", 8.1e-7)      # 888 points = 7 tiles
     wblob, bias = [t.cuda() for t in packing.pack_field(field.state_dict())]
@@ -126,6 +127,18 @@ def test_tmem_operand_form_is_bit_identical(monkeypatch):
         for a, b in zip(prod[:5], other[:5]):
             assert torch.equal(a, b)
         assert torch.equal(prod[5][..., :7], other[5][..., :7])      # aux: 7 of 8 floats per point are defined
+    for _ in range(20):                                                # repeated launches of either form: bit-identical
+        monkeypatch.setenv("RSN_FWD_TS", "0")
+        try:
+            _lib.use_dbg(True)
+            again_ss = run()
+        finally:
+            _lib.use_dbg(False)
+        again = run()
+        torch.cuda.synchronize()
+        for ref, got in ((ss, again_ss), (prod, again)):
+            for a, b in zip(ref[:5], got[:5]):
+                assert torch.equal(a, b)
 
 
 def test_two_fields_on_two_streams_do_not_share_bias_state():

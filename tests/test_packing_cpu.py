@@ -27,6 +27,18 @@ def test_block_image_roundtrip_and_swizzle():
     assert raw.item() == m[r, k].item()
 
 
+def test_chunk_major_image_roundtrip_and_offsets():
+    """csrc/field_layout.cuh stash_chunk_off: chunk c (8 features) of point r at (r // 64) * 8192 + c * 1024 + (r % 64) * 16."""
+    from reflect_sampling_nerf_b200.blocks import pack_blocks_cm, unpack_blocks_cm
+    m = torch.randn(256, 128).bfloat16()
+    img = pack_blocks_cm(m)
+    assert img.shape == (2, 2, 16384) and img.dtype == torch.uint8
+    assert torch.equal(unpack_blocks_cm(img), m)
+    for t, kb, r, c in ((0, 0, 0, 0), (1, 1, 77, 5), (0, 1, 127, 7), (1, 0, 64, 3)):
+        off = (r // 64) * 8192 + c * 1024 + (r % 64) * 16
+        assert torch.equal(img[t, kb, off:off + 16].view(torch.bfloat16), m[128 * t + r, kb * 64 + 8 * c: kb * 64 + 8 * c + 8])
+
+
 def test_layout_constants_match_library():
     lib = _lib.lib()
     assert lib.rsn_field_blob_bytes() == packing.FWD_BLOB_BYTES

@@ -44,6 +44,25 @@ def test_mnmajor_tile_gemm(NB):
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("NB", [1, 2, 4])
+def test_mnmajor_chunk_major_tile_gemm(NB):
+    """The wgrad's read of chunk-major stash blocks: NO-swizzle MN-major descriptors, LBO = 128 (next 8 points), SBO = 1024
+    (next 8 features); the swapped pair must NOT give the product (pins which field carries which stride)."""
+    from reflect_sampling_nerf_b200.blocks import pack_blocks_cm
+    g = torch.Generator().manual_seed(10 + NB)
+    u = torch.randn(128, 128, generator=g).bfloat16()       # [points, M]
+    v = torch.randn(128, NB * 64, generator=g).bfloat16()   # [points, N]
+    ub, vb = pack_blocks_cm(u)[0].cuda(), pack_blocks_cm(v)[0].cuda()
+    ref = u.float().T @ v.float()
+    out = torch.full((128, NB * 64), float("nan"), device="cuda")
+    _lib.call("rsn_probe_umma_mnmajor_cm", ub.data_ptr(), vb.data_ptr(), NB, 128, 1024, out.data_ptr(), 0, None, _lib.stream())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-2)
+    _lib.call("rsn_probe_umma_mnmajor_cm", ub.data_ptr(), vb.data_ptr(), NB, 1024, 128, out.data_ptr(), 0, None, _lib.stream())
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max() > 1.0
+
+
 @pytest.mark.parametrize("N,KB", [(256, 4), (256, 1), (128, 2), (16, 4), (64, 3)])
 def test_cta_pair_tile_gemm(N, KB):
     """tcgen05.mma.cta_group::2: M = 256 over a CTA pair, each CTA staging its 128 rows of X and N/2 rows of W."""

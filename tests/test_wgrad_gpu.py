@@ -32,7 +32,7 @@ def test_wgrad_matches_matmul(n_tiles):
     for b in SWIZZLED_X_BLOCKS:
         x_img[:, b] = x_sw[:, b]
     xs = torch.cat([x_img.reshape(n_tiles, -1), torch.zeros(n_tiles, 36864, dtype=torch.uint8)], dim=1).cuda()
-    dys = torch.stack([pack_blocks(dy[t * 128:(t + 1) * 128]) for t in range(n_tiles)]).cuda()
+    dys = pack_blocks_cm(dy).cuda()                      # every dY block is a chunk-major image
     offs, shapes, total = ops.wgrad_layout()
     assert len(shapes) == len(JOBS)
     blob = torch.zeros(total, device="cuda")
