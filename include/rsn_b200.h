@@ -125,8 +125,9 @@ int rsn_field_forward(const void* wblob, const float* bias, int mode, const floa
                       const float* area, const float* bins, int64_t n_rays, int64_t n_samples, float* sigma,
                       float* feat, const int* n_rays_dev, rsn_stream_t stream);
 /* Training form of rsn_field_forward: additionally writes the activation stash (rsn_field_stash_bytes(N*S)
- * bytes: per 128-point tile 41 bf16 block images = IPE, the 8 hidden activations, bottleneck, IDE, mid hidden)
- * that the normals / backward / wgrad kernels read, and aux [N*S,8] = mid rgb (3), raw normal head (3), raw roughness head, 1 spare.
+ * bytes: per 128-point tile 41 bf16 block slots = IPE, the 8 hidden activations, bottleneck (unused), IDE, mid hidden,
+ * followed by the ReLU bit masks; the encodings as swizzled shared-memory images, the activations as chunk-major images,
+ * csrc/field_layout.cuh) that the normals / backward / wgrad kernels read, and aux [N*S,8] = mid rgb (3), raw normal head (3), raw roughness head, 1 spare.
  * (stash == NULL with aux != NULL: inference that also returns the raw mid colour.) */
 int rsn_field_forward_train(const void* wblob, const float* bias, int mode, const float* origins,
                             const float* dirs, const float* area, const float* bins, int64_t n_rays,
@@ -168,8 +169,8 @@ int64_t rsn_field_blob_t_bytes(void);
 /* ---- K5 backward, dgrad chain -----------------------------------------------------------------------
  * Replaces the autograd backward of reflect_sampling_nerf_field.py:122-186 (mode 0) / 190-201 (mode 1) for one
  * pass: from g_sigma [N*S] = dL/d sigma and g_feat [N*S,16] = dL/d feat (forward layout; columns 14,15 are
- * ignored; g_sigma may be NULL = zero) to the pre-activation gradient of every Linear, written to dy_stash (rsn_field_dy_stash_bytes) for
- * rsn_field_wgrad.  feat / aux are the forward outputs.  If g_area != NULL the chain continues through layer 0
+ * ignored; g_sigma may be NULL = zero) to the pre-activation gradient of every Linear, written to dy_stash
+ * (rsn_field_dy_stash_bytes; chunk-major bf16 block images, csrc/field_layout.cuh) for rsn_field_wgrad.  feat / aux are the forward outputs.  If g_area != NULL the chain continues through layer 0
  * and the IPE damping and writes dL/d pixel_area (mode 0) or dL/d sqradius (mode 1) of every POINT [N*S]
  * (the caller sums over the samples of a ray): the roughness -> cone width path of
  * reflect_sampling_nerf_model.py:272,286,290. */
