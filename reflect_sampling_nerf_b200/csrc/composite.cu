@@ -16,6 +16,7 @@
 // 4 (dL/dsigma) + C*4 (dL/dfeat) out per sample.
 #include "rsn_common.cuh"
 #include <algorithm>
+#include <initializer_list>
 
 namespace {
 
@@ -467,6 +468,306 @@ __global__ void __launch_bounds__(256) render_weights_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The model's 16-channel form with the feature rows STAGED BY THE TMA ENGINE (S % 4 == 0, S <= 256).  A ray's features
+// (S x 64 B) and normals (S x 12 B) are contiguous, so lane 0 of each warp fetches them with two cp.async.bulk copies
+// into the warp's shared-memory stage (mbarrier complete_tx) and the warp computes the ray's weights from sigma / bins
+// (small, register-staged loads) WHILE that copy is in flight; the feature pass then runs out of shared memory.  The
+// register-staged kernels above wait on two dependent load phases per ray at 50 % occupancy (ncu: 23 warps stalled on
+// the long scoreboard per issue, 33 % of the DRAM peak); here the two phases overlap and ~10 KB per warp are in flight
+// without holding a register.  The feature pass is branch-free (the per-sample normal losses are selected per lane, not
+// branched on).  Arithmetic and its order are those of the kernels above.
+constexpr int TMA_WARPS = 4;
+constexpr int TMA_MAX_SAMPLES = 256;
+
+__device__ __forceinline__ uint32_t cs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cs_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cs_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cs_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cs_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(cs_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cs_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   cs_smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(cs_smem_u32(bar))
+               : "memory");
+}
+// lane 0: fetch ray r's features (and normals) into the warp's stage
+__device__ __forceinline__ void cs_fetch_ray(float* stage, uint64_t* bar, const float* feat, const float* normals, int64_t r,
+                                             int S) {
+  cs_mbar_expect_tx(bar, (uint32_t)S * (normals ? 76u : 64u));
+  cs_bulk_g2s(stage, feat + r * S * 16, (uint32_t)S * 64u, bar);
+  if (normals) cs_bulk_g2s(stage + 16 * S, normals + r * S * 3, (uint32_t)S * 12u, bar);
+}
+// per-warp shared memory (floats): [feat 16 S | normals 3 S | work rows: forward S (weights), backward 3 S]
+__host__ __device__ constexpr int cs_warp_floats(int S, bool bwd) { return 19 * S + (bwd ? 3 * S : S); }
+
+template <int K>
+__global__ void __launch_bounds__(TMA_WARPS * 32) composite16_fwd_tma_kernel(
+    const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends, int64_t bin_stride,
+    const float* __restrict__ feat, float* __restrict__ weights, float* __restrict__ acc_out, float* __restrict__ depth_out,
+    float4* __restrict__ feat_out4, int64_t n_rays, int S, const float* __restrict__ normals, float* __restrict__ pnl_out,
+    float* __restrict__ ol_out, float* __restrict__ blend_out, const int* __restrict__ n_rays_dev) {
+  extern __shared__ __align__(128) float sm_tma[];
+  __shared__ uint64_t bars[TMA_WARPS];
+  n_rays = rsn_count(n_rays, n_rays_dev);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* const fs = sm_tma + (size_t)warp * cs_warp_floats(S, false);
+  float* const nrm = fs + 16 * S;
+  float* const ws = nrm + 3 * S;
+  uint64_t* const bar = &bars[warp];
+  if (lane == 0) {
+    cs_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int64_t warp0 = (int64_t)blockIdx.x * TMA_WARPS + warp, nwarps = (int64_t)gridDim.x * TMA_WARPS;
+  uint32_t phase = 0;
+  const int quad = lane & 3;
+  const float sel2 = quad == 2 ? 1.f : 0.f, sel3 = quad == 3 ? 1.f : 0.f;
+  if (warp0 < n_rays && lane == 0) cs_fetch_ray(fs, bar, feat, normals, warp0, S);
+  for (int64_t r = warp0; r < n_rays; r += nwarps) {
+    const float* sg = sigma + r * S;
+    const float* st = starts + r * bin_stride;
+    const float* en = ends + r * bin_stride;
+    double tau_carry = 0.0, cw_carry = 0.0;
+    float acc = 0.f;
+    int median = S;
+    for (int b0 = 0; b0 < S; b0 += 32 * K) {   // the ray's weights, while the TMA engine fetches its features
+      float dd[K], w[K], tn[K];
+      weights_round<K>(sg, st, en, b0, S, lane, tau_carry, dd, w, tn);
+      const int s0 = b0 + lane * K;
+      double local = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (s0 + k < S) {
+          ws[s0 + k] = w[k];
+          acc += w[k];
+        }
+        local += (double)w[k];
+      }
+      if (K == 4 && s0 + 3 < S) {
+        *reinterpret_cast<float4*>(weights + r * S + s0) = make_float4(w[0], w[1], w[2], w[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (s0 + k < S) weights[r * S + s0 + k] = w[k];
+      }
+      const double incl = warp_incl_scan(local, lane);
+      double cw = cw_carry + (incl - local);
+      int mine = S;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        cw += (double)w[k];
+        if (mine == S && s0 + k < S && (float)cw >= 0.5f) mine = s0 + k;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(RSN_FULL, mine, o));
+      median = min(median, mine);
+      cw_carry += __shfl_sync(RSN_FULL, incl, 31);
+    }
+    acc = warp_sum(acc);
+    __syncwarp();
+    cs_mbar_wait(bar, phase);
+    phase ^= 1u;
+    const float4* const f4 = reinterpret_cast<const float4*>(fs);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lsum = 0.f;   // with normals: quad 2 accumulates w |n - n_pred|^2, quad 3 accumulates w max(0, n.d)^2
+    if (normals) {
+#pragma unroll 4
+      for (int idx = lane; idx < S * 4; idx += 32) {
+        const float4 v = f4[idx];
+        const int smp = idx >> 2;
+        const float wv = ws[smp];
+        a.x += wv * v.x, a.y += wv * v.y, a.z += wv * v.z, a.w += wv * v.w;
+        // quad 2: feature columns 8..11 = tint_b, pred_normal xyz; quad 3: columns 12..15 = sigmoid roughness, n.d, ...
+        const float d0 = nrm[smp * 3] - v.y, d1 = nrm[smp * 3 + 1] - v.z, d2 = nrm[smp * 3 + 2] - v.w;
+        const float pz = fmaxf(v.y, 0.f);
+        lsum += wv * (sel2 * (d0 * d0 + d1 * d1 + d2 * d2) + sel3 * (pz * pz));
+      }
+#pragma unroll
+      for (int o = 16; o >= 4; o >>= 1) lsum += __shfl_xor_sync(RSN_FULL, lsum, o);
+      if (lane == 2) pnl_out[r] = lsum;
+      if (lane == 3) ol_out[r] = lsum;
+    } else {
+#pragma unroll 4
+      for (int idx = lane; idx < S * 4; idx += 32) {
+        const float4 v = f4[idx];
+        const float wv = ws[idx >> 2];
+        a.x += wv * v.x, a.y += wv * v.y, a.z += wv * v.z, a.w += wv * v.w;
+      }
+    }
+    __syncwarp();   // every lane is done with the stage and the work row: fetch the next ray
+    if (r + nwarps < n_rays && lane == 0) cs_fetch_ray(fs, bar, feat, normals, r + nwarps, S);
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) {
+      a.x += __shfl_xor_sync(RSN_FULL, a.x, o), a.y += __shfl_xor_sync(RSN_FULL, a.y, o);
+      a.z += __shfl_xor_sync(RSN_FULL, a.z, o), a.w += __shfl_xor_sync(RSN_FULL, a.w, o);
+    }
+    if (lane < 4) feat_out4[r * 4 + lane] = a;
+    if (lane == 0) {
+      if (blend_out) {   // RGBRenderer with the white background, then torch.clip (model.py:176-177): clip(rgb + (1 - acc))
+        const float rest = 1.f - acc;
+        blend_out[r * 3 + 0] = fminf(fmaxf(a.x + rest, 0.f), 1.f);
+        blend_out[r * 3 + 1] = fminf(fmaxf(a.y + rest, 0.f), 1.f);
+        blend_out[r * 3 + 2] = fminf(fmaxf(a.z + rest, 0.f), 1.f);
+      }
+      acc_out[r] = acc;
+      const int mi = min(median, S - 1);
+      depth_out[r] = (__ldg(st + mi) + __ldg(en + mi)) / 2.f;
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(TMA_WARPS * 32) composite16_bwd_tma_kernel(
+    const float* __restrict__ sigma, const float* __restrict__ starts, const float* __restrict__ ends, int64_t bin_stride,
+    const float* __restrict__ feat, const float* __restrict__ g_weights, const float* __restrict__ g_acc,
+    const float4* __restrict__ g_feat_out4, float* __restrict__ g_sigma, float4* __restrict__ g_feat4, int64_t n_rays, int S,
+    const float* __restrict__ normals, const float* __restrict__ g_pnl, const float* __restrict__ g_ol,
+    const float* __restrict__ g_blend, const float* __restrict__ feat_out, const float* __restrict__ acc_in,
+    const int* __restrict__ n_rays_dev) {
+  extern __shared__ __align__(128) float sm_tma[];
+  __shared__ uint64_t bars[TMA_WARPS];
+  n_rays = rsn_count(n_rays, n_rays_dev);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* const fs = sm_tma + (size_t)warp * cs_warp_floats(S, true);
+  float* const nrm = fs + 16 * S;
+  float* const ws = nrm + 3 * S;             // weights
+  float* const tns = ws + S;                 // transmittance behind the sample
+  float* const gws = tns + S;                // dL/dw_s (explicit + accumulation + features)
+  uint64_t* const bar = &bars[warp];
+  if (lane == 0) {
+    cs_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int64_t warp0 = (int64_t)blockIdx.x * TMA_WARPS + warp, nwarps = (int64_t)gridDim.x * TMA_WARPS;
+  uint32_t phase = 0;
+  const int quad = lane & 3;
+  if (warp0 < n_rays && lane == 0) cs_fetch_ray(fs, bar, feat, normals, warp0, S);
+  for (int64_t r = warp0; r < n_rays; r += nwarps) {
+    const float* sg = sigma + r * S;
+    const float* st = starts + r * bin_stride;
+    const float* en = ends + r * bin_stride;
+    float ga = g_acc ? __ldg(g_acc + r) : 0.f;
+    float4 go = g_feat_out4 ? __ldg(g_feat_out4 + r * 4 + quad) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g_blend) {   // blend = clip(feat_out[0:3] + (1 - acc), 0, 1): torch.clip passes the gradient inside [0, 1]
+      const float rest = 1.f - __ldg(acc_in + r);
+      float gb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = __ldg(feat_out + r * 16 + c) + rest;
+        gb[c] = (v >= 0.f && v <= 1.f) ? __ldg(g_blend + r * 3 + c) : 0.f;
+      }
+      ga -= gb[0] + gb[1] + gb[2];
+      if (quad == 0) go.x += gb[0], go.y += gb[1], go.z += gb[2];
+    }
+    // per-lane multipliers of the two normal-loss gradients (quad 2: 2 g_pnl; quad 3: 2 g_ol), no branches in the pass
+    const float c2 = (normals && g_pnl && quad == 2) ? 2.f * __ldg(g_pnl + r) : 0.f;
+    const float c3 = (normals && g_ol && quad == 3) ? 2.f * __ldg(g_ol + r) : 0.f;
+    double tau_carry = 0.0;
+    for (int b0 = 0; b0 < S; b0 += 32 * K) {   // weights, T_next and the explicit part of dL/dw while the features arrive
+      float dd[K], w[K], tn[K];
+      weights_round<K>(sg, st, en, b0, S, lane, tau_carry, dd, w, tn);
+      const int s0 = b0 + lane * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (s0 + k < S) {
+          ws[s0 + k] = w[k], tns[s0 + k] = tn[k];
+          gws[s0 + k] = ga + (g_weights ? __ldg(g_weights + r * S + s0 + k) : 0.f);
+        }
+    }
+    __syncwarp();
+    cs_mbar_wait(bar, phase);
+    phase ^= 1u;
+    // one pass over the features: dL/dw_s and dL/dfeat
+    const float4* const f4 = reinterpret_cast<const float4*>(fs);
+    float4* const gf4 = g_feat4 + (int64_t)r * S * 4;
+#pragma unroll 4
+    for (int idx = lane; idx < S * 4; idx += 32) {
+      const int smp = idx >> 2;
+      const float4 v = f4[idx];
+      float dot = go.x * v.x + go.y * v.y + go.z * v.z + go.w * v.w;
+      dot += __shfl_xor_sync(RSN_FULL, dot, 1);
+      dot += __shfl_xor_sync(RSN_FULL, dot, 2);
+      const float wv = ws[smp];
+      if (quad == 0) gws[smp] += dot;
+      float4 g = make_float4(go.x * wv, go.y * wv, go.z * wv, go.w * wv);
+      if (normals) {   // per-sample normal losses: the weight is a constant there (detached upstream)
+        const float k2 = c2 * wv, k3 = c3 * wv;
+        g.y += k2 * (v.y - nrm[smp * 3]) + k3 * fmaxf(v.y, 0.f);
+        g.z += k2 * (v.z - nrm[smp * 3 + 1]);
+        g.w += k2 * (v.w - nrm[smp * 3 + 2]);
+      }
+      gf4[idx] = g;
+    }
+    __syncwarp();
+    if (r + nwarps < n_rays && lane == 0) cs_fetch_ray(fs, bar, feat, normals, r + nwarps, S);
+    if (g_sigma != nullptr) {   // (NULL: density detached upstream -- bounce passes, model.py:297,323)
+      // dL/d(dd_j) = gw_j T_{j+1} - sum_{s>j} gw_s w_s ;  dL/dsigma_j = dL/d(dd_j) * delta_j
+      double total = 0.0;
+      for (int s = lane; s < S; s += 32) total += (double)(gws[s] * ws[s]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(RSN_FULL, total, o);
+      double pre_carry = 0.0;
+      for (int b0 = 0; b0 < S; b0 += 32 * K) {
+        const int s0 = b0 + lane * K;
+        float gw[K], w[K], out[K];
+        double local = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const bool ok = s0 + k < S;
+          gw[k] = ok ? gws[s0 + k] : 0.f;
+          w[k] = ok ? ws[s0 + k] : 0.f;
+          local += (double)(gw[k] * w[k]);
+        }
+        const double incl = warp_incl_scan(local, lane);
+        double pre = pre_carry + (incl - local);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          pre += (double)(gw[k] * w[k]);
+          out[k] = 0.f;
+          if (s0 + k < S)
+            out[k] = (gw[k] * tns[s0 + k] - (float)(total - pre)) * (__ldg(en + s0 + k) - __ldg(st + s0 + k));
+        }
+        if (K == 4 && s0 + 3 < S) {
+          *reinterpret_cast<float4*>(g_sigma + r * S + s0) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            if (s0 + k < S) g_sigma[r * S + s0 + k] = out[k];
+        }
+        pre_carry += __shfl_sync(RSN_FULL, incl, 31);
+      }
+    }
+    __syncwarp();   // the work rows are free for the next ray
+  }
+}
+
+// the TMA-staged form applies to the model's shapes: 16 channels, S a multiple of 4 up to 256, 16-byte aligned rows
+inline bool tma_form_ok(int S, std::initializer_list<const void*> rows) {
+  if (S % 4 != 0 || S > TMA_MAX_SAMPLES || S < 4) return false;
+  for (const void* p : rows)
+    if (((uintptr_t)p & 15) != 0) return false;
+  return true;
+}
+
 constexpr int VEC_MAX_SAMPLES = 1024;   // 8 warps x 3 rows x 4 KB of dynamic shared memory in the backward
 
 template <int C>
@@ -477,6 +778,25 @@ int launch_fwd(const float* sigma, const float* starts, const float* ends, int64
   const int threads = 256;
   int64_t want = (n_rays * 32 + threads - 1) / threads;
   int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
+  if (C == 16 && tma_form_ok(S, {feat, feat_out, sigma, weights, normals})) {
+    const size_t smem = (size_t)TMA_WARPS * cs_warp_floats(S, false) * sizeof(float);
+    static std::atomic<unsigned long long> done[3];
+    const int bpsm = std::max(1, std::min(8, (int)((225 * 1024) / (smem + 1024))));
+    blocks = (int)std::min<int64_t>((n_rays + TMA_WARPS - 1) / TMA_WARPS, (int64_t)rsn_num_sms() * bpsm);
+#define RSN_FWDT(K, I)                                                                                               \
+  do {                                                                                                               \
+    RSN_CUDA(rsn_ensure_smem(composite16_fwd_tma_kernel<K>, (int)(TMA_WARPS * cs_warp_floats(TMA_MAX_SAMPLES, false) * 4), done[I])); \
+    composite16_fwd_tma_kernel<K><<<blocks, TMA_WARPS * 32, smem, stream>>>(sigma, starts, ends, bin_stride, feat, weights, \
+                                                                          acc, depth, (float4*)feat_out, n_rays, S,    \
+                                                                          normals, pnl, ol, blend, n_rays_dev);         \
+  } while (0)
+    if (S <= 32) RSN_FWDT(1, 0);
+    else if (S <= 64) RSN_FWDT(2, 1);
+    else RSN_FWDT(4, 2);
+#undef RSN_FWDT
+    RSN_LAUNCH_CHECK("composite16_fwd_tma_kernel");
+    return 0;
+  }
   if (C >= 4 && C % 4 == 0 && S <= VEC_MAX_SAMPLES && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)feat_out & 15) == 0) {
     constexpr int Q = C >= 4 ? C / 4 : 1;
     const int s_pad = (S + 3) & ~3;
@@ -515,6 +835,25 @@ int launch_bwd(const float* sigma, const float* starts, const float* ends, int64
   const int threads = 256;
   int64_t want = (n_rays * 32 + threads - 1) / threads;
   int blocks = (int)std::min<int64_t>(want, (int64_t)rsn_num_sms() * 16);
+  if (C == 16 && g_feat && tma_form_ok(S, {feat, g_feat_out, g_feat, sigma, g_weights, g_sigma, normals})) {
+    const size_t smem = (size_t)TMA_WARPS * cs_warp_floats(S, true) * sizeof(float);
+    static std::atomic<unsigned long long> done_t[3];
+    const int bpsm = std::max(1, std::min(8, (int)((225 * 1024) / (smem + 1024))));
+    blocks = (int)std::min<int64_t>((n_rays + TMA_WARPS - 1) / TMA_WARPS, (int64_t)rsn_num_sms() * bpsm);
+#define RSN_BWDT(K, I)                                                                                               \
+  do {                                                                                                               \
+    RSN_CUDA(rsn_ensure_smem(composite16_bwd_tma_kernel<K>, (int)(TMA_WARPS * cs_warp_floats(TMA_MAX_SAMPLES, true) * 4), done_t[I])); \
+    composite16_bwd_tma_kernel<K><<<blocks, TMA_WARPS * 32, smem, stream>>>(                                          \
+        sigma, starts, ends, bin_stride, feat, g_weights, g_acc, (const float4*)g_feat_out, g_sigma, (float4*)g_feat, \
+        n_rays, S, normals, g_pnl, g_ol, g_blend, feat_out, acc_in, n_rays_dev);                                     \
+  } while (0)
+    if (S <= 32) RSN_BWDT(1, 0);
+    else if (S <= 64) RSN_BWDT(2, 1);
+    else RSN_BWDT(4, 2);
+#undef RSN_BWDT
+    RSN_LAUNCH_CHECK("composite16_bwd_tma_kernel");
+    return 0;
+  }
   if (C >= 4 && C % 4 == 0 && S <= VEC_MAX_SAMPLES && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)g_feat_out & 15) == 0 &&
       ((uintptr_t)g_feat & 15) == 0) {
     constexpr int Q = C >= 4 ? C / 4 : 1;
