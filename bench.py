@@ -15,7 +15,9 @@ Rays shard across ranks with no data-path collective (weak scaling: 16,384 rays 
 per-step gradient all-reduce of the training workload.
 
 Prints ONE JSON line (rank 0).  `value` = whole-job rays/s with the scene (cameras + uint8 images) resident in HBM;
-`e2e` = the same through the public API with HOST (pinned) ray / pixel buffers, H2D + D2H copies inside the timed region.
+`e2e` = the same through the public API (TrainStep.step(bundle, image): static-buffer copy + CUDA-graph replay at N = 1, eager at
+N > 1) with HOST (pinned) ray / pixel buffers, H2D + D2H copies inside the timed region.  (The resident path generates its rays
+on the GPU inside the step, the e2e path receives them from the host: the two differ by one small kernel vs 655 KB of H2D.)
 `--impl reference` times the oracle restatement of the reference's PyTorch path on the host CPU cores
 (the reference itself cannot be imported: nerfstudio is absent).
 """
@@ -317,7 +319,11 @@ def run_b200(args):
         torch.cuda.profiler.stop()
     ar_events = model.field.__dict__.pop("_allreduce_events", None) or []
     allreduce_ms = (sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events)) if ar_events else None
-    ms_e2e, _, _ = timed("e2e", args.steps, 2)
+    if train and cuda_graph:
+        # the public API's own CUDA-graph form (TrainStep(graph=True)): the host batch is copied into the graph's static
+        # input buffers and the captured step is replayed -- the first step() below captures it
+        stepper.graph_requested, stepper.steps_done = True, 3
+    ms_e2e, _, _ = timed("e2e", args.steps, 3)
 
     # roofline: every field kernel from its own CUDA-event launch durations; `roofline` = the one with the largest
     # share of the step (tensor-bound kernels against the sustained cuBLAS bf16 peak, HBM-bound against the copy peak)
@@ -400,7 +406,10 @@ def run_b200(args):
             "masked_rays": {"mean_per_step_rank0": m_mean, "min": min(n_masked) if n_masked else None,
                             "max": max(n_masked) if n_masked else None, "of": n},
             "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                    "api": ("TrainStep.step(bundle, image) on pinned host buffers, CUDA-graph replay" if (train and cuda_graph)
+                            else "TrainStep.step(bundle, image) on pinned host buffers, eager" if train
+                            else "model(bundle) on pinned host buffers + D2H of the two rendered images")},
             "eager": {"ms_per_step": ms_eager, "gpu_launches_per_step": launches_eager / args.steps},
             "gpu_launches": launches if not cuda_graph else launches_eager,
             "gpu_launches_note": ("kernels launched by librsn_b200.so inside the timed region; with cuda_graph they are graph "
