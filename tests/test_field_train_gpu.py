@@ -228,6 +228,51 @@ def test_gradients_against_the_bf16_emulated_autograd_oracle():
         assert abs(r - 1) < 0.005, (name, c, r)  # measured: within 0.25 %
 
 
+def test_stashed_hidden_blocks_and_relu_bit_masks():
+    """The activation stash the stash warps write (csrc/field_fwd.cu, csrc/field_layout.cuh): the hidden activations of the 8
+    base layers and the mid layer as CHUNK-MAJOR bf16 block images, and the ReLU bit masks.  (1) Masks and blocks are
+    consistent bit for bit (bit set <=> stashed value > 0); (2) the blocks are the bf16-emulated oracle's hidden activations
+    (bf16 half-ulp of the value, plus the rounding the inputs of a 256-term fp32 dot product pick up layer by layer)."""
+    from reflect_sampling_nerf_b200.blocks import unpack_blocks_cm
+    n, s = 24, 32                                             # 768 points = 6 tiles
+    field, o, d, pa, bins, g = _setup(n, s, 33, "uniform", 3.2e-6)
+    sd = field.state_dict()
+    wblob, bias = [t.cuda() for t in packing.pack_field(sd)]
+    sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, 0, o.cuda(), d.cuda(), pa.cuda(), bins.cuda())
+    torch.cuda.synchronize()
+    tile_bytes, n_tiles = 41 * 16384 + 36864, (n * s + 127) // 128
+    st = stash.cpu().view(n_tiles, tile_bytes)
+    blocks = st[:, :41 * 16384].reshape(n_tiles, 41, 16384)
+    masks = st[:, 41 * 16384:].contiguous().view(torch.int32).view(n_tiles, 9, 4, 128, 2)      # [tile, layer, group, row, word]
+    hid = unpack_blocks_cm(blocks[:, 2:34].contiguous()).float()[: n * s]                        # h0..h7: [P, 8 * 256]
+    midh = unpack_blocks_cm(blocks[:, 39:41].contiguous()).float()[: n * s]                      # [P, 128]
+    # (1) bit i of word w of (layer, group, row) = column 32 w + 2 i of the group is > 0, bit 16 + i = column 32 w + 2 i + 1
+    def expand(m):                                            # [tiles, groups, 128 rows, 2 words] -> bool [P, groups * 64]
+        bits = ((m[..., None] >> torch.arange(32)) & 1).bool()                   # [..., word, bit]
+        cols = torch.stack([bits[..., :16], bits[..., 16:]], dim=-1)             # [..., word, i, parity] -> column 32 w + 2 i + parity
+        t = cols.reshape(*m.shape[:-1], 64)                                      # [tiles, groups, rows, 64]
+        return t.permute(0, 2, 1, 3).reshape(m.shape[0] * 128, -1)[: n * s]
+    for l in range(8):
+        assert torch.equal(expand(masks[:, l]), hid[:, 256 * l: 256 * (l + 1)] > 0), f"layer {l}"
+    assert torch.equal(expand(masks[:, 8, :2]), midh > 0)
+    # (2) against the bf16-operand emulation of the oracle field
+    ex = lambda x: x[:, None, :].expand(n, s, x.shape[-1])  # noqa: E731
+    mean, cov = R.frustum_gaussian(ex(o), ex(d), bins[:, :-1, None], bins[:, 1:, None], ex(pa))
+    mean, cov = R.contract(mean, cov)
+    prm = dict(field.named_parameters())
+    with torch.no_grad():
+        enc = R.ipe(mean, cov).reshape(n * s, -1)
+        h = enc
+        for l in range(8):
+            if l == 4:
+                h = torch.cat([enc, h], -1)
+            h = F.relu(_bf(h) @ _bf(prm[f"mlp_base.layers.{l}.weight"]).T + prm[f"mlp_base.layers.{l}.bias"])
+            got = hid[:, 256 * l: 256 * (l + 1)]
+            err = (got - h).abs()
+            assert float(err.max()) < 2e-2 * (1.0 + float(h.abs().max())), (l, float(err.max()))
+            assert float(err.mean()) < 2e-3 * (1e-3 + float(h.abs().mean())) + 2e-4, (l, float(err.mean()), float(h.abs().mean()))
+
+
 def test_pixel_area_gradient_against_fp32_and_bf16_emulated_oracles():
     """d loss / d pixel_area of a reflected pass (the roughness -> cone-width path, model.py:272,286): the chain kernel
     continues through layer 0 and the IPE damping using the bf16-stashed encodings.  Per-ray values against (i) fp32
