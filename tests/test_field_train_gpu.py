@@ -273,6 +273,28 @@ def test_stashed_hidden_blocks_and_relu_bit_masks():
             assert float(err.mean()) < 2e-3 * (1e-3 + float(h.abs().mean())) + 2e-4, (l, float(err.mean()), float(h.abs().mean()))
 
 
+@pytest.mark.parametrize("n,s", [(37, 24), (5, 24), (129, 1)])
+def test_stash_writers_stay_inside_their_buffers(n, s):
+    """The stash warps address the chunk-major images themselves (st.global from registers, no TMA bounds): guard zones on
+    both sides of the activation stash and of the dY stash must survive a forward / backward of a ragged last tile."""
+    field, o, d, pa, bins, g = _setup(n, s, 9, "uniform", 3.2e-6)
+    sd = field.state_dict()
+    wblob, bias = [t.cuda() for t in packing.pack_field(sd)]
+    wblob_t, wd = [t.cuda() for t in packing.pack_field_t(sd)]
+    o, d, pa, bins = o.cuda(), d.cuda(), pa.cuda().reshape(-1), bins.cuda()
+    guard = 1 << 20
+    nb, nd = _lib.lib().rsn_field_stash_bytes(n * s), _lib.lib().rsn_field_dy_stash_bytes(n * s)
+    big_s = torch.full((nb + 2 * guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    big_d = torch.full((nd + 2 * guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    sigma, feat, stash, aux = ops.field_forward_train(wblob, bias, 0, o, d, pa, bins, stash=big_s[guard: guard + nb])
+    g_sigma = (torch.randn(n, s, generator=g) * 0.1).cuda()
+    g_feat = (torch.randn(n, s, 16, generator=g) * 0.1).cuda()
+    ops.field_backward(wblob_t, stash, 0, o, d, pa, bins, n, s, g_sigma, g_feat, feat, aux, big_d[guard: guard + nd], True)
+    torch.cuda.synchronize()
+    for big, size in ((big_s, nb), (big_d, nd)):
+        assert bool((big[:guard] == 0xA5).all()) and bool((big[guard + size:] == 0xA5).all())
+
+
 def test_pixel_area_gradient_against_fp32_and_bf16_emulated_oracles():
     """d loss / d pixel_area of a reflected pass (the roughness -> cone-width path, model.py:272,286): the chain kernel
     continues through layer 0 and the IPE damping using the bf16-stashed encodings.  Per-ray values against (i) fp32
