@@ -205,6 +205,22 @@ def _render(field, grad: bool, primary: bool, o, d, area, eu_bins, count=None):
     return feat, normals, w, acc, depth, comp, None, None
 
 
+def _stratification_noise(samplers, n: int, dev):
+    """The four samplers' stratification noise of one step.  Training without injected noise: ONE torch.rand launch whose
+    contiguous chunks the samplers share (instead of one launch per sampler); otherwise each sampler's own noise()."""
+    plain = all(s.train_stratified and s.training and s.injected_rand is None and not getattr(s, "single_jitter", False)
+                for s in samplers)
+    if not plain:
+        return [s.noise(n, dev) for s in samplers]
+    cols = [s.num_samples + 1 for s in samplers]
+    flat = torch.rand(n * sum(cols), device=dev)
+    out, off = [], 0
+    for c in cols:
+        out.append(flat[off: off + n * c].view(n, c))
+        off += n * c
+    return out
+
+
 def get_outputs(model, ray_bundle, grad: bool) -> Dict[str, Tensor]:
     """reflect_sampling_nerf_model.py:142-344.  grad=True: training mode with autograd."""
     field = model.field
@@ -215,10 +231,12 @@ def get_outputs(model, ray_bundle, grad: bool) -> Dict[str, Tensor]:
 
     # A. coarse (model.py:148-177)
     su, sp = model.sampler_uniform, model.sampler_pdf
-    sp_c, eu_c = ops.sample_spaced(nears, fars, su.num_samples, su.kind, su.noise(n, dev))
+    sr, sq = model.sampler_reciprocal, model.sampler_reflect_pdf
+    noise_u, noise_p, noise_r, noise_q = _stratification_noise((su, sp, sr, sq), n, dev)
+    sp_c, eu_c = ops.sample_spaced(nears, fars, su.num_samples, su.kind, noise_u)
     feat_c, nrm_c, w_c, acc_c, depth_c, comp_c, nl_c, rgb_c = _render(field, grad, True, o, d, area, eu_c)
     # B. fine (model.py:182-211)
-    sp_f, eu_f = ops.pdf_resample(w_c.detach(), sp_c, nears, fars, sp.num_samples, sp.kind, rand=sp.noise(n, dev),
+    sp_f, eu_f = ops.pdf_resample(w_c.detach(), sp_c, nears, fars, sp.num_samples, sp.kind, rand=noise_p,
                                   train=training)
     feat_f, nrm_f, w_f, acc_f, depth_f, comp_f, nl_f, rgb_f = _render(field, grad, True, o, d, area, eu_f)
     # C. per-ray quantities of the bounce (model.py:215-229): everything detached except the roughness (one kernel),
@@ -254,14 +272,13 @@ def get_outputs(model, ray_bundle, grad: bool) -> Dict[str, Tensor]:
     else:
         bg = field.get_inf_color(w_r, sqr, count)
     # E. reflected coarse (model.py:292-313)
-    sr, sq = model.sampler_reciprocal, model.sampler_reflect_pdf
-    sp_rc, eu_rc = ops.sample_spaced(nears2, fars2, sr.num_samples, sr.kind, sr.noise(n, dev), count)
+    sp_rc, eu_rc = ops.sample_spaced(nears2, fars2, sr.num_samples, sr.kind, noise_r, count)
     _, _, w_rc, acc_rc, _, comp_rc, _, _ = _render(field, grad, False, o2, w_r, area2, eu_rc, count)
     outputs["mid_reflect_coarse"], _ = ops.reflect_compose(acc_f, diff_r, tint_r, inv, comp_rc, bg, acc_rc.detach(),
                                                            None, clamp_inner=not training)
     # F. reflected fine (model.py:317-341)
     sp_rf, eu_rf = ops.pdf_resample(w_rc.detach(), sp_rc, nears2, fars2, sq.num_samples, sq.kind,
-                                    rand=sq.noise(n, dev), train=training, count=count)
+                                    rand=noise_q, train=training, count=count)
     _, _, w_rf, acc_rf, depth_rf, comp_rf, _, _ = _render(field, grad, False, o2, w_r, area2, eu_rf, count)
     outputs["mid_reflect_fine"], depth_pad = ops.reflect_compose(acc_f, diff_r, tint_r, inv, comp_rf, bg,
                                                                  acc_rf.detach(), depth_rf, clamp_inner=not training)
