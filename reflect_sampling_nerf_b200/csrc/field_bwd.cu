@@ -12,14 +12,16 @@
 //       model.py:272,286,290).
 //
 // Same machinery as the forward (csrc/field_fwd.cu): persistent CTA per SM, one tile in flight; warp 0
-// streams the TRANSPOSED weight blob (B[n = input feature][k = output feature]) through a 3 x 32 KB ring,
-// warp 6 streams the forward's stashed activation blocks (ReLU masks, and the encoding values the IPE
-// Jacobian needs) through a 3 x 16 KB ring, warp 1 issues tcgen05.mma into two alternating 256-column TMEM
-// accumulators, warps 2-5 run the per-row epilogues: dX = acc * (h > 0) -> bf16 -> the next step's A
-// operand, published per 64-column group -- by default written back into TMEM (tcgen05.st; the next MMA takes its A
-// operand from there), with RSN_BWD_TS=0 in place into the shared-memory activation blocks.  The ReLU masks arrive as the
-// forward's bit masks (8 bytes per row, layer and group, prefetched into registers), only the two stashed encoding blocks
-// go through the second ring.
+// streams the TRANSPOSED weight blob (B[n = input feature][k = output feature]) through a 5 x 32 KB ring,
+// warp 6 streams the two stashed encoding blocks the IPE Jacobian needs through a 2 x 16 KB ring, warp 1 issues
+// tcgen05.mma into two alternating 256-column TMEM accumulators, warps 2-5 run the per-row epilogues:
+// dX = acc * (h > 0) -> bf16 -> the next step's A operand, published per 64-column group and written back into TMEM
+// (tcgen05.st; the next MMA takes its A operand from there).  The ReLU masks arrive as the forward's bit masks (8 bytes
+// per row, layer and group, prefetched into registers).  BACKWARD launches four more warps (7-10) that read every
+// handed-over dY group back out of TMEM and write it to the dY stash with coalesced st.global (chunk-major block image,
+// csrc/field_layout.cuh): the stash is not on the step-critical path, and the issuer re-uses an accumulator buffer only
+// after they have released it.  The test build keeps the shared-memory operand form (RSN_BWD_TS=0; its epilogue writes
+// the stash rows itself), pinned bit-identical by tests.
 //
 // Roofline: bf16 tensor.  Algorithmic FLOPs per point: NORMALS 1,019,392; BACKWARD dgrad 1,179,904 primary,
 // 1,229,056 reflected.  HBM: masks 288 B/pt (+ encodings 256 B/pt) in, dY 4.4 KB/pt out (dY of the

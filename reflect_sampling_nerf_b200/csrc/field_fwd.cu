@@ -10,9 +10,9 @@
 //   IntegratedSHEncoding                              reflect_sampling_nerf_components.py:52-140
 //   call sites                                        reflect_sampling_nerf_model.py:151-175,185-209,290,293-310,319-336
 //
-// One persistent CTA per SM, 10 warps, one 128-point tile in flight per CTA:
+// One persistent CTA per SM, 10 warps (14 in training), one 128-point tile in flight per CTA:
 //   warp 0      weight producer: streams the pre-packed bf16 weight blob (L2 resident, 1.27 MB) through a ring of
-//               32 KB shared-memory stages (3; 5 when no stash is written) with cp.async.bulk + mbarrier complete_tx
+//               5 x 32 KB shared-memory stages with cp.async.bulk + mbarrier complete_tx
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M128, N<=256, K16, bf16 -> fp32 in TMEM) and requests each
 //               wide layer's fp32 bias into a two-slot shared-memory buffer two layers ahead
 //   warps 6-9   epilogue: tcgen05.ld the accumulator row of "their" point, bias + ReLU, bf16, and hand the row to the next
@@ -29,7 +29,8 @@
 // soon as that group is written: MMA of layer l+1 overlaps the epilogue of layer l.
 //
 // Roofline: bf16 tensor.  Algorithmic FLOPs per point: 1,230,592 (primary),
-// 1,229,056 (reflected), 1,225,472 (infinity colour).  HBM: 24 B/ray + 8 B/sample in, 68 B/point out.
+// 1,229,056 (reflected), 1,225,472 (infinity colour).  HBM: 24 B/ray + 8 B/sample in, 68 B/point out (+ 5,024 B/point of
+// stash in training).
 #include "rsn_common.cuh"
 #include "umma.cuh"
 #include "field_layout.cuh"
@@ -712,7 +713,7 @@ __global__ void __launch_bounds__(TRAIN ? NUM_THREADS_TRAIN : NUM_THREADS, 1) fi
         if (TS) tmem_st_wait(); else fence_proxy_async();
         tc_fence_before();
         arrive_issuer(&bars.act_ready[buf * 4 + g]);
-        RSN_TRACE((p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0, 2100 + 10 * (jw - 1) + g);
+        RSN_TRACE((p.debug & 32) && blockIdx.x == 0 && it == 2 && warp == 6 && lane == 0, 2100 + 10 * ((jw - 1) % WIDE_LAYERS) + g);
       };
       using T_ = std::integral_constant<bool, true>;
       using F_ = std::integral_constant<bool, false>;

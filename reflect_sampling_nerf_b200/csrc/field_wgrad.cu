@@ -6,8 +6,10 @@
 //   field_output_mid            reflect_sampling_nerf_field.py:54-86 (forward at field.py:132-186)
 //
 // Operands are the block images the forward (X, csrc/field_fwd.cu stash) and the dgrad chain (dY,
-// csrc/field_bwd.cu) left in HBM: [128 points][64 features] bf16, 128-byte swizzled.  Read "transposed"
-// (MN-major UMMA descriptors, features contiguous) they are directly the A = dY^T and B = X operands of
+// csrc/field_bwd.cu) left in HBM: [128 points][64 features] bf16 -- chunk-major images for everything the epilogues
+// wrote (hidden activations, every dY block), 128-byte swizzled shared-memory images for the IPE / IDE encodings
+// (csrc/field_layout.cuh).  Read "transposed" (MN-major UMMA descriptors, features contiguous: no-swizzle descriptors
+// for the chunk-major blocks, SWIZZLE_128B ones for the encodings) they are directly the A = dY^T and B = X operands of
 //   D[out, in] (+)= sum over 16 points  dY[pt, out] * X[pt, in]            (tcgen05.mma, fp32 in TMEM)
 // One CTA owns one job = (layer, all <=256 output features, <=256 input features) and a contiguous range of
 // tiles (split-K over points); its accumulators stay in TMEM for the whole range and are flushed once with
