@@ -62,10 +62,144 @@ __global__ void __launch_bounds__(256) sample_spaced_kernel(
   }
 }
 
+// The same per (bin, ray) arithmetic with one THREAD PER BIN COLUMN walking `rays_per_block` rays: everything that depends
+// on the bin only (lin[i], the stratification interval) is computed once per thread, no index division at all, and a
+// warp's accesses to a row are contiguous.  Used whenever a row fits a block (n_bins <= 1024).
+__global__ void __launch_bounds__(1024) sample_spaced_rows_kernel(
+    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ lin,
+    const float* __restrict__ t_rand, int64_t t_rand_cols, Spacing kind, float* __restrict__ spacing,
+    float* __restrict__ euclid, int64_t n_rays, int n_bins, int rays_per_block, const int* __restrict__ n_rays_dev) {
+  const int i = threadIdx.x;
+  if (i >= n_bins) return;
+  const int64_t n_valid = rsn_count(n_rays, n_rays_dev);
+  const int64_t r0 = (int64_t)blockIdx.x * rays_per_block;
+  const int64_t r1 = r0 + rays_per_block < n_valid ? r0 + rays_per_block : n_valid;
+  const float b0 = __ldg(lin + i);
+  float lower = b0, width = 0.f;
+  if (t_rand != nullptr) {
+    lower = i == 0 ? b0 : __fmul_rn(__fadd_rn(b0, __ldg(lin + i - 1)), 0.5f);
+    const float upper = i == n_bins - 1 ? b0 : __fmul_rn(__fadd_rn(__ldg(lin + i + 1), b0), 0.5f);
+    width = __fsub_rn(upper, lower);
+  }
+  const int64_t tcol = t_rand_cols == 1 ? 0 : i;
+#pragma unroll 4
+  for (int64_t r = r0; r < r1; ++r) {
+    float b = b0;
+    if (t_rand != nullptr) b = __fadd_rn(lower, __fmul_rn(width, __ldg(t_rand + r * t_rand_cols + tcol)));
+    const float s_near = spacing_fn(__ldg(nears + r), kind);
+    const float s_far = spacing_fn(__ldg(fars + r), kind);
+    spacing[r * n_bins + i] = b;
+    euclid[r * n_bins + i] = to_euclid(b, s_near, s_far, kind);
+  }
+}
+
 // One warp per ray.  smem per warp: cdf[S+1], the existing spacing bins[S+1] and the ray's weights (+ histogram padding),
 // staged with coalesced loads (lane-strided) and read back by the lane that owns the sample's chunk; the staging row is
 // skewed by one word per 32 so that the chunked reads (lane stride = chunk words) hit distinct banks.  The arithmetic
 // and its order are unchanged (fp64 partial sums per lane-chunk, xor-tree, fp64 scan), so the bins stay bit-exact.
+// searchsorted(cdf[0..S], u, side="right") = number of entries <= u, as a fixed-trip-count, branch-free descent (the CDF is
+// non-decreasing: a cumulative sum of non-negative terms, clamped at 1) -- the same index the bisection loop finds
+template <int MAXSTEP>
+__device__ __forceinline__ int count_le(const float* cdf, int n, float u) {
+  int pos = 0;
+#pragma unroll
+  for (int step = MAXSTEP; step >= 1; step >>= 1) {
+    const int nxt = pos + step;
+    if (nxt <= n && cdf[nxt - 1] <= u) pos = nxt;
+  }
+  return pos;
+}
+
+// CHUNK = ceil(S / 32) known at compile time (S <= 256): every per-sample loop is unrolled and predicated, the PDF value of
+// a sample is divided once and kept in a register between the sum and the CDF pass, the search is branch-free.  Same
+// arithmetic in the same order as the generic kernel below (ncu of the generic form: 1,370 warp instructions per ray, 68 %
+// issue-active, two thirds of them loop and address bookkeeping).
+template <int WARPS, int CHUNK>
+__global__ void __launch_bounds__(WARPS * 32) pdf_resample_chunk_kernel(
+    const float* __restrict__ weights, int64_t w_stride, const float* __restrict__ bins_in,
+    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ u_base,
+    const float* __restrict__ rand, Spacing kind, float hist_pad, float* __restrict__ spacing_out,
+    float* __restrict__ euclid_out, int64_t* __restrict__ inds_out, int64_t n_rays, int S, int nb,
+    const int* __restrict__ n_rays_dev) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_words = 2 * (S + 1) + S + (S >> 5) + 1;
+  float* cdf = smem + (size_t)warp * row_words;
+  float* ebins = cdf + (S + 1);
+  float* wp = ebins + (S + 1);      // wp[i + (i >> 5)] = weights[i] + histogram_padding
+  const int chunk = (S + 31) / 32;  // consecutive samples per lane (<= CHUNK)
+  const int64_t n_valid = rsn_count(n_rays, n_rays_dev);
+  constexpr int MAXSTEP = CHUNK <= 1 ? 32 : CHUNK <= 3 ? 64 : CHUNK <= 7 ? 128 : 256;   // largest power of two <= 32 CHUNK + 1
+
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < n_valid; r += (int64_t)gridDim.x * WARPS) {
+    const float* w = weights + r * w_stride;
+    const int lo = lane * chunk;
+#pragma unroll
+    for (int it = 0; it < CHUNK; ++it) {
+      const int i = lane + 32 * it;
+      if (i < S) wp[i + (i >> 5)] = __fadd_rn(__ldg(w + i), hist_pad);
+    }
+#pragma unroll
+    for (int it = 0; it <= CHUNK; ++it) {
+      const int i = lane + 32 * it;
+      if (i <= S) ebins[i] = __ldg(bins_in + r * (S + 1) + i);
+    }
+    __syncwarp();
+    float wv[CHUNK];
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < CHUNK; ++k) {
+      const int i = lo + k;
+      const bool ok = k < chunk && i < S;
+      wv[k] = ok ? wp[i + (i >> 5)] : 0.f;
+      if (ok) part += (double)wv[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(RSN_FULL, part, o);
+    float wsum = (float)part;
+    const float padding = fmaxf(__fsub_rn(1e-5f, wsum), 0.0f);  // relu(eps - sum)
+    const float pad_each = __fdiv_rn(padding, (float)S);
+    wsum = __fadd_rn(wsum, padding);
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < CHUNK; ++k) {
+      const bool ok = k < chunk && lo + k < S;
+      wv[k] = ok ? __fdiv_rn(__fadd_rn(wv[k], pad_each), wsum) : 0.f;    // the PDF value, divided once
+      if (ok) run += (double)wv[k];
+    }
+    const double incl = warp_incl_scan(run, lane);
+    double acc = incl - run;  // exclusive offset of this lane's chunk
+#pragma unroll
+    for (int k = 0; k < CHUNK; ++k) {
+      const int i = lo + k;
+      if (k < chunk && i < S) {
+        acc += (double)wv[k];
+        cdf[i + 1] = fminf(1.0f, (float)acc);
+      }
+    }
+    if (lane == 0) cdf[0] = 0.0f;
+    __syncwarp();
+
+    const float s_near = spacing_fn(__ldg(nears + r), kind);
+    const float s_far = spacing_fn(__ldg(fars + r), kind);
+    const float nbf = (float)nb;
+    for (int j = lane; j < nb; j += 32) {
+      float u = __ldg(u_base + j);
+      if (rand != nullptr) u = __fadd_rn(u, __fdiv_rn(__ldg(rand + r * nb + j), nbf));
+      const int a = count_le<MAXSTEP>(cdf, S + 1, u);
+      const int below = min(max(a - 1, 0), S), above = min(a, S);
+      const float c0 = cdf[below], c1 = cdf[above], b0 = ebins[below], b1 = ebins[above];
+      float t = nan_to_num(__fdiv_rn(__fsub_rn(u, c0), __fsub_rn(c1, c0)));
+      t = fminf(fmaxf(t, 0.0f), 1.0f);
+      const float nbv = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+      spacing_out[r * nb + j] = nbv;
+      euclid_out[r * nb + j] = to_euclid(nbv, s_near, s_far, kind);
+      if (inds_out != nullptr) inds_out[r * nb + j] = a;
+    }
+    __syncwarp();
+  }
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) pdf_resample_kernel(
     const float* __restrict__ weights, int64_t w_stride, const float* __restrict__ bins_in,
@@ -154,7 +288,12 @@ extern "C" int rsn_sample_spaced(const float* nears, const float* fars, const fl
   const int n_bins = (int)n_samples + 1;
   int64_t total = n_rays * n_bins;
   int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)rsn_num_sms() * 8);
-  if (total < (int64_t)2147483647 - (int64_t)blocks * 256)
+  if (n_bins <= 1024) {
+    const int threads = (n_bins + 31) & ~31;
+    const int rpb = 16;
+    sample_spaced_rows_kernel<<<(unsigned)((n_rays + rpb - 1) / rpb), threads, 0, stream>>>(
+        nears, fars, lin_bins, t_rand, t_rand_cols, sp, spacing_bins, euclid_bins, n_rays, n_bins, rpb, n_rays_dev);
+  } else if (total < (int64_t)2147483647 - (int64_t)blocks * 256)
     sample_spaced_kernel<unsigned><<<blocks, 256, 0, stream>>>(nears, fars, lin_bins, t_rand, t_rand_cols, sp, spacing_bins,
                                                                euclid_bins, n_rays, n_bins, n_rays_dev);
   else
@@ -182,9 +321,20 @@ extern "C" int rsn_pdf_resample(const float* weights, int64_t weights_row_stride
   static std::atomic<unsigned long long> done;   // sized for the 4096-sample maximum, set once per device
   RSN_CUDA(rsn_ensure_smem(pdf_resample_kernel<WARPS>, (int)(WARPS * (2 * 4097 + 4096 + 129) * sizeof(float)), done));
   int blocks = (int)std::min<int64_t>((n_rays + WARPS - 1) / WARPS, (int64_t)rsn_num_sms() * 16);
-  pdf_resample_kernel<WARPS><<<blocks, WARPS * 32, smem, stream>>>(
-      weights, weights_row_stride, spacing_bins_in, nears, fars, u_base, rand, sp, histogram_padding,
-      spacing_bins_out, euclid_bins_out, inds_out, n_rays, S, nb, n_rays_dev);
+#define RSN_PDF_CHUNK(C)                                                                                      \
+  pdf_resample_chunk_kernel<WARPS, C><<<blocks, WARPS * 32, smem, stream>>>(                                  \
+      weights, weights_row_stride, spacing_bins_in, nears, fars, u_base, rand, sp, histogram_padding,        \
+      spacing_bins_out, euclid_bins_out, inds_out, n_rays, S, nb, n_rays_dev)
+  const int chunk = (S + 31) / 32;
+  if (chunk <= 1) RSN_PDF_CHUNK(1);
+  else if (chunk <= 2) RSN_PDF_CHUNK(2);
+  else if (chunk <= 4) RSN_PDF_CHUNK(4);
+  else if (chunk <= 8) RSN_PDF_CHUNK(8);
+  else
+    pdf_resample_kernel<WARPS><<<blocks, WARPS * 32, smem, stream>>>(
+        weights, weights_row_stride, spacing_bins_in, nears, fars, u_base, rand, sp, histogram_padding,
+        spacing_bins_out, euclid_bins_out, inds_out, n_rays, S, nb, n_rays_dev);
+#undef RSN_PDF_CHUNK
   RSN_LAUNCH_CHECK("pdf_resample_kernel");
   return 0;
 }

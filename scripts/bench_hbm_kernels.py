@@ -41,7 +41,10 @@ def run(n):
     g = torch.Generator(device=dev).manual_seed(0)
     nears, fars = torch.full((n,), 2.0, device=dev), torch.full((n,), 6.0, device=dev)
     rnd = [torch.rand(n, S + 1, device=dev, generator=g) for _ in range(nbuf)]
-    ms = timeit(lambda i: ops.sample_spaced(nears, fars, S, 0, rnd[i]), nbuf)
+    lin = torch.linspace(0, 1, S + 1, device=dev)
+    sp_o, eu_o = torch.empty(n, S + 1, device=dev), torch.empty(n, S + 1, device=dev)
+    ms = timeit(lambda i: _lib.call("rsn_sample_spaced", nears.data_ptr(), fars.data_ptr(), lin.data_ptr(), rnd[i].data_ptr(),
+                                    S + 1, 0, 0.25, sp_o.data_ptr(), eu_o.data_ptr(), n, S, None, _lib.stream()), nbuf)
     report("K1 sample_spaced", n, ms, n * (S + 1) * 12)
     sp, eu = ops.sample_spaced(nears, fars, S, 0, rnd[0])
     sig = [torch.rand(n, S, device=dev, generator=g) * 5 for _ in range(nbuf)]
@@ -49,7 +52,10 @@ def run(n):
     nrm = [torch.nn.functional.normalize(torch.randn(n, S, 3, device=dev, generator=g), dim=-1) for _ in range(nbuf)]
     w0 = ops.composite16(sig[0], eu, feat[0])[0]
     wts = [w0 * (0.5 + 0.1 * i) for i in range(nbuf)]
-    ms = timeit(lambda i: ops.pdf_resample(wts[i], sp, nears, fars, S, 0, rand=rnd[i], train=True), nbuf)
+    u_base = ops._pdf_u_base(S, True, torch.device(dev))
+    ms = timeit(lambda i: _lib.call("rsn_pdf_resample", wts[i].data_ptr(), S, sp.data_ptr(), nears.data_ptr(), fars.data_ptr(),
+                                    u_base.data_ptr(), rnd[i].data_ptr(), 0, 0.25, 0.01, sp_o.data_ptr(), eu_o.data_ptr(), None,
+                                    n, S, S, None, _lib.stream()), nbuf)
     report("K2 pdf_resample", n, ms, n * S * 20)
     # K8 forward / backward, direct calls (the model's form: 16 channels + per-sample normal losses + white blend)
     weights = torch.empty(n, S, device=dev)
