@@ -93,6 +93,54 @@ __global__ void __launch_bounds__(1024) sample_spaced_rows_kernel(
   }
 }
 
+// The flat form: the [N, n_bins] arrays are contiguous, so a thread takes FOUR consecutive flat elements -- one 128-bit
+// load of the noise, two 128-bit stores -- and splits the flat index into (ray, bin) once (32-bit division), stepping the
+// pair for the other three.  Same per-element arithmetic.  Needs 16-byte aligned arrays and fewer than 2^31 bins per pass.
+__global__ void __launch_bounds__(256) sample_spaced_vec4_kernel(
+    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ lin,
+    const float* __restrict__ t_rand, Spacing kind, float* __restrict__ spacing, float* __restrict__ euclid, int64_t n_rays,
+    int n_bins, const int* __restrict__ n_rays_dev) {
+  const unsigned total = (unsigned)(rsn_count(n_rays, n_rays_dev) * n_bins);
+  const unsigned nb = (unsigned)n_bins;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q * 4u < total; q += gridDim.x * blockDim.x) {
+    const unsigned idx = q * 4u;
+    unsigned r = idx / nb, i = idx - r * nb;
+    float t[4] = {0.f, 0.f, 0.f, 0.f}, sp[4], eu[4];
+    const bool full = idx + 4u <= total;
+    if (t_rand != nullptr) {
+      if (full) {
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(t_rand + idx));
+        t[0] = tv.x, t[1] = tv.y, t[2] = tv.z, t[3] = tv.w;
+      } else {
+        for (unsigned k = 0; idx + k < total; ++k) t[k] = __ldg(t_rand + idx + k);
+      }
+    }
+    float s_near = spacing_fn(__ldg(nears + r), kind), s_far = spacing_fn(__ldg(fars + r), kind);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float b = __ldg(lin + i);
+      if (t_rand != nullptr) {
+        const float lower = i == 0 ? b : __fmul_rn(__fadd_rn(b, __ldg(lin + i - 1)), 0.5f);
+        const float upper = i == nb - 1 ? b : __fmul_rn(__fadd_rn(__ldg(lin + i + 1), b), 0.5f);
+        b = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t[k]));
+      }
+      sp[k] = b;
+      eu[k] = to_euclid(b, s_near, s_far, kind);
+      if (++i == nb && k < 3) {   // next ray
+        i = 0;
+        ++r;
+        if (idx + k + 1 < total) s_near = spacing_fn(__ldg(nears + r), kind), s_far = spacing_fn(__ldg(fars + r), kind);
+      }
+    }
+    if (full) {
+      *reinterpret_cast<float4*>(spacing + idx) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+      *reinterpret_cast<float4*>(euclid + idx) = make_float4(eu[0], eu[1], eu[2], eu[3]);
+    } else {
+      for (unsigned k = 0; idx + k < total; ++k) spacing[idx + k] = sp[k], euclid[idx + k] = eu[k];
+    }
+  }
+}
+
 // One warp per ray.  smem per warp: cdf[S+1], the existing spacing bins[S+1] and the ray's weights (+ histogram padding),
 // staged with coalesced loads (lane-strided) and read back by the lane that owns the sample's chunk; the staging row is
 // skewed by one word per 32 so that the chunked reads (lane stride = chunk words) hit distinct banks.  The arithmetic
@@ -288,7 +336,13 @@ extern "C" int rsn_sample_spaced(const float* nears, const float* fars, const fl
   const int n_bins = (int)n_samples + 1;
   int64_t total = n_rays * n_bins;
   int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)rsn_num_sms() * 8);
-  if (n_bins <= 1024) {
+  const bool vec_ok = total < (int64_t)2147483647 - 4096 && (t_rand == nullptr || t_rand_cols == n_bins) &&
+                      (((uintptr_t)t_rand | (uintptr_t)spacing_bins | (uintptr_t)euclid_bins) & 15) == 0;
+  if (vec_ok) {
+    const int64_t quads = (total + 3) / 4;
+    sample_spaced_vec4_kernel<<<(unsigned)std::min<int64_t>((quads + 255) / 256, (int64_t)rsn_num_sms() * 16), 256, 0, stream>>>(
+        nears, fars, lin_bins, t_rand, sp, spacing_bins, euclid_bins, n_rays, n_bins, n_rays_dev);
+  } else if (n_bins <= 1024) {
     const int threads = (n_bins + 31) & ~31;
     const int rpb = 16;
     sample_spaced_rows_kernel<<<(unsigned)((n_rays + rpb - 1) / rpb), threads, 0, stream>>>(
