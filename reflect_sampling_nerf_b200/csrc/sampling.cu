@@ -12,6 +12,9 @@
 #include "rsn_common.cuh"
 #include <algorithm>
 
+#ifndef RSN_PDF_MINB
+#define RSN_PDF_MINB 1
+#endif
 namespace {
 
 // ReciprocalSampler (reflect_sampling_nerf_components.py:30-33): spacing_fn = x / (1/tan + x), inverse = x / tan / (1 - x);
@@ -162,26 +165,42 @@ __device__ __forceinline__ int count_le(const float* cdf, int n, float u) {
 // a sample is divided once and kept in a register between the sum and the CDF pass, the search is branch-free.  Same
 // arithmetic in the same order as the generic kernel below (ncu of the generic form: 1,370 warp instructions per ray, 68 %
 // issue-active, two thirds of them loop and address bookkeeping).
-template <int WARPS, int CHUNK>
-__global__ void __launch_bounds__(WARPS * 32) pdf_resample_chunk_kernel(
+// S_T > 0: additionally specialised on the sample count itself (the model's S = 128 and 64 with S + 1 output bins): every
+// predicate of the unrolled loops folds away.
+template <int WARPS, int CHUNK, int S_T>
+__global__ void __launch_bounds__(WARPS * 32, RSN_PDF_MINB) pdf_resample_chunk_kernel(
     const float* __restrict__ weights, int64_t w_stride, const float* __restrict__ bins_in,
     const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ u_base,
     const float* __restrict__ rand, Spacing kind, float hist_pad, float* __restrict__ spacing_out,
-    float* __restrict__ euclid_out, int64_t* __restrict__ inds_out, int64_t n_rays, int S, int nb,
+    float* __restrict__ euclid_out, int64_t* __restrict__ inds_out, int64_t n_rays, int S_rt, int nb_rt,
     const int* __restrict__ n_rays_dev) {
+  const int S = S_T ? S_T : S_rt, nb = S_T ? S_T + 1 : nb_rt;
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_words = 2 * (S + 1) + S + (S >> 5) + 1;
+  constexpr int OUT = CHUNK + 1;    // consecutive outputs per lane in the fast output phase (needs nb <= 32 OUT)
+  const bool fast_out = nb <= 32 * OUT;
+  const int row_words = 2 * (S + 1) + S + (S >> 5) + 1 + (fast_out ? 3 * nb : 0);
   float* cdf = smem + (size_t)warp * row_words;
   float* ebins = cdf + (S + 1);
   float* wp = ebins + (S + 1);      // wp[i + (i >> 5)] = weights[i] + histogram_padding
+  float* rnd_s = wp + S + (S >> 5) + 1;   // fast output phase: the ray's noise, then its two output rows
+  float* out_s = rnd_s + nb;
   const int chunk = (S + 31) / 32;  // consecutive samples per lane (<= CHUNK)
   const int64_t n_valid = rsn_count(n_rays, n_rays_dev);
   constexpr int MAXSTEP = CHUNK <= 1 ? 32 : CHUNK <= 3 ? 64 : CHUNK <= 7 ? 128 : 256;   // largest power of two <= 32 CHUNK + 1
+  // u_base of this lane's outputs (the same for every ray)
+  float ub[OUT];
+#pragma unroll
+  for (int k = 0; k < OUT; ++k) ub[k] = (fast_out && lane * OUT + k < nb) ? __ldg(u_base + lane * OUT + k) : 0.f;
 
   for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < n_valid; r += (int64_t)gridDim.x * WARPS) {
     const float* w = weights + r * w_stride;
     const int lo = lane * chunk;
+    float rr[OUT];   // the ray's noise, loaded coalesced now and staged for the per-lane consecutive outputs after the CDF
+    if (fast_out && rand != nullptr) {
+#pragma unroll
+      for (int k = 0; k < OUT; ++k) rr[k] = (lane + 32 * k < nb) ? __ldg(rand + r * nb + lane + 32 * k) : 0.f;
+    }
 #pragma unroll
     for (int it = 0; it < CHUNK; ++it) {
       const int i = lane + 32 * it;
@@ -226,11 +245,55 @@ __global__ void __launch_bounds__(WARPS * 32) pdf_resample_chunk_kernel(
       }
     }
     if (lane == 0) cdf[0] = 0.0f;
+    if (fast_out && rand != nullptr) {
+#pragma unroll
+      for (int k = 0; k < OUT; ++k)
+        if (lane + 32 * k < nb) rnd_s[lane + 32 * k] = rr[k];
+    }
     __syncwarp();
 
     const float s_near = spacing_fn(__ldg(nears + r), kind);
     const float s_far = spacing_fn(__ldg(fars + r), kind);
     const float nbf = (float)nb;
+    if (fast_out) {
+      // Lane l owns the OUT consecutive outputs j = l OUT + k.  Their u are (almost always) non-decreasing, so only the first
+      // index is searched; the following ones advance from their predecessor (a fresh search if a u steps back by an ulp).
+      int a = 0;
+      float u_prev = 0.f;
+#pragma unroll
+      for (int k = 0; k < OUT; ++k) {
+        const int j = lane * OUT + k;
+        if (j < nb) {
+          float u = ub[k];
+          if (rand != nullptr) u = __fadd_rn(u, __fdiv_rn(rnd_s[j], nbf));
+          if (k == 0 || u < u_prev) {
+            a = count_le<MAXSTEP>(cdf, S + 1, u);
+          } else {
+            while (a <= S && cdf[a] <= u) ++a;
+          }
+          u_prev = u;
+          const int below = min(max(a - 1, 0), S), above = min(a, S);
+          const float c0 = cdf[below], c1 = cdf[above], b0 = ebins[below], b1 = ebins[above];
+          float t = nan_to_num(__fdiv_rn(__fsub_rn(u, c0), __fsub_rn(c1, c0)));
+          t = fminf(fmaxf(t, 0.0f), 1.0f);
+          const float nbv = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+          out_s[j] = nbv;
+          out_s[nb + j] = to_euclid(nbv, s_near, s_far, kind);
+          if (inds_out != nullptr) inds_out[r * nb + j] = a;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < OUT; ++k) {   // coalesced write-out
+        const int j = lane + 32 * k;
+        if (j < nb) {
+          spacing_out[r * nb + j] = out_s[j];
+          euclid_out[r * nb + j] = out_s[nb + j];
+        }
+      }
+      __syncwarp();
+      continue;
+    }
     for (int j = lane; j < nb; j += 32) {
       float u = __ldg(u_base + j);
       if (rand != nullptr) u = __fadd_rn(u, __fdiv_rn(__ldg(rand + r * nb + j), nbf));
@@ -371,19 +434,24 @@ extern "C" int rsn_pdf_resample(const float* weights, int64_t weights_row_stride
           "rsn_pdf_resample: null pointer");
   constexpr int WARPS = 4;
   const int S = (int)n_in_samples, nb = (int)n_out_samples + 1;
-  size_t smem = (size_t)WARPS * (2 * (S + 1) + S + (S >> 5) + 1) * sizeof(float);
+  // (+ 3 nb floats per warp when the specialised kernel's fast output phase applies: nb <= 32 (ceil(S / 32) + 1))
+  const int chunk_t = (S + 31) / 32 <= 1 ? 1 : (S + 31) / 32 <= 2 ? 2 : (S + 31) / 32 <= 4 ? 4 : 8;
+  const bool fast_out = (S + 31) / 32 <= 8 && nb <= 32 * (chunk_t + 1);
+  size_t smem = (size_t)WARPS * (2 * (S + 1) + S + (S >> 5) + 1 + (fast_out ? 3 * nb : 0)) * sizeof(float);
   static std::atomic<unsigned long long> done;   // sized for the 4096-sample maximum, set once per device
   RSN_CUDA(rsn_ensure_smem(pdf_resample_kernel<WARPS>, (int)(WARPS * (2 * 4097 + 4096 + 129) * sizeof(float)), done));
   int blocks = (int)std::min<int64_t>((n_rays + WARPS - 1) / WARPS, (int64_t)rsn_num_sms() * 16);
-#define RSN_PDF_CHUNK(C)                                                                                      \
-  pdf_resample_chunk_kernel<WARPS, C><<<blocks, WARPS * 32, smem, stream>>>(                                  \
+#define RSN_PDF_CHUNK(C, ST)                                                                                  \
+  pdf_resample_chunk_kernel<WARPS, C, ST><<<blocks, WARPS * 32, smem, stream>>>(                              \
       weights, weights_row_stride, spacing_bins_in, nears, fars, u_base, rand, sp, histogram_padding,        \
       spacing_bins_out, euclid_bins_out, inds_out, n_rays, S, nb, n_rays_dev)
   const int chunk = (S + 31) / 32;
-  if (chunk <= 1) RSN_PDF_CHUNK(1);
-  else if (chunk <= 2) RSN_PDF_CHUNK(2);
-  else if (chunk <= 4) RSN_PDF_CHUNK(4);
-  else if (chunk <= 8) RSN_PDF_CHUNK(8);
+  if (S == 128 && nb == 129) RSN_PDF_CHUNK(4, 128);       // the model's primary passes
+  else if (S == 64 && nb == 65) RSN_PDF_CHUNK(2, 64);     // ... and its bounce passes
+  else if (chunk <= 1) RSN_PDF_CHUNK(1, 0);
+  else if (chunk <= 2) RSN_PDF_CHUNK(2, 0);
+  else if (chunk <= 4) RSN_PDF_CHUNK(4, 0);
+  else if (chunk <= 8) RSN_PDF_CHUNK(8, 0);
   else
     pdf_resample_kernel<WARPS><<<blocks, WARPS * 32, smem, stream>>>(
         weights, weights_row_stride, spacing_bins_in, nears, fars, u_base, rand, sp, histogram_padding,
