@@ -41,6 +41,18 @@ CFG = dict(num_coarse_samples=128, num_importance_samples=128,
 RAYS_PER_GPU = 16384
 SCENE = dict(n_views=100, resolution=400)     # BASELINE.json configs[1]: shiny sphere, 400x400, 100 views
 FLOP_PRIMARY, FLOP_REFLECT, FLOP_INF = 1230592, 1229056, 1225472   # forward, per point
+# dram__bytes_read.sum + dram__bytes_write.sum per work unit (point / sample), from ONE `ncu --set full` capture of each kernel
+# at C2 primary-pass size (profiles/r02_field_all_v1_ncu.txt: 2,097,152 points; profiles/r02_composite16_*_ncu.txt: 65,536 x
+# 128 samples).  `roofline.traffic` = this figure x the units the timed launches actually processed, per launch.
+NCU_DRAM_BYTES_PER_UNIT = {
+    "field_fwd_kernel": (0.010343e9 + 0.084744e9) / 2097152,
+    "field_fwd_kernel[train]": (0.080746e9 + 10.652934e9) / 2097152,
+    "field_chain_kernel<normals>": (1.075013e9 + 0.029699e9) / 2097152,
+    "field_chain_kernel<backward>": (0.956941e9 + 9.354154e9) / 2097152,
+    "field_wgrad_kernel": (20.880054e9 + 0.006595e9) / 2097152,
+    "composite_fwd_kernel": (704.934656e6 + 37.376512e6) / (65536 * 128),
+    "composite_bwd_kernel": (749.599744e6 + 522.126336e6) / (65536 * 128),
+}
 
 
 def scene_batch_cpu(n: int, seed: int, n_views: int = 8, resolution: int = 100):
@@ -349,8 +361,11 @@ def run_b200(args):
                              "unit": "GB/s" if hbm_bound else "TFLOP/s",
                              "frac": (gb / bw_peak) if hbm_bound else (tf / tf_peak),
                              "tflops": tf, "gbs": gb,
-                             # dram__bytes per launch is NOT measured by this script (it needs ncu): see profiles/r02_*_ncu.txt
-                             "traffic": None,
+                             # measured DRAM bytes per launch: the per-unit figure of one ncu capture (NCU_DRAM_BYTES_PER_UNIT) x
+                             # the units these launches processed; None for kernels without a capture
+                             "traffic": (NCU_DRAM_BYTES_PER_UNIT[name] * (nbytes / ops.KERNEL_WORK[name][1]) / cnt
+                                         if name in NCU_DRAM_BYTES_PER_UNIT else None),
+                             "algorithmic_bytes": nbytes / cnt,
                              "launches": cnt, "avg_launch_ms": ms / cnt, "share_of_step": ms / (ms_eager * args.steps)})
         roof_all.sort(key=lambda r: -r["share_of_step"])
         roof = dict(roof_all[0], peak_source=src,
