@@ -197,7 +197,7 @@ def run_b200(args):
     with torch.no_grad():
         hb, hbatch = dm.next_train(0)
         host = [t.cpu().pin_memory() for t in (hb.origins, hb.directions, hb.pixel_area, hbatch["image"])]
-    use_graph = train and (args.graph == "on" or (args.graph == "auto" and world == 1))
+    use_graph = train and args.graph in ("on", "auto")
     stepper = None
     if train:
         from reflect_sampling_nerf_b200.train_path import TrainStep
@@ -251,10 +251,27 @@ def run_b200(args):
             one_step(False)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        if world == 1:
+            with torch.cuda.graph(g):
+                bundle, batch = dm.next_train(0)
+                graph_state["loss"] = stepper._eager(bundle, batch["image"])
+            graph_state["replay"] = g.replay
+            return g
+        # N > 1: two graphs around the step's one collective (NCCL stays outside the captures), as TrainStep(graph=True)
+        from reflect_sampling_nerf_b200.train_path import _allreduce_blob
         with torch.cuda.graph(g):
             bundle, batch = dm.next_train(0)
-            graph_state["loss"] = stepper._eager(bundle, batch["image"])
-        graph_state["launches_per_replay"] = None
+            graph_state["loss"] = stepper._forward_backward_tape(bundle, batch["image"], flush=False)
+        blob = model.field._grad_blob
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, pool=g.pool()):
+            stepper.finish_step()
+
+        def replay():
+            g.replay()
+            _allreduce_blob(model.field, blob)
+            g2.replay()
+        graph_state["replay"], graph_state["g2"] = replay, g2
         return g
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
@@ -263,7 +280,7 @@ def run_b200(args):
     def timed(mode: str, steps: int, warmup: int):
         """mode: 'graph' (replay), 'eager' (resident data, PROFILE events on), 'e2e' (host buffers)."""
         e2e = mode == "e2e"
-        run = (lambda: graph_state["g"].replay()) if mode == "graph" else (lambda: one_step(e2e))
+        run = graph_state["replay"] if mode == "graph" else (lambda: one_step(e2e))
         for _ in range(warmup):
             run()
         torch.cuda.synchronize()
@@ -271,7 +288,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
         ops.PROFILE = [] if mode == "eager" else None
-        if mode == "eager" and world > 1:
+        if mode in ("eager", "graph") and world > 1:
             model.field.__dict__["_allreduce_events"] = []
         counters["launches"] = 0
         evs = []
@@ -316,6 +333,8 @@ def run_b200(args):
         sampler.start()
     ms_step, launches, _ = timed("graph" if cuda_graph else "eager", args.steps, args.warmup)
     step_ms = [round(x, 2) for x in timed.last_per_step]
+    ar_main = model.field.__dict__.get("_allreduce_events") or []      # the timed steps' own all-reduce (N > 1)
+    allreduce_ms_timed = (sum(a.elapsed_time(b) for a, b in ar_main) / len(ar_main)) if ar_main else None
     per_rank_ms = [round(x, 3) for x in timed.per_rank]
     if sampler:
         sampler.stop_flag.set()
@@ -416,7 +435,8 @@ def run_b200(args):
                                    f"bouncing ray, random-init field", "rays_per_gpu": n, **CFG,
                        "l2": "256 MB buffer written between timed iterations; per-pass field outputs (134 MB) exceed L2",
                        "parallelism": f"dp{world} (rays sharded, no data-path collective)",
-                       "cuda_graph": cuda_graph},
+                       "cuda_graph": (cuda_graph if world == 1 or not cuda_graph else
+                                      "two graphs per step around the eager NCCL all-reduce of the gradient blob")},
             "field_samples_per_sec": samples_per_step * world / (ms_step * 1e-3),
             "masked_rays": {"mean_per_step_rank0": m_mean, "min": min(n_masked) if n_masked else None,
                             "max": max(n_masked) if n_masked else None, "of": n},
@@ -429,7 +449,7 @@ def run_b200(args):
             "gpu_launches": launches if not cuda_graph else launches_eager,
             "gpu_launches_note": ("kernels launched by librsn_b200.so inside the timed region; with cuda_graph they are graph "
                                   "nodes replayed by one cudaGraphLaunch per step, counted from the eager pass of the same steps"),
-            "step_ms_rank0": step_ms, "per_rank_step_ms": per_rank_ms, "allreduce_ms": allreduce_ms,
+            "step_ms_rank0": step_ms, "per_rank_step_ms": per_rank_ms, "allreduce_ms": allreduce_ms_timed if allreduce_ms_timed is not None else allreduce_ms,
             "clocks": sampler.summary() if sampler else None, "roofline": roof, "roofline_all": roof_all,
             "cpu_baseline": cpu_base, "cuda_baseline": cuda_base,
         }

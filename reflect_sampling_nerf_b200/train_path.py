@@ -27,21 +27,31 @@ from . import _lib, ops, packing
 
 
 # ----------------------------------------------------------------------------------------- gradient flush
-def _flush_grads(field) -> None:
-    """Engine callback at the end of backward: (all-reduce and) unpack the gradient blob into .grad."""
+def _allreduce_blob(field, blob) -> None:
+    """Data parallelism: the ONE collective of a step -- mean of the gradient blob over the ranks (DDP averages,
+    reflect_sampling_nerf_pipeline.py:73-77)."""
+    timing = field.__dict__.get("_allreduce_events")
+    if timing is not None and blob.is_cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    if blob.is_cuda and dist.get_backend() == "nccl":
+        dist.all_reduce(blob, op=dist.ReduceOp.AVG)       # (NCCL averages inside the collective: no scaling launch)
+    else:
+        dist.all_reduce(blob, op=dist.ReduceOp.SUM)
+        blob.mul_(1.0 / field.dp_world_size)
+    if timing is not None and blob.is_cuda:
+        e1.record()
+        timing.append((e0, e1))
+
+
+def _flush_grads(field, allreduce: bool = True) -> None:
+    """Engine callback at the end of backward: (all-reduce and) unpack the gradient blob into .grad.
+    allreduce=False: the caller has already reduced the blob (TrainStep's split CUDA graphs)."""
     blob, field._grad_blob = field._grad_blob, None
     if blob is None:
         return
-    if field.dp_world_size > 1:
-        timing = field.__dict__.get("_allreduce_events")
-        if timing is not None and blob.is_cuda:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        dist.all_reduce(blob, op=dist.ReduceOp.SUM)
-        if timing is not None and blob.is_cuda:
-            e1.record()
-            timing.append((e0, e1))
-        blob.mul_(1.0 / field.dp_world_size)          # DDP averages (pipeline.py:75)
+    if field.dp_world_size > 1 and allreduce:
+        _allreduce_blob(field, blob)
     params = dict(field.named_parameters())
     # bottleneck layer: its gradients come from G = dY_mid^T h7 (linear in the blob, so after the all-reduce)
     ops.wgrad_finish(blob, params["field_output_bottleneck.net.weight"], params["field_output_bottleneck.net.bias"],
@@ -316,8 +326,10 @@ class TrainStep:
 
     The backward is replayed from ops.Tape (the same Function.backward kernels torch.autograd would call, in the same
     order, on one thread and one stream); autograd=True runs it through torch.autograd instead (A/B tests).
-    graph=True captures the whole step (forward, backward, all-reduce, optimizer) in a CUDA graph after 3 eager steps;
-    inputs are copied into static buffers and the step is one cudaGraphLaunch."""
+    graph=True captures the whole step (forward, backward, optimizer) in a CUDA graph after 3 eager steps; inputs are
+    copied into static buffers and the step is one cudaGraphLaunch.  With world_size > 1 the step is TWO graphs around the
+    one collective -- [forward + losses + backward] -> eager NCCL all-reduce of the gradient blob -> [finish + unpack +
+    RAdam + re-pack] -- so that NCCL never runs inside a capture."""
 
     def __init__(self, model, world_size: int = 1, lr: float = 1e-3, lr_final: float = 0.0, max_steps: int = 0,
                  graph: bool = False, torch_optimizer: bool = False, autograd: bool = False) -> None:
@@ -337,7 +349,8 @@ class TrainStep:
         self.steps_done = 0
         self._one = None
 
-    def _forward_backward_tape(self, ray_bundle, image: Tensor) -> Tensor:
+    def _forward_backward_tape(self, ray_bundle, image: Tensor, flush: bool = True) -> Tensor:
+        """flush=False leaves the un-reduced gradient blob on the field (field._grad_blob) for finish_step()."""
         field = self.model.field
         if not self.model.training:
             raise RuntimeError("TrainStep needs the model in training mode")
@@ -356,9 +369,22 @@ class TrainStep:
             finally:
                 ops.TAPE = None
                 tape.records.clear()
-            _flush_grads(field)
+            if flush:
+                _flush_grads(field)
         self.last_outputs = out
         return total
+
+    def allreduce_grads(self) -> None:
+        """The step's one collective, on the blob _forward_backward_tape(flush=False) left behind (no-op at world_size 1)."""
+        field = self.model.field
+        if field.dp_world_size > 1 and field._grad_blob is not None:
+            _allreduce_blob(field, field._grad_blob)
+
+    def finish_step(self) -> None:
+        """Second half of a split step: reduced blob -> flat gradient vector -> fused RAdam + re-pack."""
+        with torch.no_grad():
+            _flush_grads(self.model.field, allreduce=False)
+        self.opt.step()
 
     def _eager(self, ray_bundle, image: Tensor) -> Tensor:
         if self.autograd or not self.fused:
@@ -388,16 +414,32 @@ class TrainStep:
                   "a": ray_bundle.pixel_area.clone(), "img": image.clone()}
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            split = self.model.field.dp_world_size > 1
             with torch.cuda.graph(g):
                 bundle = RayBundle(origins=st["o"], directions=st["d"], pixel_area=st["a"])
-                st["loss"] = self._eager(bundle, st["img"])
+                if split:
+                    st["loss"] = self._forward_backward_tape(bundle, st["img"], flush=False)
+                else:
+                    st["loss"] = self._eager(bundle, st["img"])
+            if split:                          # (the blob is a persistent buffer of the field: both graphs address it)
+                st["blob"] = self.model.field._grad_blob
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g.pool()):
+                    self.finish_step()
+                st["finish"] = g2
             self.graph, self.static = g, st
-            g.replay()                         # capture does not execute: run the step it recorded on this batch
-            return st["loss"]
+            return self._replay()              # capture does not execute: run the step it recorded on this batch
         st = self.static
         st["o"].copy_(ray_bundle.origins, non_blocking=True)
         st["d"].copy_(ray_bundle.directions, non_blocking=True)
         st["a"].copy_(ray_bundle.pixel_area, non_blocking=True)
         st["img"].copy_(image, non_blocking=True)
+        return self._replay()
+
+    def _replay(self) -> Tensor:
+        st = self.static
         self.graph.replay()
+        if "finish" in st:
+            _allreduce_blob(self.model.field, st["blob"])
+            st["finish"].replay()
         return st["loss"]
