@@ -66,7 +66,7 @@ struct BBarriers {
                               // may lag the issuer by up to two steps without aliasing the phase parity
   uint64_t a_free[2];         // BACKWARD: the stash warps have read the dY operand that lived in accumulator buffer b
   uint64_t seed_ready;
-  uint64_t acc_full[2];
+  uint64_t acc_full[4];       // [accumulator buffer][output half]: wide steps commit columns 0-127 before 128-255
   uint32_t tmem_slot;
 };
 
@@ -262,8 +262,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
       for (int i = 0; i < 8; ++i) mbar_init(&bars.act_ready[i], TILE);
       for (int i = 0; i < 2; ++i) mbar_init(&bars.a_free[i], 4);
       mbar_init(&bars.seed_ready, TILE);
-      mbar_init(&bars.acc_full[0], 1);
-      mbar_init(&bars.acc_full[1], 1);
+      for (int i = 0; i < 4; ++i) mbar_init(&bars.acc_full[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -353,12 +352,20 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
         tc_fence_after();
         return s_w + (uint32_t)stage * W_STAGE_BYTES;
       };
-      auto ring_release = [&]() {
-        mma_commit(&bars.w_empty[stage]);
+      auto ring_advance = [&]() -> int {     // -> the slot just consumed (to be released with ring_release_slot)
+        const int s_ = stage;
         if (++stage == NWS) {
           stage = 0;
           wphase ^= 1;
         }
+        return s_;
+      };
+      auto ring_release_slot = [&](int s_) { mma_commit(&bars.w_empty[s_]); };
+      auto ring_release = [&]() { ring_release_slot(ring_advance()); };
+      // one commit for both output halves (steps that are not split)
+      auto commit_acc = [&]() {
+        mma_commit(&bars.acc_full[2 * buf]);
+        mma_commit(&bars.acc_full[2 * buf + 1]);
       };
       auto wait_act = [&](int g) {
         const int i = (buf ^ 1) * 4 + g;     // handed over by the previous step, which accumulated into the other buffer
@@ -402,6 +409,45 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
           acc = true;
         }
       };
+      constexpr uint32_t HALF_B = 128u * 128u;   // bytes of 128 weight rows (one output half) inside a [256][64] K-block image
+      // NORMALS only (measured, 30 launches alternating between two builds: normals 1.97 -> 1.88 ms, but BACKWARD 2.98 ->
+      // 3.09 ms, + area 3.50 -> 3.64 ms: there the stash warps' TMEM reads and stores already pace the epilogue, and the
+      // early first half only adds issue work).
+      constexpr bool SPLIT = KIND == KIND_NORMALS;
+      // A wide step (K = 256 from the four handed-over groups, N = 256) as two N = 128 accumulations (columns 0-127 | 128-255,
+      // weight rows 0-127 | 128-255 of every K-block image), the first COMMITTED while the tensor pipe still works on the
+      // second -- the epilogue converts groups 0, 1 (and the next step's first K-blocks start) two K-block times earlier;
+      // same tensor time as N = 256 (the forward kernel's form, field_fwd.cu).  Issue order:
+      //   [kb0: h0 h1] [kb1: h0 h1] [kb2: h0] [kb3: h0] before_h0() commit(h0) [kb2: h1] [kb3: h1] before_h1() commit(h1)
+      // before_h0 / before_h1: extra MMAs of the step that belong in front of the first / second commit.
+      auto issue_wide = [&](auto&& before_h0, auto&& before_h1) {
+        const uint32_t tm = tmem + (uint32_t)buf * 256;
+        bool acc0 = false, acc1 = false;
+        for (int g = 0; g < 2; ++g) {
+          wait_act(g);
+          const uint32_t w = ring_wait();
+          issue_act(g, w, ID128, tm, acc0);
+          issue_act(g, w + HALF_B, ID128, tm + 128, acc1);
+          ring_release();
+        }
+        wait_act(2);
+        const uint32_t w2 = ring_wait();
+        const int s2 = ring_advance();
+        issue_act(2, w2, ID128, tm, acc0);
+        wait_act(3);
+        const uint32_t w3 = ring_wait();
+        const int s3 = ring_advance();
+        issue_act(3, w3, ID128, tm, acc0);
+        before_h0(acc0);
+        mma_commit(&bars.acc_full[2 * buf]);
+        issue_act(2, w2 + HALF_B, ID128, tm + 128, acc1);
+        ring_release_slot(s2);
+        issue_act(3, w3 + HALF_B, ID128, tm + 128, acc1);
+        ring_release_slot(s3);
+        before_h1(acc1);
+        mma_commit(&bars.acc_full[2 * buf + 1]);
+      };
+      auto nothing = [](bool&) {};
       constexpr uint32_t ENC4_COL = TS ? 128u : 0u;   // layer-4 encoding part: columns of the other buffer (TS: A sits in 0..127)
       for (int it = 0; it < n_my_tiles; ++it) {
         bool acc;
@@ -414,7 +460,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
           uint32_t w = ring_wait();
           issue_kb(s_seed, w, 1, ID128, tmem + (uint32_t)buf * 256, acc);
           ring_release();
-          mma_commit(&bars.acc_full[buf]);
+          commit_acc();
           buf ^= 1;
           // S1: d bottleneck = dY_mid (K=128) x Wmid[:,34:]^T, N = 256
           acc = false;
@@ -425,7 +471,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
             issue_act(g, w, ID256, tmem + (uint32_t)buf * 256, acc);
             ring_release();
           }
-          mma_commit(&bars.acc_full[buf]);
+          commit_acc();
           buf ^= 1;
           // S2: d emb = dY_bott (K=256) x Wbott^T + dY_heads (K=16, seed block columns 16-31) x Wheads^T
           acc = false;
@@ -439,29 +485,36 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
           w = ring_wait();
           issue_kb(s_seed + 32, w, 1, ID256, tmem + (uint32_t)buf * 256, acc);
           ring_release();
-          mma_commit(&bars.acc_full[buf]);
+          commit_acc();
           buf ^= 1;
         }
         // base layers 7..1: d h_{l-1} = dY_l x W_l^T  (layer 4: hidden part, then the encoding part)
         for (int l = 7; l >= 1; --l) {
-          acc = false;
           wait_a_free();
-          for (int g = 0; g < 4; ++g) {
-            wait_act(g);
-            const uint32_t w = ring_wait();
-            issue_act(g, w, ID256, tmem + (uint32_t)buf * 256, acc);
-            ring_release();
-          }
-          if (l == 4 && with_enc) {
-            // every act_ready of the previous epilogue has been observed => it no longer reads buf^1
-            bool acc_e = false;
+          if (!SPLIT || (l == 4 && with_enc)) {
+            // Not split (layer 4 with its encoding part): the encoding part of layer 4 (four more weight chunks, N = 128 into the OTHER buffer) has to be
+            // complete before the epilogue hands group 0 over (the next step then starts to overwrite that buffer), and
+            // the round-robin weight ring cannot deliver its fourth chunk while two slots of the wide step are still held.
+            // (every act_ready of the previous epilogue has been observed => it no longer reads buf^1)
+            bool acc = false;
             for (int g = 0; g < 4; ++g) {
+              wait_act(g);
               const uint32_t w = ring_wait();
-              issue_act(g, w, ID128, tmem + (uint32_t)(buf ^ 1) * 256 + ENC4_COL, acc_e);
+              issue_act(g, w, ID256, tmem + (uint32_t)buf * 256, acc);
               ring_release();
             }
+            if (l == 4 && with_enc) {
+              bool acc_e = false;
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t w = ring_wait();
+                issue_act(g, w, ID128, tmem + (uint32_t)(buf ^ 1) * 256 + ENC4_COL, acc_e);
+                ring_release();
+              }
+            }
+            commit_acc();
+          } else {
+            issue_wide(nothing, nothing);
           }
-          mma_commit(&bars.acc_full[buf]);
           buf ^= 1;
         }
         if (!with_enc) {
@@ -479,7 +532,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
             issue_act(g, w, ID128, tmem + (uint32_t)buf * 256, acc);
             ring_release();
           }
-          mma_commit(&bars.acc_full[buf]);
+          commit_acc();
           buf ^= 1;
         }
       }
@@ -497,10 +550,15 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
       const bool valid = pt < n_points;
       uint8_t* const dyt = (KIND == KIND_BACKWARD) ? p.dy_stash + (size_t)tile * DY_BLOCKS * BLOCK_BYTES : nullptr;
       auto dblk = [&](int b) -> uint8_t* { return dyt + (size_t)b * BLOCK_BYTES; };
-      auto wait_acc = [&]() {
-        mbar_wait(&bars.acc_full[buf], (af_phase >> buf) & 1u);
-        af_phase ^= (1u << buf);
+      auto wait_half = [&](int h) {          // output half h of the step accumulating into `buf` is complete
+        const int i = 2 * buf + h;
+        mbar_wait(&bars.acc_full[i], (af_phase >> i) & 1u);
+        af_phase ^= (1u << i);
         tc_fence_after();
+      };
+      auto wait_acc = [&]() {                // the whole accumulator (steps that are not split commit both halves at once)
+        wait_half(0);
+        wait_half(1);
       };
       // one 64-column group of a step: convert and hand to the issuer (and, BACKWARD, to the stash warps): act_ready[buf][g]
       auto convert = [&](auto mask_c, int g, uint2 mbits, uint8_t* stash_blk) {
@@ -631,7 +689,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
       for (int l = first; l >= 1; --l) {
         uint2 mk[4];
         load_masks(l - 1, 4, mk);       // this step masks with h_{l-1}
-        wait_acc();
+        wait_half(0);                   // wide step: columns 0-127 first (groups 0, 1), see issue_wide
         if (l == 4 && with_enc) {
           // encoding part of layer 4 (other accumulator, columns 0..111): consume before the hidden part
           const uint32_t e0 = mask_wait();
@@ -648,8 +706,10 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
           mask_release();
           mask_release();
         }
-        for (int g = 0; g < 4; ++g)   // output = dY_{l-1}: stash block DY_H + 4 (l-1) + g
+        for (int g = 0; g < 4; ++g) { // output = dY_{l-1}: stash block DY_H + 4 (l-1) + g
+          if (g == 2) wait_half(1);
           convert(T_{}, g, mk[g], (KIND == KIND_BACKWARD) ? dblk(DY_H + 4 * (l - 1) + g) : nullptr);
+        }
         buf ^= 1;
       }
       if (with_enc) {
