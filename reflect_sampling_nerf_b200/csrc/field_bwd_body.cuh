@@ -85,12 +85,13 @@ __device__ __forceinline__ uint4 lds128b(uint32_t saddr) {
 }
 // Stashed ReLU bit masks (csrc/field_layout.cuh): bit i / 16 + i of word w = columns 32 w + 2 i / + 1 of the group.
 // 0xFFFF in each half of packed word i whose column was > 0 in the forward.
-// (shift bit i to the top of byte 0 and bit 16 + i to the top of byte 2, then one PRMT whose selector nibbles 0x8 / 0xA
-// replicate the sign of byte 0 / byte 2 over two bytes each)
+// (shift bit i & 7 to the top of byte 0 and bit 16 + (i & 7) to the top of byte 2 -- the same shift puts the bits of word
+// i + 8 at the top of bytes 1 and 3, so words i and i + 8 share one shifted register --, then one PRMT whose selector
+// nibbles 0x8 / 0xA (0x9 / 0xB) replicate the sign of byte 0 / byte 2 (byte 1 / byte 3) over two bytes each)
 __device__ __forceinline__ uint32_t relu_mask_word(uint32_t bits, int i) {
-  const uint32_t t = (i <= 7) ? (bits << (7 - i)) : (bits >> (i - 7));
+  const uint32_t t = bits << (7 - (i & 7));
   uint32_t m;   // (inline PTX: the __byte_perm intrinsic only honours the low three bits of each selector nibble)
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(t), "r"(0u), "r"(0xAA88u));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(t), "r"(0u), "r"((i & 8) ? 0xBB99u : 0xAA88u));
   return m;
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
