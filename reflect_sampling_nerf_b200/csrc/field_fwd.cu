@@ -58,6 +58,9 @@ constexpr int SMEM_BIAS = SMEM_BARS + 256;
 constexpr int SMEM_TOTAL = SMEM_BIAS + 2 * BIAS_SLOT_BYTES;      // 231,936 of the 232,448 a CTA may have
 constexpr int WIDE_LAYERS = 10;                                  // per tile: base 0..7, bottleneck, mid
 constexpr int NUM_THREADS = 320;          // inference launches
+#ifndef RSN_STASH_LAG_FWD
+#define RSN_STASH_LAG_FWD 0
+#endif
 constexpr int NUM_THREADS_TRAIN = 448;    // + the four stash warps
 
 // (Biases never live in __constant__ memory: every layer's fp32 bias reaches the epilogue through a two-slot shared-memory
@@ -881,9 +884,16 @@ __global__ void __launch_bounds__(TRAIN ? NUM_THREADS_TRAIN : NUM_THREADS, 1) fi
         uint8_t* const st = p.stash + (size_t)tile_of(it) * STASH_TILE_BYTES;
         uint2* const masks = reinterpret_cast<uint2*>(st + STASH_MASK_OFF);
         // one layer use with NG stashed groups: mask layer ml, stash blocks blk0 .. blk0 + NG - 1
+        // RSN_STASH_LAG_FWD = k: group g is read and stored once the epilogue has handed group min(g + k, last) over
+        // (0: right behind its own hand-over).  The operand stays valid until the issuer re-uses the buffer two layers
+        // later (a_free).  Measured over 30 sustained launches: k = 0 3.07, 1 3.09, 2 2.98-3.05, 3 3.2 ms -- no lag here
+        // (the mask arithmetic makes a layer's stash work longer than the stretch it would be deferred into); the
+        // backward chain, whose stash warps only copy, gains 5 % from k = 4 (field_bwd_body.cuh).
         auto stash_layer = [&](int ng, int ml, int blk0) {
+          int waited = 0;
           for (int g = 0; g < ng; ++g) {
-            wait_group(g);
+            const int need = min(g + RSN_STASH_LAG_FWD, ng - 1);
+            while (waited <= need) wait_group(waited++);
             uint32_t a[32];
             tmem_ld32(tlane + (uint32_t)sbuf * 256 + (uint32_t)g * 32u, a);
             tmem_ld_wait();
