@@ -12,6 +12,9 @@ namespace {
 using namespace umma;
 using namespace rsnf;
 
+#ifndef RSN_BWD_SPLIT
+#define RSN_BWD_SPLIT 0
+#endif
 #ifndef RSN_STASH_LAG_BWD
 #define RSN_STASH_LAG_BWD 4
 #endif
@@ -417,7 +420,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& p) {
       // NORMALS only (measured, 30 launches alternating between two builds: normals 1.97 -> 1.88 ms, but BACKWARD 2.98 ->
       // 3.09 ms, + area 3.50 -> 3.64 ms: there the stash warps' TMEM reads and stores already pace the epilogue, and the
       // early first half only adds issue work).
-      constexpr bool SPLIT = KIND == KIND_NORMALS;
+      constexpr bool SPLIT = KIND == KIND_NORMALS || RSN_BWD_SPLIT;
       // A wide step (K = 256 from the four handed-over groups, N = 256) as two N = 128 accumulations (columns 0-127 | 128-255,
       // weight rows 0-127 | 128-255 of every K-block image), the first COMMITTED while the tensor pipe still works on the
       // second -- the epilogue converts groups 0, 1 (and the next step's first K-blocks start) two K-block times earlier;
