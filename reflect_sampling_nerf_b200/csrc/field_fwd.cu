@@ -58,8 +58,11 @@ constexpr int SMEM_BIAS = SMEM_BARS + 256;
 constexpr int SMEM_TOTAL = SMEM_BIAS + 2 * BIAS_SLOT_BYTES;      // 231,936 of the 232,448 a CTA may have
 constexpr int WIDE_LAYERS = 10;                                  // per tile: base 0..7, bottleneck, mid
 constexpr int NUM_THREADS = 320;          // inference launches
+#ifndef RSN_FWD_TRAIN_SPLIT
+#define RSN_FWD_TRAIN_SPLIT 0
+#endif
 #ifndef RSN_STASH_LAG_FWD
-#define RSN_STASH_LAG_FWD 0
+#define RSN_STASH_LAG_FWD 4
 #endif
 constexpr int NUM_THREADS_TRAIN = 448;    // + the four stash warps
 
@@ -555,7 +558,17 @@ __global__ void __launch_bounds__(TRAIN ? NUM_THREADS_TRAIN : NUM_THREADS, 1) fi
             ring_release();
             if (l == 0) commit(&bars.acc_full[2 * buf + 1]);
           }
-          if (l > 0) {
+          if (l > 0 && TRAIN && !RSN_FWD_TRAIN_SPLIT) {
+            for (int g = 0; g < 4; ++g) {
+              wait_act(g);
+              if (g == 3) request_bias(it * WIDE_LAYERS + l + 1);
+              const uint32_t w = ring_wait();
+              issue_act(g, w, ID256, tm, a_tm, acc);
+              ring_release();
+            }
+            commit(&bars.acc_full[2 * buf]);
+            commit(&bars.acc_full[2 * buf + 1]);
+          } else if (l > 0) {
             for (int g = 0; g < 2; ++g) {
               wait_act(g);
               RSN_TRACE(tr, 1000 + 10 * l + g);
@@ -885,10 +898,12 @@ __global__ void __launch_bounds__(TRAIN ? NUM_THREADS_TRAIN : NUM_THREADS, 1) fi
         uint2* const masks = reinterpret_cast<uint2*>(st + STASH_MASK_OFF);
         // one layer use with NG stashed groups: mask layer ml, stash blocks blk0 .. blk0 + NG - 1
         // RSN_STASH_LAG_FWD = k: group g is read and stored once the epilogue has handed group min(g + k, last) over
-        // (0: right behind its own hand-over).  The operand stays valid until the issuer re-uses the buffer two layers
-        // later (a_free).  Measured over 30 sustained launches: k = 0 3.07, 1 3.09, 2 2.98-3.05, 3 3.2 ms -- no lag here
-        // (the mask arithmetic makes a layer's stash work longer than the stretch it would be deferred into); the
-        // backward chain, whose stash warps only copy, gains 5 % from k = 4 (field_bwd_body.cuh).
+        // (0: right behind its own hand-over; 4: the whole layer after its last hand-over, i.e. in the stretch in which the
+        // epilogue warps of the same SMSPs wait for the next layer's accumulator).  The operand stays valid until the issuer
+        // re-uses the buffer two layers later (a_free).  Measured over 30 sustained launches, alternating builds: with the
+        // two-halves commit (RSN_FWD_TRAIN_SPLIT, which shortens that stretch) k = 0 / 1 / 2 / 3: 3.07 / 3.09 / 2.98-3.05 /
+        // 3.2 ms; with plain N = 256 layers k = 0 / 2 / 3 / 4: 3.06 / 2.95 / 2.94 / 2.91 ms against 3.01 ms for the previous
+        // default (split, k = 0).  Training therefore runs N = 256 layers with k = 4; inference keeps the split.
         auto stash_layer = [&](int ng, int ml, int blk0) {
           int waited = 0;
           for (int g = 0; g < ng; ++g) {
