@@ -24,6 +24,7 @@
 //               issuer re-uses the accumulator buffer two layers later, which waits for a_free), derive the ReLU bit masks
 //               and write the row straight to the activation stash with coalesced st.global.v4 (chunk-major block image,
 //               field_layout.cuh) -- no shared-memory staging, no proxy fence, nothing on the layer-critical path
+//               (a layer's groups after its LAST hand-over, RSN_STASH_LAG_FWD; training layers are plain N = 256 steps)
 // The two 256-column TMEM accumulator buffers alternate by layer, and every layer's epilogue publishes
 // its output per 64-column group (mbarrier act_ready[g]) so that the next layer's K-block g is issued as
 // soon as that group is written: MMA of layer l+1 overlaps the epilogue of layer l.
