@@ -83,12 +83,20 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                self.power_limit_w = nv.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            except Exception:  # noqa: BLE001
+                self.power_limit_w = None
             while not self.stop_flag.is_set():
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, mx, int(reasons)))
-                self.stop_flag.wait(0.1)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:  # noqa: BLE001
+                    pw = None
+                self.samples.append((sm, mx, int(reasons), pw))
+                self.stop_flag.wait(0.05)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
@@ -96,8 +104,10 @@ class ClockSampler(threading.Thread):
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
         sm = sorted(s[0] for s in self.samples)
         reasons = sorted({name for s in self.samples for name, b in bits.items() if s[2] & b})
+        pw = sorted(s[3] for s in self.samples if s[3] is not None)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.samples[0][1] if self.samples else None,
-                "reasons": reasons, "samples": len(self.samples), "source": "nvml", "error": self.err}
+                "reasons": reasons, "samples": len(self.samples), "power_w": pw[len(pw) // 2] if pw else None,
+                "power_limit_w": getattr(self, "power_limit_w", None), "power_note": "NVML board power, ~1 s average", "source": "nvml", "error": self.err}
 
 
 # ------------------------------------------------------------------------------------------ oracle arms
