@@ -138,6 +138,43 @@ def test_flat_gradient_allreduce_world_size_2(tmp_path):
     assert all(torch.load(os.path.join(tmp_path, f"ok{r}.pt")) for r in range(2))
 
 
+def _split_flush_worker(rank, world, port, out_dir):
+    """The two halves TrainStep's split CUDA graphs are built from: reduce the blob, then flush WITHOUT a collective."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from reflect_sampling_nerf_b200.train_path import _allreduce_blob, _flush_grads
+    torch.manual_seed(0)
+    _, _, total = ops.wgrad_layout()
+    base = torch.randn(total)
+    grads = []
+    for split in (False, True):
+        torch.manual_seed(1)                                  # same parameters: the bottleneck layer's gradients depend on them
+        field = ReflectSamplingNeRFNerfField()
+        field.dp_world_size = world
+        field._grad_blob = base * float(rank + 1)
+        if split:
+            _allreduce_blob(field, field._grad_blob)          # (gloo: SUM + scale; NCCL averages inside the collective)
+            _flush_grads(field, allreduce=False)
+        else:
+            _flush_grads(field)
+        grads.append(torch.cat([p.grad.reshape(-1) for p in field.parameters() if p.grad is not None]))
+    # a flush with allreduce=False on an un-reduced blob must NOT communicate: rank-local values stay rank-local
+    field = ReflectSamplingNeRFNerfField()
+    field.dp_world_size = world
+    field._grad_blob = torch.full((total,), float(rank + 1))
+    _flush_grads(field, allreduce=False)
+    g = field.mlp_base.layers[3].weight.grad
+    torch.save({"same": bool(torch.equal(grads[0], grads[1])), "local": bool(torch.allclose(g, torch.full_like(g, float(rank + 1))))},
+               os.path.join(out_dir, f"s{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_split_flush_equals_the_one_call_flush_world_size_2(tmp_path):
+    mp.spawn(_split_flush_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    res = [torch.load(os.path.join(tmp_path, f"s{r}.pt")) for r in range(2)]
+    assert all(r["same"] and r["local"] for r in res), res
+
+
 def _bcast_worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
