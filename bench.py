@@ -227,7 +227,12 @@ def run_b200(args):
                  "buf": [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]}
 
     def one_step(e2e: bool):
-        if e2e:
+        if e2e and train:
+            # the public API takes the pinned HOST batch as it is: TrainStep.step copies it to the device (into the static
+            # input buffers of its CUDA graph once the step is captured) inside this timed call
+            bundle = RayBundle(origins=host[0], directions=host[1], pixel_area=host[2])
+            bi = host[3]
+        elif e2e:
             bo, bd, ba, bi = [t.to(dev, non_blocking=True) for t in host]
             bundle = RayBundle(origins=bo, directions=bd, pixel_area=ba)
         else:

@@ -403,7 +403,16 @@ class TrainStep:
         return loss
 
     def step(self, ray_bundle, image: Tensor) -> Tensor:
+        """ray_bundle / image may live on the device or in (pinned) HOST memory -- the form a CPU data loader hands over:
+        host batches are copied to the device here; once the step is a CUDA graph, straight into its static input buffers."""
         self.steps_done += 1
+        if not ray_bundle.origins.is_cuda and not (self.graph_requested and self.graph is not None):
+            from .rays import RayBundle
+            dev = next(self.model.field.parameters()).device
+            ray_bundle = RayBundle(origins=ray_bundle.origins.to(dev, non_blocking=True),
+                                   directions=ray_bundle.directions.to(dev, non_blocking=True),
+                                   pixel_area=ray_bundle.pixel_area.to(dev, non_blocking=True))
+            image = image.to(dev, non_blocking=True)
         if not self.graph_requested:
             return self._eager(ray_bundle, image)
         if self.graph is None:

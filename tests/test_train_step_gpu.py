@@ -111,22 +111,28 @@ def test_train_step_is_sync_free_and_graph_replay_matches_eager():
     jit = dict(uniform=torch.rand(n, 33, generator=g), pdf=torch.rand(n, 33, generator=g),
                reciprocal=torch.rand(n, 17, generator=g), reflect_pdf=torch.rand(n, 17, generator=g))
     results = {}
-    for mode in ("eager", "graph"):
+    host = [t.cpu().pin_memory() for t in (o, d, pa, img)]          # (c) the same batch handed over in pinned HOST memory
+    for mode in ("eager", "graph", "graph_host"):
         model = make()
         model.set_jitter(**{k: v.cuda() for k, v in jit.items()})
-        stepper = TrainStep(model, graph=(mode == "graph"))
+        stepper = TrainStep(model, graph=(mode != "eager"))
         losses = []
         for i in range(7):
             if mode == "eager" and i == 5:
                 torch.cuda.synchronize()
                 torch.cuda.set_sync_debug_mode("error")
             try:
-                losses.append(stepper.step(RayBundle(origins=o, directions=d, pixel_area=pa), img).clone())
+                if mode == "graph_host":
+                    losses.append(stepper.step(RayBundle(origins=host[0], directions=host[1], pixel_area=host[2]), host[3]).clone())
+                else:
+                    losses.append(stepper.step(RayBundle(origins=o, directions=d, pixel_area=pa), img).clone())
             finally:
                 torch.cuda.set_sync_debug_mode("default")
         torch.cuda.synchronize()
-        assert (stepper.graph is not None) == (mode == "graph")
+        assert (stepper.graph is not None) == (mode != "eager")
         results[mode] = (torch.stack(losses).cpu(), model.field.mlp_base.layers[3].weight.detach().cpu().clone())
+    torch.testing.assert_close(results["graph_host"][0], results["graph"][0], rtol=2e-3, atol=1e-5)
+    torch.testing.assert_close(results["graph_host"][1], results["graph"][1], rtol=0, atol=2e-4)
     le, lg = results["eager"][0], results["graph"][0]
     assert bool((le[1:] < le[:-1]).sum() >= 4), le.tolist()          # the loss goes down on a fixed batch
     torch.testing.assert_close(lg, le, rtol=2e-3, atol=1e-5)         # same step; fp32 atomics order differs run to run
